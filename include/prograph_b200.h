@@ -1,0 +1,216 @@
+/* prograph_b200.h -- C ABI of the B200-native graph-construction path.
+ *
+ * The reference (acmater/prograph) is pure Python and has no FFI; its plug-in seam
+ * is the distance-function protocol  fn(X[N,D], Y[M,D], similarity=False) -> (M,N)
+ * (prograph/distance/hamming.py:8-39, minkowski.py:8-41) consumed by
+ * Prograph.build_graph / calc_neighbours / neighbourhood / indexing
+ * (prograph/prograph.py:254-343, 526-588, 656-765).  The entry points below are what a
+ * ctypes binding on the reference side calls instead of the torch broadcasting
+ * expressions; each one names the reference lines it replaces.  INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *   - every function returns PG_OK (0) or a negative pgStatus; pg_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns
+ *     every buffer, the library allocates nothing that outlives a call except where a
+ *     workspace pointer + size is passed in explicitly;
+ *   - every launch goes to the cudaStream_t passed as `stream` (a void*; NULL = legacy
+ *     default stream); calls are asynchronous unless stated otherwise;
+ *   - row indices are 64-bit, distances of the Hamming family are 32-bit inside the
+ *     library and widened to the reference's dtypes (int64 / float32) on output.
+ */
+#ifndef PROGRAPH_B200_H
+#define PROGRAPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PG_OK = 0,
+  PG_ERR_INVALID = -1,      /* bad argument (maps to ValueError)                    */
+  PG_ERR_UNSUPPORTED = -2,  /* configuration outside the fused kernels (host falls
+                               back to the tile kernels, never to the CPU)          */
+  PG_ERR_CUDA = -3,         /* CUDA runtime error (RuntimeError)                    */
+  PG_ERR_RANGE = -4         /* a token does not fit the requested bit planes        */
+} pgStatus;
+
+typedef enum {
+  PG_U8 = 0, PG_I16 = 1, PG_I32 = 2, PG_I64 = 3, PG_F16 = 4, PG_F32 = 5, PG_F64 = 6
+} pgDtype;
+
+/* comparison opcodes, python's operator.{lt,le,eq,ne,ge,gt} (prograph.py:665,734-736) */
+typedef enum { PG_LT = 0, PG_LE = 1, PG_EQ = 2, PG_NE = 3, PG_GE = 4, PG_GT = 5 } pgCmp;
+
+/* how a Hamming distance d is written out */
+typedef enum {
+  PG_W_I64 = 0,   /* d as int64                      (hamming.py:34)                */
+  PG_W_SIM_F32 = 1,/* 1/(1+d) as float32             (hamming.py:37-38)             */
+  PG_W_I32 = 2    /* d as int32 (library-internal tiles)                            */
+} pgWeight;
+
+int         pg_version(void);
+const char* pg_last_error(void);
+/* sm count, compute capability and resident-CTA figure used for grid sizing */
+int pg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * Packed token table.  Replaces the fp16 staging copy of prograph.py:726 for integer
+ * tokens: residue l of row n is spread over `planes` bit planes; word w of plane p
+ * holds bit p of residues 32w..32w+31.  Layout [rows_padded][planes][words] uint32,
+ * rows_padded = pg_packed_rows(N), words = pg_packed_words(L); pad rows/residues are 0
+ * (the reference pads with token 0, distance/utils.py:32-38).
+ * ------------------------------------------------------------------------- */
+int     pg_packed_words(int L);             /* 1,2,4,8 or a multiple of 8            */
+int64_t pg_packed_rows(int64_t N);          /* N rounded up to the stream tile       */
+size_t  pg_packed_bytes(int64_t N, int L, int planes);
+/* tokens: [N][L] of `dtype` with row stride ld (elements).  Lw = words of the output
+ * (>= pg_packed_words(L); lets two operands of different width share one width).
+ * *flag (device int, caller-zeroed) is set to 1 if a token is negative, non-integral
+ * or >= 2^planes.  */
+int pg_pack_tokens(const void* tokens, int dtype, int64_t N, int L, int64_t ld,
+                   uint32_t* packed, int planes, int words, int* flag, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused Hamming sweeps: "own" rows live in registers, the "stream" table is swept
+ * through shared memory; the (own x stream) distance matrix never reaches HBM.
+ * Replaces hamming.py:34 + the consumer that follows it in prograph.py.
+ * ------------------------------------------------------------------------- */
+
+/* size in bytes of the workspace the fused sweeps need (split partials) */
+size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1);
+
+/* kNN (prograph.py:755-765: sort each row, keep sorted positions drop..drop+k-1).
+ * For every own row r in [row0,row0+rows): the first (drop+k) stream rows in
+ * (distance, index) order; positions [drop, drop+k) are written:
+ *   out_idx[r*k + j]  int64,  out_w[r*k + j] per `weight`.
+ * If stream_rows < drop+k the tail is filled with idx = -1.  */
+int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                   const uint32_t* stream_tab, int64_t stream_rows,
+                   int planes, int words, int k, int drop, int weight,
+                   int64_t* out_idx, void* out_w,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* epsilon graph, pass 1 (prograph.py:731-736): per own row, the number of stream rows
+ * whose distance d has bit d set in `lut` (a host array of (L+32)/32 words: the
+ * truth table of  comp(d, eps) & (d > 0)  -- or any other predicate of d -- evaluated
+ * by the caller for d = 0..L).  counts[r] int64, r relative to row0.  */
+int pg_hamming_eps_count(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                         const uint32_t* stream_tab, int64_t stream_rows,
+                         int planes, int words, const uint32_t* lut_host, int lut_words,
+                         int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* epsilon graph, pass 2 (prograph.py:736-739 + prod_neighbours :626-654): writes, for
+ * row r, its neighbours in ascending index order at indptr[r]..indptr[r+1]:
+ *   out_idx int64, out_w per `weight`.  indptr is the exclusive scan of `counts`
+ * (pg_exclusive_scan_i64).  The workspace must be the one pass 1 filled.  */
+int pg_hamming_eps_fill(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                        const uint32_t* stream_tab, int64_t stream_rows,
+                        int planes, int words, const uint32_t* lut_host, int lut_words,
+                        const int64_t* indptr, int weight, int64_t* out_idx, void* out_w,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* materialised distance tile (hamming.py:34-38): out[m*ld + n] for query rows
+ * m in [q0,q0+qrows) of `queries` against all `data_rows` rows of `data`;
+ * `weight` picks int64 / float32-similarity / int32.  */
+int pg_hamming_tile(const uint32_t* data, int64_t data_rows,
+                    const uint32_t* queries, int64_t query_rows, int64_t q0, int64_t qrows,
+                    int planes, int words, int weight, void* out, int64_t ld, void* stream);
+
+/* out[i] = sum_{j<i} in[j], out[n] = total (n+1 outputs); int64; used for indptr */
+int pg_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Element-wise metric tiles (float / generic values).
+ * ------------------------------------------------------------------------- */
+/* minkowski.py:36-40.  X [N][D], Y [M][D] of `dtype` in {PG_F16, PG_F32, PG_F64, PG_I64};
+ * out (rows q0..q0+qrows of Y) x N, dtype F16 for F16 input, F32 for F32/I64, F64 for
+ * F64; every rounding step of the reference chain is reproduced.  */
+int pg_minkowski_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_t q0, int64_t qrows,
+                      int D, int dtype, double p, int similarity, void* out, int64_t ld, void* stream);
+/* hamming.py:34 on arbitrary numeric values (x != y counted per component, IEEE: NaN
+ * differs from everything): out int64 (or float32 similarity). */
+int pg_hamming_values_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_t q0, int64_t qrows,
+                           int D, int dtype, int weight, void* out, int64_t ld, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Consumers of a materialised (rows x N) tile: used for Minkowski, for user supplied
+ * distance callables (README.md:48) and for single-row queries.
+ * ------------------------------------------------------------------------- */
+/* stable top-k of each tile row (prograph.py:757-762): positions [drop, drop+k) of the
+ * row sorted by (value, index) ascending, or descending with NaN first when
+ * `descending` (torch.sort semantics).  out_idx int64 [rows][k], out_val tile dtype. */
+int pg_tile_topk(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld,
+                 int k, int drop, int descending, int64_t* out_idx, void* out_val, void* stream);
+
+/* threshold test of prograph.py:734-736 / :544 on a tile:
+ *   keep = cmp(v, eps)            swap = 0
+ *   keep = cmp(eps, v)            swap = 1   (similarity: operands swapped, :734)
+ *   and, per `guard`: 0 none, 1  v > 0  (:736),  2  v < 1  (:734).
+ * eps is rounded to the tile dtype first (a python scalar is compared in the tensor's
+ * dtype).  Pass 1 writes counts[r]; pass 2 writes ascending column indices and the
+ * values at indptr[r].. ; `tile` may also be a uint8 mask (dtype PG_U8, cmp ignored). */
+int pg_tile_threshold_count(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld,
+                            int cmp, double eps, int swap, int guard, int64_t* counts, void* stream);
+int pg_tile_threshold_fill(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld,
+                           int cmp, double eps, int swap, int guard, const int64_t* indptr,
+                           int64_t* out_idx, void* out_val, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Mutation masks and index selections (prograph.py:254-343, 349-368, 488-505).
+ * All work on the packed table; `ref` is one packed row (planes*words words).
+ * ------------------------------------------------------------------------- */
+/* mut[n][w] = OR_p (table[n][p][w] ^ ref[p][w]): bit l set <=> residue l differs from
+ * the reference row (boolean_mutant_array, :488-492, as a bit mask). */
+int pg_mutant_bits(const uint32_t* table, int64_t N, int planes, int words,
+                   const uint32_t* ref, uint32_t* mut, void* stream);
+/* the same as the reference's (N, L) bool array (one byte per residue) */
+int pg_mutant_bool(const uint32_t* table, int64_t N, int planes, int words, int L,
+                   const uint32_t* ref, uint8_t* out, void* stream);
+/* any_bits[w] = OR_n mut[n][w]  (calc_mutated_positions, :494-505) */
+int pg_mutant_any(const uint32_t* mut, int64_t N, int words, uint32_t* any_bits, void* stream);
+/* row selection: flag[n] = dist_ok & pos_ok with
+ *   dist_ok = dist_lut == NULL or bit popc(mut[n]) of dist_lut set       (:300-308)
+ *   pos_ok  = pos_mode 0: true
+ *             1 ("or") : (mut & inside) != 0 and (mut & outside) == 0    (:316-325)
+ *             2 ("and"): (mut & inside) == inside and (mut & outside) == 0
+ *             3        : (mut & inside) == 0    (get_mutated_positions, :362-365;
+ *                        `inside` then holds the positions that must stay constant)
+ * `outside` = the positions that must be unchanged (the reference walks the positions of
+ * the reference sequence's own length that are not selected, :316,:322-324).
+ * dist_lut_host / inside_host / outside_host are HOST arrays of `words` (lut: lut_words)
+ * uint32. flag: uint8 [N]. */
+int pg_select_rows(const uint32_t* mut, int64_t N, int words,
+                   const uint32_t* dist_lut_host, int lut_words,
+                   const uint32_t* inside_host, const uint32_t* outside_host, int pos_mode,
+                   uint8_t* flag, void* stream);
+/* ascending indices of the set flags (np.where, :308,:325): *count_out (device int64)
+ * receives the number written; out_idx must hold N entries. */
+int pg_flag_indices(const uint8_t* flag, int64_t N, int64_t* out_idx, int64_t* count_out, void* stream);
+/* hist[d] += 1 for d = popc(mut[n]) (the distance-from-reference histogram used for
+ * np.unique(d_data), :305, and __str__, :147-154); hist: int64 [words*32+1], zeroed by
+ * the caller. */
+int pg_distance_hist(const uint32_t* mut, int64_t N, int words, int64_t* hist, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Measurement helpers.
+ * ------------------------------------------------------------------------- */
+/* integer-pipe peak for the roofline: runs a register-only kernel with the same
+ * 5 LOP3 : 1 POPC : 1 IADD mix as the Hamming inner loop (mix 0), LOP3 only (1) or
+ * POPC only (2) and returns lane-ops per second (synchronous). */
+int pg_measure_int_peak(int mix, int iters, double* lane_ops_per_s, double* ms);
+/* number of kernel launches issued by this library since the last reset */
+int64_t pg_launch_count(int reset);
+/* average device time (CUDA events on the launch stream) of the fused sweep kernel since
+ * the last reset: total ms and launches. Enable with pg_time_sweeps(1). */
+int pg_time_sweeps(int enable);
+int pg_sweep_time(double* total_ms, int64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROGRAPH_B200_H */

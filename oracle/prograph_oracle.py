@@ -331,3 +331,20 @@ def to_csr(lst):
     wl = [np.asarray(w) for _, w in lst if len(w)]
     w = np.concatenate(wl) if wl else np.zeros(0, np.int64)
     return indptr, idx, w
+
+
+# --------------------------------------------------------------------------
+# CPU baseline leg of bench.py: the reference's own loop body with torch CPU ops
+# --------------------------------------------------------------------------
+
+
+def reference_knn_batch_torch(X, batch, k, similarity=False):
+    """One iteration of the reference kNN loop (prograph.py:756-762) exactly as it executes
+    on the host: the broadcasting compare of hamming.py:34 on fp16-staged tokens, then a full
+    sort of every row (stable, the parity contract) and the [:, 1:k+1] slice."""
+    import torch
+    d = torch.sum(X != batch[:, None, :], axis=2)
+    if similarity:
+        d = 1 / (1 + d)
+    s = torch.sort(d, dim=1, descending=similarity, stable=True)
+    return s.indices[:, 1:k + 1].numpy(), s.values[:, 1:k + 1].numpy()

@@ -1,0 +1,191 @@
+// Mutation masks and index selections on the packed table (HBM-bound, one pass each).
+//   prograph.py:488-492  boolean_mutant_array        -> pg_mutant_bits / pg_mutant_bool
+//   prograph.py:494-505  calc_mutated_positions      -> pg_mutant_any
+//   prograph.py:254-343  indexing (distances, positions, Bool) and
+//   prograph.py:349-368  get_mutated_positions       -> pg_select_rows + pg_flag_indices
+//   prograph.py:147-154, :305  distance census        -> pg_distance_hist
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr int kMaxMaskWords = 64;  // sequences up to 2048 residues for the selection kernels
+
+struct WordVec { uint32_t w[kMaxMaskWords]; };
+
+__global__ void mutant_bits_kernel(const uint32_t* __restrict__ table, long long N, int planes, int words,
+                                   const uint32_t* __restrict__ ref, uint32_t* __restrict__ mut) {
+  const long long total = N * words;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / words;
+    const int w = static_cast<int>(i - n * words);
+    const uint32_t* row = table + static_cast<size_t>(n) * planes * words;
+    uint32_t m = 0;
+    for (int p = 0; p < planes; ++p) m |= row[p * words + w] ^ __ldg(ref + p * words + w);
+    mut[i] = m;
+  }
+}
+
+__global__ void mutant_bool_kernel(const uint32_t* __restrict__ table, long long N, int planes, int words, int L,
+                                   const uint32_t* __restrict__ ref, uint8_t* __restrict__ out) {
+  // one thread per (row, residue): byte stores are coalesced along the residue index
+  const long long total = N * L;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / L;
+    const int l = static_cast<int>(i - n * L);
+    const int w = l >> 5, b = l & 31;
+    const uint32_t* row = table + static_cast<size_t>(n) * planes * words;
+    uint32_t m = 0;
+    for (int p = 0; p < planes; ++p) m |= row[p * words + w] ^ __ldg(ref + p * words + w);
+    out[i] = (m >> b) & 1u;
+  }
+}
+
+__global__ void mutant_any_kernel(const uint32_t* __restrict__ mut, long long N, int words, uint32_t* __restrict__ any_bits) {
+  // grid-stride OR per word column; a warp OR-reduces, one atomicOr per warp and word
+  for (int w = 0; w < words; ++w) {
+    uint32_t acc = 0;
+    for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < N;
+         n += static_cast<long long>(gridDim.x) * blockDim.x)
+      acc |= mut[static_cast<size_t>(n) * words + w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicOr(any_bits + w, acc);
+  }
+}
+
+__global__ void select_rows_kernel(const uint32_t* __restrict__ mut, long long N, int words, WordVec dist_lut,
+                                   int use_lut, WordVec inside, WordVec outside, int pos_mode,
+                                   uint8_t* __restrict__ flag) {
+  for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < N;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t* m = mut + static_cast<size_t>(n) * words;
+    int d = 0;
+    bool any_in = false, all_in = true, none_out = true;
+    for (int w = 0; w < words; ++w) {
+      const uint32_t v = m[w], in = inside.w[w];
+      d += __popc(v);
+      any_in |= (v & in) != 0;
+      all_in &= (v & in) == in;
+      none_out &= (v & outside.w[w]) == 0;
+    }
+    bool ok = true;
+    if (use_lut) ok = (dist_lut.w[d >> 5] >> (d & 31)) & 1u;
+    if (pos_mode == 1) ok = ok && any_in && none_out;
+    else if (pos_mode == 2) ok = ok && all_in && none_out;
+    else if (pos_mode == 3) ok = ok && !any_in;
+    flag[n] = ok ? 1 : 0;
+  }
+}
+
+__global__ void distance_hist_kernel(const uint32_t* __restrict__ mut, long long N, int words, long long* __restrict__ hist,
+                                     int bins) {
+  extern __shared__ unsigned sh[];
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < N;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int d = 0;
+    for (int w = 0; w < words; ++w) d += __popc(mut[static_cast<size_t>(n) * words + w]);
+    atomicAdd(&sh[d], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x)
+    if (sh[i]) atomicAdd(reinterpret_cast<unsigned long long*>(hist + i), static_cast<unsigned long long>(sh[i]));
+}
+
+static unsigned grid_for(long long work, int threads) {
+  long long b = ceil_div(work, threads);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_mutant_bits(const uint32_t* table, int64_t N, int planes, int words, const uint32_t* ref, uint32_t* mut,
+                   void* stream) {
+  PG_CHECK_ARG(table && ref && mut && N > 0 && planes > 0 && words > 0, "bad arguments");
+  mutant_bits_kernel<<<grid_for(N * words, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes, words,
+                                                                                             ref, mut);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_mutant_bool(const uint32_t* table, int64_t N, int planes, int words, int L, const uint32_t* ref, uint8_t* out,
+                   void* stream) {
+  PG_CHECK_ARG(table && ref && out && N > 0 && planes > 0 && words > 0 && L > 0 && L <= words * 32, "bad arguments");
+  mutant_bool_kernel<<<grid_for(N * L, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes, words, L,
+                                                                                         ref, out);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_mutant_any(const uint32_t* mut, int64_t N, int words, uint32_t* any_bits, void* stream) {
+  PG_CHECK_ARG(mut && any_bits && N > 0 && words > 0, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_CUDA(cudaMemsetAsync(any_bits, 0, sizeof(uint32_t) * words, s));
+  mutant_any_kernel<<<grid_for(N, 256), 256, 0, s>>>(mut, N, words, any_bits);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_select_rows(const uint32_t* mut, int64_t N, int words, const uint32_t* dist_lut_host, int lut_words,
+                   const uint32_t* inside_host, const uint32_t* outside_host, int pos_mode, uint8_t* flag,
+                   void* stream) {
+  PG_CHECK_ARG(mut && flag && N > 0, "bad arguments");
+  PG_CHECK_ARG(words > 0 && words <= kMaxMaskWords, "selection kernels support up to %d words", kMaxMaskWords);
+  PG_CHECK_ARG(pos_mode >= 0 && pos_mode <= 3, "bad pos_mode %d", pos_mode);
+  PG_CHECK_ARG(pos_mode == 0 || inside_host, "positions mask missing");
+  PG_CHECK_ARG(!dist_lut_host || (lut_words >= 1 && lut_words <= kMaxMaskWords && lut_words * 32 > words * 32),
+               "distance lut must cover 0..%d", words * 32);
+  PG_CHECK_ARG(!(pos_mode == 1 || pos_mode == 2) || outside_host, "unchanged-positions mask missing");
+  WordVec lut, inside, outside;
+  memset(&lut, 0, sizeof(lut));
+  memset(&inside, 0, sizeof(inside));
+  memset(&outside, 0, sizeof(outside));
+  if (outside_host) memcpy(outside.w, outside_host, sizeof(uint32_t) * words);
+  if (dist_lut_host) memcpy(lut.w, dist_lut_host, sizeof(uint32_t) * lut_words);
+  if (inside_host) memcpy(inside.w, inside_host, sizeof(uint32_t) * words);
+  select_rows_kernel<<<grid_for(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mut, N, words, lut, dist_lut_host ? 1 : 0, inside, outside, pos_mode, flag);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_flag_indices(const uint8_t* flag, int64_t N, int64_t* out_idx, int64_t* count_out, void* stream) {
+  PG_CHECK_ARG(flag && out_idx && count_out && N > 0 && N < (1ll << 31), "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  thrust::counting_iterator<long long> ids(0);
+  size_t tmp_bytes = 0;
+  PG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, flag, reinterpret_cast<long long*>(out_idx),
+                                     reinterpret_cast<long long*>(count_out), static_cast<int>(N), s));
+  void* tmp = nullptr;
+  PG_CUDA(cudaMallocAsync(&tmp, tmp_bytes, s));
+  cudaError_t e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, ids, flag, reinterpret_cast<long long*>(out_idx),
+                                             reinterpret_cast<long long*>(count_out), static_cast<int>(N), s);
+  count_launch();
+  cudaFreeAsync(tmp, s);
+  if (e != cudaSuccess) { set_error("cub select failed: %s", cudaGetErrorString(e)); return PG_ERR_CUDA; }
+  return PG_OK;
+}
+
+int pg_distance_hist(const uint32_t* mut, int64_t N, int words, int64_t* hist, void* stream) {
+  PG_CHECK_ARG(mut && hist && N > 0 && words > 0, "bad arguments");
+  const int bins = words * 32 + 1;
+  distance_hist_kernel<<<grid_for(N, 256), 256, bins * sizeof(unsigned), static_cast<cudaStream_t>(stream)>>>(
+      mut, N, words, reinterpret_cast<long long*>(hist), bins);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// C-ABI entry points of the fused Hamming sweeps (see pg_sweep.cuh and
+// include/prograph_b200.h).  Host-side work here: geometry (row blocks x stream splits),
+// workspace carving, the split-merge / finalise kernels and the launch bookkeeping.
+#include <vector>
+#include <mutex>
+
+#include <cub/device/device_scan.cuh>
+
+#include "pg_sweep.cuh"
+
+namespace pg {
+
+// ---- launch timing (CUDA events on the launch stream; read by bench.py) ------------
+static std::mutex g_time_mu;
+static bool g_time_enabled = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;
+
+struct SweepTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  explicit SweepTimer(cudaStream_t stream) : s(stream) {
+    std::lock_guard<std::mutex> g(g_time_mu);
+    if (!g_time_enabled) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+  }
+  ~SweepTimer() {
+    if (!a) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> g(g_time_mu);
+    g_time_events.emplace_back(a, b);
+  }
+};
+
+// ---- geometry -------------------------------------------------------------------
+struct Geometry {
+  int n_rowblocks, n_splits, tiles_per_split, n_tiles, tile_cols;
+};
+
+static int tile_cols_for(int words) { return 512 / words; }
+
+// Splits of the stream make the persistent grid's last wave short: aim for >= 32 items per
+// resident CTA, but keep >= 8 ring tiles per item so the own-row load and the list
+// write-back stay amortised.
+static Geometry make_geometry(long long rows, long long stream_rows, int words) {
+  Geometry g;
+  g.tile_cols = tile_cols_for(words);
+  g.n_rowblocks = static_cast<int>(ceil_div(rows, kConsumers));
+  g.n_tiles = static_cast<int>(ceil_div(stream_rows, g.tile_cols));
+  const long long resident = static_cast<long long>(num_sms()) * 2;
+  long long want = ceil_div(32 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
+  long long max_splits = g.n_tiles / 8;
+  if (max_splits < 1) max_splits = 1;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  g.tiles_per_split = static_cast<int>(ceil_div(g.n_tiles, want));
+  g.n_splits = static_cast<int>(ceil_div(g.n_tiles, g.tiles_per_split));
+  return g;
+}
+
+static int dispatch(int planes, int words, const SweepParams& prm, const SweepLaunch& l) {
+#define PG_CASE(P, W) \
+  if (planes == P && words == W) return sweep_p##P##_w##W(prm, l);
+  PG_CASE(5, 1) PG_CASE(5, 2) PG_CASE(5, 4) PG_CASE(5, 8)
+  PG_CASE(8, 1) PG_CASE(8, 2) PG_CASE(8, 4) PG_CASE(8, 8)
+#undef PG_CASE
+  set_error("fused sweep supports planes in {5,8} and words in {1,2,4,8}; got planes=%d words=%d", planes, words);
+  return PG_ERR_UNSUPPORTED;
+}
+
+static int check_common(const void* own, long long own_rows, long long row0, long long rows, const void* str,
+                        long long stream_rows, int planes, int words) {
+  PG_CHECK_ARG(own && str, "null table pointer");
+  PG_CHECK_ARG(rows > 0 && row0 >= 0 && row0 + rows <= own_rows, "own row range [%lld,%lld) outside table of %lld rows",
+               row0, row0 + rows, own_rows);
+  PG_CHECK_ARG(stream_rows > 0, "empty stream table");
+  PG_CHECK_ARG(stream_rows < (1ll << 32), "stream table too large for 32-bit indices");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(str) & 15) == 0, "stream table must be 16-byte aligned");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(own) & 15) == 0, "own table must be 16-byte aligned");
+  if (!((planes == 5 || planes == 8) && (words == 1 || words == 2 || words == 4 || words == 8))) {
+    set_error("fused sweep supports planes in {5,8} and words in {1,2,4,8}; got planes=%d words=%d", planes, words);
+    return PG_ERR_UNSUPPORTED;
+  }
+  return PG_OK;
+}
+
+static void fill_common(SweepParams& prm, const Geometry& g, const uint32_t* own, long long row0, long long rows,
+                        const uint32_t* str, long long stream_rows) {
+  memset(&prm, 0, sizeof(prm));
+  prm.own = own;
+  prm.own_row0 = row0;
+  prm.rows = rows;
+  prm.str = str;
+  prm.str_rows = stream_rows;
+  prm.n_rowblocks = g.n_rowblocks;
+  prm.n_splits = g.n_splits;
+  prm.tiles_per_split = g.tiles_per_split;
+  prm.n_tiles = g.n_tiles;
+}
+
+// A truth table over d = 0..L that is one contiguous run becomes a range test.
+static bool lut_as_range(const uint32_t* lut, int lut_words, int* lo, unsigned* span) {
+  int first = -1, last = -1, pop = 0;
+  for (int d = 0; d < lut_words * 32; ++d) {
+    if ((lut[d >> 5] >> (d & 31)) & 1u) {
+      if (first < 0) first = d;
+      last = d;
+      ++pop;
+    }
+  }
+  if (pop == 0) { *lo = 0x7fffffff; *span = 0; return true; }
+  if (last - first + 1 != pop) return false;
+  *lo = first;
+  *span = static_cast<unsigned>(last - first);
+  return true;
+}
+
+// ---- kNN: merge the per-split lists, drop leading entries, widen ---------------------
+__global__ void knn_finalize_kernel(const unsigned long long* __restrict__ part, int n_splits, int k1, long long rows,
+                                    int k, int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  unsigned long long last = 0;
+  bool have_last = false;
+  for (int j = 0; j < drop + k; ++j) {
+    unsigned long long best = ~0ull;
+    if (n_splits == 1) {
+      best = j < k1 ? part[static_cast<size_t>(j) * rows + r] : ~0ull;
+    } else {
+      // keys are unique (index in the low word), so "smallest key above the last one" walks
+      // the merged order; each split list is ascending, stop at the first usable entry
+      for (int s = 0; s < n_splits; ++s) {
+        const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
+        for (int i = 0; i < k1; ++i) {
+          const unsigned long long v = lst[static_cast<size_t>(i) * rows];
+          if (have_last && v <= last) continue;
+          if (v < best) best = v;
+          break;
+        }
+      }
+    }
+    last = best;
+    have_last = true;
+    if (j >= drop) {
+      const long long at = r * k + (j - drop);
+      if (best == ~0ull) {
+        out_idx[at] = -1;
+        write_weight(out_w, at, 0, weight);
+      } else {
+        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
+        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
+      }
+    }
+  }
+}
+
+__global__ void sum_splits_kernel(const long long* __restrict__ split_counts, int n_splits, long long rows,
+                                  long long* __restrict__ counts) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  long long s = 0;
+  for (int i = 0; i < n_splits; ++i) s += split_counts[static_cast<size_t>(i) * rows + r];
+  counts[r] = s;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1) {
+  if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
+  if (words > 8) words = 8;
+  const Geometry g = make_geometry(own_rows, stream_rows, words);
+  const size_t per_row = static_cast<size_t>(g.n_splits) * 8 * static_cast<size_t>(k1 > 1 ? k1 : 1);
+  return per_row * static_cast<size_t>(own_rows) + 256;
+}
+
+int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows, const uint32_t* stream_tab,
+                   int64_t stream_rows, int planes, int words, int k, int drop, int weight, int64_t* out_idx,
+                   void* out_w, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(own, own_rows, row0, rows, stream_tab, stream_rows, planes, words);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(k >= 1 && drop >= 0, "k must be >= 1 and drop >= 0");
+  PG_CHECK_ARG(out_idx && out_w && workspace, "null output/workspace pointer");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
+  const int k1 = drop + k;
+  const Geometry g = make_geometry(rows, stream_rows, words);
+  const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
+  PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  const size_t list_bytes = static_cast<size_t>(k1) * kConsumers * 8;
+  if (list_bytes + 70 * 1024 > 227 * 1024) {
+    set_error("k=%d too large for the in-shared-memory lists of the fused sweep", k);
+    return PG_ERR_UNSUPPORTED;
+  }
+  SweepParams prm;
+  fill_common(prm, g, own, row0, rows, stream_tab, stream_rows);
+  prm.part = static_cast<unsigned long long*>(workspace);
+  prm.k1 = k1;
+  SweepLaunch l{MODE_KNN, 0, weight, 0, list_bytes, static_cast<cudaStream_t>(stream)};
+  {
+    SweepTimer t(l.stream);
+    rc = dispatch(planes, words, prm, l);
+  }
+  if (rc != PG_OK) return rc;
+  const int threads = 128;
+  knn_finalize_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
+      prm.part, g.n_splits, k1, rows, k, drop, weight, reinterpret_cast<long long*>(out_idx), out_w);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                    const uint32_t* stream_tab, int64_t stream_rows, int planes, int words, const uint32_t* lut_host,
+                    int lut_words, int64_t* counts, const int64_t* indptr, int weight, int64_t* out_idx, void* out_w,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(own, own_rows, row0, rows, stream_tab, stream_rows, planes, words);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(lut_host && lut_words >= 1 && lut_words <= kMaxLutWords, "lut_words must be in [1,%d]", kMaxLutWords);
+  PG_CHECK_ARG(lut_words * 32 > words * 32, "lut must cover distances 0..%d", words * 32);
+  PG_CHECK_ARG(workspace, "null workspace");
+  const Geometry g = make_geometry(rows, stream_rows, words);
+  const size_t need = static_cast<size_t>(g.n_splits) * rows * 8;
+  PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  SweepParams prm;
+  fill_common(prm, g, own, row0, rows, stream_tab, stream_rows);
+  prm.split_counts = static_cast<long long*>(workspace);
+  for (int i = 0; i < lut_words; ++i) prm.lut[i] = lut_host[i];
+  const bool ranged = lut_as_range(lut_host, lut_words, &prm.lo, &prm.span);
+  SweepLaunch l{mode, ranged ? 0 : 1, weight, 0, 0, static_cast<cudaStream_t>(stream)};
+  if (mode == MODE_FILL) {
+    prm.indptr = reinterpret_cast<const long long*>(indptr);
+    prm.out_idx = reinterpret_cast<long long*>(out_idx);
+    prm.out_w = out_w;
+  }
+  {
+    SweepTimer t(l.stream);
+    rc = dispatch(planes, words, prm, l);
+  }
+  if (rc != PG_OK) return rc;
+  if (mode == MODE_COUNT) {
+    const int threads = 256;
+    sum_splits_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
+        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts));
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}
+
+int pg_hamming_eps_count(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                         const uint32_t* stream_tab, int64_t stream_rows, int planes, int words,
+                         const uint32_t* lut_host, int lut_words, int64_t* counts, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  PG_CHECK_ARG(counts, "null counts");
+  return eps_pass(MODE_COUNT, own, own_rows, row0, rows, stream_tab, stream_rows, planes, words, lut_host, lut_words,
+                  counts, nullptr, PG_W_I64, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int pg_hamming_eps_fill(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                        const uint32_t* stream_tab, int64_t stream_rows, int planes, int words,
+                        const uint32_t* lut_host, int lut_words, const int64_t* indptr, int weight, int64_t* out_idx,
+                        void* out_w, void* workspace, size_t workspace_bytes, void* stream) {
+  PG_CHECK_ARG(indptr && out_idx && out_w, "null indptr/output");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32, "fill writes int64 distances or float32 similarities");
+  return eps_pass(MODE_FILL, own, own_rows, row0, rows, stream_tab, stream_rows, planes, words, lut_host, lut_words,
+                  nullptr, indptr, weight, out_idx, out_w, workspace, workspace_bytes, stream);
+}
+
+int pg_hamming_tile(const uint32_t* data, int64_t data_rows, const uint32_t* queries, int64_t query_rows, int64_t q0,
+                    int64_t qrows, int planes, int words, int weight, void* out, int64_t ld, void* stream) {
+  // own = dataset rows (coalesced stores along n), stream = the query rows
+  PG_CHECK_ARG(q0 >= 0 && qrows > 0 && q0 + qrows <= query_rows, "query range outside table");
+  PG_CHECK_ARG(q0 % kStreamRowPad == 0, "q0 must be a multiple of %d", kStreamRowPad);
+  int rc = check_common(data, data_rows, 0, data_rows, queries, qrows, planes, words);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(out && ld >= data_rows, "bad output / leading dimension");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
+  Geometry g = make_geometry(data_rows, qrows, words);
+  g.n_splits = 1;  // every (own, stream) pair is written exactly once; splits only add launches
+  g.tiles_per_split = g.n_tiles;
+  SweepParams prm;
+  fill_common(prm, g, data, 0, data_rows, queries + static_cast<size_t>(q0) * planes * words, qrows);
+  prm.out = out;
+  prm.ld = ld;
+  SweepLaunch l{MODE_TILE, 0, weight, 0, 0, static_cast<cudaStream_t>(stream)};
+  SweepTimer t(l.stream);
+  return dispatch(planes, words, prm, l);
+}
+
+int pg_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream) {
+  PG_CHECK_ARG(in && out && n >= 0, "bad scan arguments");
+  if (n == 0) {
+    PG_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), static_cast<cudaStream_t>(stream)));
+    return PG_OK;
+  }
+  // out[0..n-1] exclusive, out[n] = total: run an inclusive scan into out+1 and zero out[0]
+  size_t tmp_bytes = 0;
+  PG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out + 1, static_cast<int>(n),
+                                        static_cast<cudaStream_t>(stream)));
+  void* tmp = nullptr;
+  PG_CUDA(cudaMallocAsync(&tmp, tmp_bytes, static_cast<cudaStream_t>(stream)));
+  cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, in, out + 1, static_cast<int>(n),
+                                                static_cast<cudaStream_t>(stream));
+  count_launch();
+  cudaFreeAsync(tmp, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { set_error("cub scan failed: %s", cudaGetErrorString(e)); return PG_ERR_CUDA; }
+  PG_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), static_cast<cudaStream_t>(stream)));
+  return PG_OK;
+}
+
+int pg_time_sweeps(int enable) {
+  std::lock_guard<std::mutex> g(g_time_mu);
+  g_time_enabled = enable != 0;
+  return PG_OK;
+}
+
+int pg_sweep_time(double* total_ms, int64_t* launches, int reset) {
+  std::lock_guard<std::mutex> g(g_time_mu);
+  double tot = 0;
+  for (auto& ev : g_time_events) {
+    cudaEventSynchronize(ev.second);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev.first, ev.second);
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<int64_t>(g_time_events.size());
+  if (reset) {
+    for (auto& ev : g_time_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    g_time_events.clear();
+  }
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// Fused all-pairs Hamming sweep for sm_100a.
+//
+// Replaces  torch.sum(X != Y[:,None,:], axis=2)  (prograph/distance/hamming.py:34) together
+// with the consumer that follows it in prograph/prograph.py (sort+slice :757-762,
+// where+gather :734-739, or the plain (M,N) result).
+//
+// Mapping ("own rows in registers, stream rows by broadcast"):
+//   * a CTA owns 256 "own" rows, one per consumer thread; the thread keeps its row's
+//     P bit planes x W words (P*W registers) for the whole sweep;
+//   * the "stream" table is swept through a 4-stage shared-memory ring filled by one
+//     producer lane with 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier);
+//     every consumer reads the same stream row at the same time, so shared-memory
+//     reads are pure broadcasts (one wavefront per 128-bit load, no bank conflicts);
+//   * per pair and 32 residues: 5 LOP3 (xor/or fold of the planes) + 1 POPC + 1 IADD;
+//   * the epilogue sees (own row, stream row, distance) in ascending stream order and
+//     never writes the distance matrix: kNN keeps a sorted (distance,index) list per
+//     own row in shared memory behind a register threshold; the epsilon passes count /
+//     emit edges; the tile mode stores distances coalesced along the own index.
+// Work items are (row block, stream split) pairs walked by a persistent grid.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;  // own rows per CTA
+constexpr int kSweepThreads = kConsumers + 32;   // + one producer warp
+constexpr int kStages = 4;
+constexpr int kMaxLutWords = 64;                 // distances up to 2047
+
+enum SweepMode { MODE_KNN = 0, MODE_COUNT = 1, MODE_FILL = 2, MODE_TILE = 3 };
+
+template <int W>
+struct TileCols {  // stream rows per ring stage: 64 rows of 8 words (2 KB per plane)
+  static constexpr int value = 512 / W;
+};
+
+struct SweepParams {
+  const uint32_t* own;   // packed table holding the own rows
+  long long own_row0;    // first own row to process
+  long long rows;        // number of own rows to process
+  const uint32_t* str;   // packed stream table (padded to kStreamRowPad rows)
+  long long str_rows;    // valid stream rows
+  int n_rowblocks, n_splits, tiles_per_split, n_tiles;
+  // kNN
+  unsigned long long* part;  // [n_splits][k1][rows] sorted partial lists, key = d<<32 | idx
+  int k1;
+  // epsilon passes
+  int lo;                 // range test (unsigned)(d - lo) <= span when !LUT
+  unsigned span;
+  long long* split_counts;  // [n_splits][rows]
+  const long long* indptr;  // [rows+1]                          (fill)
+  long long* out_idx;       // edges                              (fill)
+  void* out_w;
+  // tile
+  void* out;
+  long long ld;
+  uint32_t lut[kMaxLutWords];
+};
+
+template <int P, int W>
+__device__ __forceinline__ int ham_row(const uint32_t (&q)[P * W], const uint32_t* __restrict__ col) {
+  uint32_t m[W];
+  if constexpr (W % 4 == 0) {
+    const uint4* c4 = reinterpret_cast<const uint4*>(col);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int h = 0; h < W / 4; ++h) {
+        const uint4 v = c4[p * (W / 4) + h];
+        const int w = h * 4;
+        if (p == 0) {
+          m[w + 0] = q[w + 0] ^ v.x;
+          m[w + 1] = q[w + 1] ^ v.y;
+          m[w + 2] = q[w + 2] ^ v.z;
+          m[w + 3] = q[w + 3] ^ v.w;
+        } else {
+          m[w + 0] |= q[p * W + w + 0] ^ v.x;
+          m[w + 1] |= q[p * W + w + 1] ^ v.y;
+          m[w + 2] |= q[p * W + w + 2] ^ v.z;
+          m[w + 3] |= q[p * W + w + 3] ^ v.w;
+        }
+      }
+    }
+  } else if constexpr (W == 2) {
+    const uint2* c2 = reinterpret_cast<const uint2*>(col);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const uint2 v = c2[p];
+      if (p == 0) {
+        m[0] = q[0] ^ v.x;
+        m[1] = q[1] ^ v.y;
+      } else {
+        m[0] |= q[p * 2 + 0] ^ v.x;
+        m[1] |= q[p * 2 + 1] ^ v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t v = col[p * W + w];
+        if (p == 0) m[w] = q[w] ^ v;
+        else m[w] |= q[p * W + w] ^ v;
+      }
+    }
+  }
+  int d = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) d += __popc(m[w]);
+  return d;
+}
+
+__device__ __forceinline__ void write_weight(void* out_w, long long at, int d, int weight) {
+  if (weight == PG_W_I64) reinterpret_cast<long long*>(out_w)[at] = d;
+  else if (weight == PG_W_SIM_F32) reinterpret_cast<float*>(out_w)[at] = sim_f32(d);
+  else reinterpret_cast<int*>(out_w)[at] = d;
+}
+
+// Sorted insertion into this thread's list (entries `stride` apart, ascending keys).
+// Precondition: key < list[k1-1].
+__device__ __forceinline__ unsigned knn_insert(unsigned long long* list, int stride, int k1,
+                                               unsigned long long key) {
+  int j = k1 - 1;
+  while (j > 0) {
+    const unsigned long long prev = list[(j - 1) * stride];
+    if (prev <= key) break;
+    list[j * stride] = prev;
+    --j;
+  }
+  list[j * stride] = key;
+  return static_cast<unsigned>(list[(k1 - 1) * stride] >> 32);
+}
+
+template <int P, int W, int MODE, bool LUT, int WEIGHT>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_constant__ SweepParams prm) {
+  constexpr int BN = TileCols<W>::value;
+  constexpr int COLW = P * W;
+  constexpr uint32_t STAGE_BYTES = BN * COLW * 4;
+  static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* stage_mem = reinterpret_cast<uint32_t*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * STAGE_BYTES);
+  uint64_t* empty = full + kStages;
+  uint32_t* lut_s = reinterpret_cast<uint32_t*>(empty + kStages);
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(lut_s + kMaxLutWords);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  if (LUT && tid < kMaxLutWords) lut_s[tid] = prm.lut[tid];
+  __syncthreads();
+
+  const int n_items = prm.n_rowblocks * prm.n_splits;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == kConsumerWarps) {
+    // ---------------- producer: one lane feeds the ring -----------------
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / prm.n_rowblocks;
+        const int t0 = split * prm.tiles_per_split;
+        const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          bulk_g2s(stage_mem + stage * (BN * COLW), prm.str + static_cast<size_t>(t) * BN * COLW, STAGE_BYTES,
+                   &full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ------------------------------------------
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int split = item / prm.n_rowblocks;
+    const int rb = item - split * prm.n_rowblocks;
+    const long long r = static_cast<long long>(rb) * kConsumers + tid;  // row relative to own_row0
+    const bool valid = r < prm.rows;
+
+    uint32_t q[COLW];
+    {
+      const uint32_t* src = prm.own + static_cast<size_t>(prm.own_row0 + (valid ? r : 0)) * COLW;
+#pragma unroll
+      for (int i = 0; i < COLW; ++i) q[i] = valid ? __ldg(src + i) : 0u;
+    }
+
+    // per-mode state
+    unsigned tau = valid ? 0xffffffffu : 0u;   // kNN: distance of the k1-th list entry
+    long long cnt = 0;                          // count / fill cursor
+    unsigned long long* my_list = lists + tid;
+    int lo = prm.lo;
+    unsigned span = prm.span;
+    if constexpr (MODE == MODE_KNN) {
+      for (int j = 0; j < prm.k1; ++j) my_list[j * kConsumers] = ~0ull;
+    }
+    if constexpr (MODE == MODE_COUNT || MODE == MODE_FILL) {
+      if (!valid) { lo = 0x7fffffff; span = 0; }
+    }
+    if constexpr (MODE == MODE_FILL) {
+      if (valid) {
+        cnt = prm.indptr[r];
+        for (int s = 0; s < split; ++s) cnt += prm.split_counts[static_cast<size_t>(s) * prm.rows + r];
+      }
+    }
+
+    const int t0 = split * prm.tiles_per_split;
+    const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait(&full[stage], phase);
+      const uint32_t* tile = stage_mem + stage * (BN * COLW);
+      const long long col0 = static_cast<long long>(t) * BN;
+      const int ncols = static_cast<int>(min(static_cast<long long>(BN), prm.str_rows - col0));
+#pragma unroll 2
+      for (int c = 0; c < ncols; ++c) {
+        const int d = ham_row<P, W>(q, tile + c * COLW);
+        if constexpr (MODE == MODE_KNN) {
+          if (static_cast<unsigned>(d) < tau) {
+            const unsigned long long key =
+                (static_cast<unsigned long long>(static_cast<unsigned>(d)) << 32) | static_cast<unsigned>(col0 + c);
+            tau = knn_insert(my_list, kConsumers, prm.k1, key);
+          }
+        } else if constexpr (MODE == MODE_COUNT) {
+          if constexpr (LUT) cnt += (lut_s[d >> 5] >> (d & 31)) & (valid ? 1u : 0u);
+          else cnt += (static_cast<unsigned>(d - lo) <= span) ? 1 : 0;
+        } else if constexpr (MODE == MODE_FILL) {
+          bool hit;
+          if constexpr (LUT) hit = ((lut_s[d >> 5] >> (d & 31)) & 1u) && valid;
+          else hit = static_cast<unsigned>(d - lo) <= span;
+          if (hit) {
+            prm.out_idx[cnt] = col0 + c;
+            write_weight(prm.out_w, cnt, d, WEIGHT);
+            ++cnt;
+          }
+        } else {  // MODE_TILE: out[stream * ld + own]
+          if (valid) write_weight(prm.out, (col0 + c) * prm.ld + r, d, WEIGHT);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+
+    if constexpr (MODE == MODE_KNN) {
+      if (valid) {
+        unsigned long long* dst = prm.part + static_cast<size_t>(split) * prm.k1 * prm.rows + r;
+        for (int j = 0; j < prm.k1; ++j) dst[static_cast<size_t>(j) * prm.rows] = my_list[j * kConsumers];
+      }
+    } else if constexpr (MODE == MODE_COUNT) {
+      if (valid) prm.split_counts[static_cast<size_t>(split) * prm.rows + r] = cnt;
+    }
+  }
+}
+
+}  // namespace pg
+
+// ---- host-side launcher, one translation unit per (P, W) ------------------------
+namespace pg {
+
+struct SweepLaunch {
+  int mode;    // SweepMode
+  int lut;     // 0 range test, 1 LUT
+  int weight;  // pgWeight (tile: compile time; fill: runtime)
+  int grid;    // 0 = let the launcher size a persistent grid
+  size_t list_bytes;  // kNN lists
+  cudaStream_t stream;
+};
+
+template <int P, int W>
+inline size_t sweep_smem_bytes(size_t list_bytes) {
+  return static_cast<size_t>(kStages) * TileCols<W>::value * P * W * 4 + 2 * kStages * sizeof(uint64_t) +
+         kMaxLutWords * 4 + list_bytes;
+}
+
+template <int P, int W, int MODE, bool LUT, int WEIGHT>
+int launch_one(const SweepParams& prm, const SweepLaunch& l) {
+  auto kern = sweep_kernel<P, W, MODE, LUT, WEIGHT>;
+  const size_t smem = sweep_smem_bytes<P, W>(l.list_bytes);
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int occ = 0;
+  PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSweepThreads, smem));
+  if (occ < 1) { set_error("sweep kernel does not fit on an SM (smem %zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
+  const long long n_items = static_cast<long long>(prm.n_rowblocks) * prm.n_splits;
+  long long grid = l.grid > 0 ? l.grid : static_cast<long long>(num_sms()) * occ;
+  if (grid > n_items) grid = n_items;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), kSweepThreads, smem, l.stream>>>(prm);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+template <int P, int W>
+int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
+  switch (l.mode) {
+    case MODE_KNN: return launch_one<P, W, MODE_KNN, false, 0>(prm, l);
+    case MODE_COUNT:
+      return l.lut ? launch_one<P, W, MODE_COUNT, true, 0>(prm, l) : launch_one<P, W, MODE_COUNT, false, 0>(prm, l);
+    case MODE_FILL:
+      if (l.weight == PG_W_SIM_F32)
+        return l.lut ? launch_one<P, W, MODE_FILL, true, PG_W_SIM_F32>(prm, l)
+                     : launch_one<P, W, MODE_FILL, false, PG_W_SIM_F32>(prm, l);
+      return l.lut ? launch_one<P, W, MODE_FILL, true, PG_W_I64>(prm, l)
+                   : launch_one<P, W, MODE_FILL, false, PG_W_I64>(prm, l);
+    case MODE_TILE:
+      if (l.weight == PG_W_I64) return launch_one<P, W, MODE_TILE, false, PG_W_I64>(prm, l);
+      if (l.weight == PG_W_SIM_F32) return launch_one<P, W, MODE_TILE, false, PG_W_SIM_F32>(prm, l);
+      return launch_one<P, W, MODE_TILE, false, PG_W_I32>(prm, l);
+  }
+  set_error("bad sweep mode %d", l.mode);
+  return PG_ERR_INVALID;
+}
+
+// defined in pg_sweep_inst.cu, one per (P, W)
+#define PG_DECL_SWEEP(P, W) int sweep_p##P##_w##W(const SweepParams& prm, const SweepLaunch& l);
+PG_DECL_SWEEP(5, 1) PG_DECL_SWEEP(5, 2) PG_DECL_SWEEP(5, 4) PG_DECL_SWEEP(5, 8)
+PG_DECL_SWEEP(8, 1) PG_DECL_SWEEP(8, 2) PG_DECL_SWEEP(8, 4) PG_DECL_SWEEP(8, 8)
+#undef PG_DECL_SWEEP
+
+}  // namespace pg

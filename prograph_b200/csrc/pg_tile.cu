@@ -1,0 +1,614 @@
+// Element-wise metric tiles and the consumers of a materialised (rows x N) distance tile.
+//
+//   pg_minkowski_tile        minkowski.py:36-40 with the reference's rounding chain
+//   pg_hamming_values_tile   hamming.py:34 on arbitrary numeric values
+//   pg_tile_topk             prograph.py:757-762 (stable sort + slice) as select-then-sort
+//   pg_tile_threshold_*      prograph.py:734-739 / :544 (where + gather) as ballot +
+//                            block prefix-sum compaction
+#include <math_constants.h>
+
+#include "pg_common.cuh"
+
+namespace pg {
+
+// =============================================================================
+// Element-wise tiles
+// =============================================================================
+enum ValKind { VK_F16 = 0, VK_F32 = 1, VK_F64 = 2, VK_I64 = 3 };
+enum PowKind { PK_ONE = 0, PK_TWO = 1, PK_THREE = 2, PK_SQRT = 3, PK_GENERAL = 4 };
+
+__device__ __forceinline__ float rh(float x) { return __half2float(__float2half_rn(x)); }  // round through fp16
+
+template <int PK>
+__device__ __forceinline__ float pow_f32(float x, float e) {
+  if (PK == PK_ONE) return x;
+  if (PK == PK_TWO) return x * x;
+  if (PK == PK_THREE) return (x * x) * x;
+  if (PK == PK_SQRT) return sqrtf(x);
+  return powf(x, e);
+}
+// fp16 tensor ** scalar: every multiply of the optimised exponents rounds to fp16
+template <int PK>
+__device__ __forceinline__ float pow_f16(float x, float e) {
+  if (PK == PK_ONE) return x;
+  if (PK == PK_TWO) return rh(x * x);
+  if (PK == PK_THREE) return rh(rh(x * x) * x);
+  if (PK == PK_SQRT) return rh(sqrtf(x));
+  return rh(powf(x, e));
+}
+template <int PK>
+__device__ __forceinline__ double pow_f64(double x, double e) {
+  if (PK == PK_ONE) return x;
+  if (PK == PK_TWO) return x * x;
+  if (PK == PK_THREE) return (x * x) * x;
+  if (PK == PK_SQRT) return sqrt(x);
+  return pow(x, e);
+}
+__device__ __forceinline__ long long ipow(long long b, int e) {  // wraps like torch's integer pow
+  long long r = 1;
+  while (e > 0) {
+    if (e & 1) r *= b;
+    b *= b;
+    e >>= 1;
+  }
+  return r;
+}
+
+static int pow_kind(double e) {
+  if (e == 1.0) return PK_ONE;
+  if (e == 2.0) return PK_TWO;
+  if (e == 3.0) return PK_THREE;
+  if (e == 0.5) return PK_SQRT;
+  return PK_GENERAL;
+}
+
+template <typename T> struct Compute { using type = float; };
+template <> struct Compute<double> { using type = double; };
+template <> struct Compute<long long> { using type = long long; };
+
+template <typename T> __device__ __forceinline__ typename Compute<T>::type load_val(const T* p) { return *p; }
+template <> __device__ __forceinline__ float load_val<__half>(const __half* p) { return __half2float(*p); }
+
+constexpr int ET_N = 64;   // dataset rows per CTA
+constexpr int ET_M = 32;   // query rows per CTA
+constexpr int ET_D = 32;   // components per staging chunk
+constexpr int ET_MPT = 8;  // queries per thread
+
+struct ElemParams {
+  const void* X; long long N;
+  const void* Y; long long q0, qrows;
+  int D;
+  void* out; long long ld;
+  float p_f, root_f;     // exponents as the tensor dtype sees them (fp16-rounded for VK_F16)
+  double p_d, root_d;
+  int p_int;             // integer exponent for VK_I64
+  int similarity;
+  int weight;            // hamming-values output kind
+};
+
+// METRIC 0: minkowski, 1: hamming on values
+template <typename T, int VK, int METRIC, int PKIN, int PKROOT>
+__global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
+  using CT = typename Compute<T>::type;
+  __shared__ CT Xs[ET_N][ET_D + 1];
+  __shared__ CT Ys[ET_M][ET_D];
+  const T* X = static_cast<const T*>(prm.X);
+  const T* Y = static_cast<const T*>(prm.Y);
+  const int tid = threadIdx.x;
+  const int nl = tid % ET_N;
+  const int mg = tid / ET_N;  // 0..3
+  const long long n0 = static_cast<long long>(blockIdx.x) * ET_N;
+  const long long m0 = static_cast<long long>(blockIdx.y) * ET_M;
+
+  // accumulators: fp32 for f16/f32 sums, double for f64, int64 for integer inputs / counts
+  float accf[ET_MPT];
+  double accd[ET_MPT];
+  long long acci[ET_MPT];
+#pragma unroll
+  for (int i = 0; i < ET_MPT; ++i) { accf[i] = 0.f; accd[i] = 0.0; acci[i] = 0; }
+
+  for (int d0 = 0; d0 < prm.D; d0 += ET_D) {
+    for (int i = tid; i < ET_N * ET_D; i += 256) {
+      const int r = i / ET_D, c = i % ET_D;
+      const long long n = n0 + r;
+      CT v = CT(0);
+      if (n < prm.N && d0 + c < prm.D) v = load_val<T>(X + static_cast<size_t>(n) * prm.D + d0 + c);
+      Xs[r][c] = v;
+    }
+    for (int i = tid; i < ET_M * ET_D; i += 256) {
+      const int r = i / ET_D, c = i % ET_D;
+      const long long m = m0 + r;
+      CT v = CT(0);
+      if (m < prm.qrows && d0 + c < prm.D) v = load_val<T>(Y + static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c);
+      Ys[r][c] = v;
+    }
+    __syncthreads();
+    const int dn = min(ET_D, prm.D - d0);
+    for (int c = 0; c < dn; ++c) {
+      const CT x = Xs[nl][c];
+#pragma unroll
+      for (int i = 0; i < ET_MPT; ++i) {
+        const CT y = Ys[mg * ET_MPT + i][c];
+        if (METRIC == 1) {
+          acci[i] += (x != y) ? 1 : 0;
+        } else if (VK == VK_F16) {
+          const float diff = rh(static_cast<float>(x) - static_cast<float>(y));
+          accf[i] += pow_f16<PKIN>(diff, prm.p_f);
+        } else if (VK == VK_F32) {
+          accf[i] += pow_f32<PKIN>(static_cast<float>(x) - static_cast<float>(y), prm.p_f);
+        } else if (VK == VK_F64) {
+          accd[i] += pow_f64<PKIN>(static_cast<double>(x) - static_cast<double>(y), prm.p_d);
+        } else {
+          acci[i] += ipow(static_cast<long long>(x) - static_cast<long long>(y), prm.p_int);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const long long n = n0 + nl;
+  if (n >= prm.N) return;
+#pragma unroll
+  for (int i = 0; i < ET_MPT; ++i) {
+    const long long m = m0 + mg * ET_MPT + i;
+    if (m >= prm.qrows) continue;
+    const size_t at = static_cast<size_t>(m) * prm.ld + n;
+    if (METRIC == 1) {
+      if (prm.weight == PG_W_I64) static_cast<long long*>(prm.out)[at] = acci[i];
+      else if (prm.weight == PG_W_SIM_F32) static_cast<float*>(prm.out)[at] = sim_f32(static_cast<int>(acci[i]));
+      else static_cast<int*>(prm.out)[at] = static_cast<int>(acci[i]);
+    } else if (VK == VK_F16) {
+      float d = pow_f16<PKROOT>(rh(accf[i]), prm.root_f);
+      if (prm.similarity) d = rh(__fdiv_rn(1.0f, rh(1.0f + d)));
+      static_cast<__half*>(prm.out)[at] = __float2half_rn(d);
+    } else if (VK == VK_F32 || VK == VK_I64) {
+      const float s = VK == VK_I64 ? static_cast<float>(acci[i]) : accf[i];
+      float d = pow_f32<PKROOT>(s, prm.root_f);
+      if (prm.similarity) d = __fdiv_rn(1.0f, 1.0f + d);
+      static_cast<float*>(prm.out)[at] = d;
+    } else {
+      double d = pow_f64<PKROOT>(accd[i], prm.root_d);
+      if (prm.similarity) d = 1.0 / (1.0 + d);
+      static_cast<double*>(prm.out)[at] = d;
+    }
+  }
+}
+
+template <typename T, int VK, int METRIC>
+static int launch_elem(const ElemParams& prm, int pk_in, int pk_root, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>(ceil_div(prm.N, ET_N)), static_cast<unsigned>(ceil_div(prm.qrows, ET_M)));
+#define PG_EL(PI, PR) elem_tile_kernel<T, VK, METRIC, PI, PR><<<grid, 256, 0, s>>>(prm)
+  if (METRIC == 1) {
+    PG_EL(PK_ONE, PK_ONE);
+  } else {
+    // the common pairs get their own instantiation; everything else takes the powf path
+    if (pk_in == PK_TWO && pk_root == PK_SQRT) PG_EL(PK_TWO, PK_SQRT);
+    else if (pk_in == PK_ONE && pk_root == PK_ONE) PG_EL(PK_ONE, PK_ONE);
+    else if (pk_in == PK_THREE) PG_EL(PK_THREE, PK_GENERAL);
+    else if (pk_in == PK_SQRT && pk_root == PK_TWO) PG_EL(PK_SQRT, PK_TWO);
+    else PG_EL(PK_GENERAL, PK_GENERAL);
+  }
+#undef PG_EL
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+// =============================================================================
+// Ordered keys (torch.sort order: ascending, NaN last, -0 == +0)
+// =============================================================================
+__device__ __forceinline__ uint32_t key_f32(float v) {
+  if (v != v) return 0xffffffffu;
+  if (v == 0.0f) v = 0.0f;
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long key_f64(double v) {
+  if (v != v) return ~0ull;
+  if (v == 0.0) v = 0.0;
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (b >> 63) ? ~b : (b | (1ull << 63));
+}
+template <typename T> struct KeyOf;
+template <> struct KeyOf<__half> { using K = uint32_t; __device__ static K get(__half v) { return key_f32(__half2float(v)); } };
+template <> struct KeyOf<float> { using K = uint32_t; __device__ static K get(float v) { return key_f32(v); } };
+template <> struct KeyOf<int> { using K = uint32_t; __device__ static K get(int v) { return static_cast<uint32_t>(v) ^ 0x80000000u; } };
+template <> struct KeyOf<double> { using K = unsigned long long; __device__ static K get(double v) { return key_f64(v); } };
+template <> struct KeyOf<long long> {
+  using K = unsigned long long;
+  __device__ static K get(long long v) { return static_cast<unsigned long long>(v) ^ (1ull << 63); }
+};
+
+// =============================================================================
+// Stable top-k of each row: radix-select the k1-th key, gather, bitonic sort (key, idx)
+// =============================================================================
+constexpr int TK_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(TK_THREADS) tile_topk_kernel(const T* __restrict__ tile, long long N, long long ld,
+                                                                int k, int drop, int descending,
+                                                                long long* __restrict__ out_idx, T* __restrict__ out_val,
+                                                                int cap /* pow2 >= k1 */) {
+  using K = typename KeyOf<T>::K;
+  constexpr int KBITS = sizeof(K) * 8;
+  extern __shared__ __align__(16) unsigned char tk_smem[];
+  K* skey = reinterpret_cast<K*>(tk_smem);                                  // [cap]
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(tk_smem + sizeof(K) * cap);   // [cap]
+  __shared__ unsigned hist[256];
+  __shared__ K s_prefix;
+  __shared__ long long s_want;
+  __shared__ int s_less, s_eq_taken;
+  __shared__ int s_warp_cnt[TK_THREADS / 32];
+
+  const long long row = blockIdx.x;
+  const T* src = tile + static_cast<size_t>(row) * ld;
+  const int tid = threadIdx.x;
+  long long k1 = static_cast<long long>(drop) + k;
+  if (k1 > N) k1 = N;
+  const K flip = descending ? ~K(0) : K(0);
+
+  // ---- radix select: the key of rank k1 (1-based) -------------------------------------
+  if (tid == 0) { s_prefix = 0; s_want = k1; }
+  __syncthreads();
+  for (int shift = KBITS - 8; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    const K prefix = s_prefix;
+    for (long long i = tid; i < N; i += TK_THREADS) {
+      const K key = KeyOf<T>::get(src[i]) ^ flip;
+      const bool match = (shift == KBITS - 8) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match) atomicAdd(&hist[static_cast<unsigned>(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long want = s_want;
+      int dgt = 0;
+      for (; dgt < 256; ++dgt) {
+        if (want <= hist[dgt]) break;
+        want -= hist[dgt];
+      }
+      s_want = want;
+      s_prefix = prefix | (static_cast<K>(dgt) << shift);
+    }
+    __syncthreads();
+  }
+  const K kth = s_prefix;
+  const int need_eq = static_cast<int>(s_want);      // entries equal to kth to take, lowest indices first
+  const int n_less = static_cast<int>(k1) - need_eq;  // entries strictly below kth
+
+  // ---- gather ------------------------------------------------------------------------------
+  for (int i = tid; i < cap; i += TK_THREADS) { skey[i] = ~K(0); sidx[i] = 0xffffffffu; }
+  if (tid == 0) { s_less = 0; s_eq_taken = 0; }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (long long base = 0; base < N; base += TK_THREADS) {
+    const long long i = base + tid;
+    bool eq = false;
+    if (i < N) {
+      const K key = KeyOf<T>::get(src[i]) ^ flip;
+      if (key < kth) {
+        const int at = atomicAdd(&s_less, 1);
+        skey[at] = key;
+        sidx[at] = static_cast<uint32_t>(i);
+      }
+      eq = key == kth;
+    }
+    // ordered placement of the ties: ballot + block prefix sum
+    const int taken = s_eq_taken;
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < TK_THREADS / 32; ++w) {
+      const int c = s_warp_cnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (eq) {
+      const int pos = taken + before + __popc(bal & ((1u << lane) - 1u));
+      if (pos < need_eq) {
+        skey[n_less + pos] = kth;
+        sidx[n_less + pos] = static_cast<uint32_t>(i);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_eq_taken = taken + total;
+    __syncthreads();
+  }
+
+  // ---- bitonic sort of (key, idx) ---------------------------------------------------------
+  for (int size = 2; size <= cap; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < cap / 2; i += TK_THREADS) {
+        const int lo = (i / stride) * stride * 2 + (i % stride);
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const K ka = skey[lo], kb = skey[hi];
+        const uint32_t ia = sidx[lo], ib = sidx[hi];
+        const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+        if (a_gt_b == up) {
+          skey[lo] = kb; skey[hi] = ka;
+          sidx[lo] = ib; sidx[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += TK_THREADS) {
+    const int src_pos = drop + j;
+    const size_t at = static_cast<size_t>(row) * k + j;
+    if (src_pos < k1) {
+      const uint32_t ix = sidx[src_pos];
+      out_idx[at] = ix;
+      out_val[at] = src[ix];
+    } else {
+      out_idx[at] = -1;
+      out_val[at] = T(0);
+    }
+  }
+}
+
+// =============================================================================
+// Threshold -> CSR compaction
+// =============================================================================
+struct ThreshParams {
+  int cmp, swap, guard;
+  float eps_f;
+  double eps_d;
+  long long eps_i;
+  int eps_is_int;
+};
+
+__device__ __forceinline__ bool cmp_apply(int cmp, double a, double b) {
+  switch (cmp) {
+    case PG_LT: return a < b;
+    case PG_LE: return a <= b;
+    case PG_EQ: return a == b;
+    case PG_NE: return a != b;
+    case PG_GE: return a >= b;
+    default: return a > b;
+  }
+}
+// v is converted exactly to double for every supported dtype except |int64| > 2^53 (not a
+// distance).  eps was rounded to the tile dtype on the host (fp16 / fp32) as torch does.
+template <typename T> __device__ __forceinline__ double as_double(T v) { return static_cast<double>(v); }
+template <> __device__ __forceinline__ double as_double<__half>(__half v) { return static_cast<double>(__half2float(v)); }
+
+template <typename T>
+__device__ __forceinline__ bool keep_value(T v, const ThreshParams& tp) {
+  if (sizeof(T) == 1) return v != T(0);  // mask input
+  const double x = as_double<T>(v);
+  const bool c = tp.swap ? cmp_apply(tp.cmp, tp.eps_d, x) : cmp_apply(tp.cmp, x, tp.eps_d);
+  if (tp.guard == 1) return c && (x > 0.0);
+  if (tp.guard == 2) return c && (x < 1.0);
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tile_thresh_count_kernel(const T* __restrict__ tile, long long N, long long ld,
+                                                                 ThreshParams tp, long long* __restrict__ counts) {
+  const long long row = blockIdx.x;
+  const T* src = tile + static_cast<size_t>(row) * ld;
+  int c = 0;
+  for (long long i = threadIdx.x; i < N; i += 256) c += keep_value<T>(src[i], tp) ? 1 : 0;
+  __shared__ int wsum[8];
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    counts[row] = t;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tile_thresh_fill_kernel(const T* __restrict__ tile, long long N, long long ld,
+                                                                ThreshParams tp, const long long* __restrict__ indptr,
+                                                                long long* __restrict__ out_idx, T* __restrict__ out_val) {
+  const long long row = blockIdx.x;
+  const T* src = tile + static_cast<size_t>(row) * ld;
+  __shared__ int wcnt[8];
+  __shared__ long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = indptr[row];
+  __syncthreads();
+  for (long long base = 0; base < N; base += 256) {
+    const long long i = base + threadIdx.x;
+    T v = T(0);
+    bool keep = false;
+    if (i < N) { v = src[i]; keep = keep_value<T>(v, tp); }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = wcnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    const long long start = s_base;
+    if (keep) {
+      const long long at = start + before + __popc(bal & ((1u << lane) - 1u));
+      out_idx[at] = i;
+      if (out_val) out_val[at] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = start + total;
+    __syncthreads();
+  }
+}
+
+static int fill_thresh(ThreshParams& tp, int dtype, int cmp, double eps, int swap, int guard) {
+  PG_CHECK_ARG(cmp >= PG_LT && cmp <= PG_GT, "bad comparison opcode %d", cmp);
+  PG_CHECK_ARG(guard >= 0 && guard <= 2, "bad guard %d", guard);
+  tp.cmp = cmp;
+  tp.swap = swap;
+  tp.guard = guard;
+  // a python scalar is compared in the tensor's dtype: round eps the way torch does
+  if (dtype == PG_F16) tp.eps_d = static_cast<double>(__half2float(__float2half_rn(static_cast<float>(eps))));
+  else if (dtype == PG_F32) tp.eps_d = static_cast<double>(static_cast<float>(eps));
+  else tp.eps_d = eps;
+  tp.eps_f = static_cast<float>(tp.eps_d);
+  tp.eps_i = static_cast<long long>(eps);
+  tp.eps_is_int = 0;
+  return PG_OK;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_minkowski_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_t q0, int64_t qrows, int D, int dtype,
+                      double p, int similarity, void* out, int64_t ld, void* stream) {
+  PG_CHECK_ARG(X && Y && out, "null pointer");
+  PG_CHECK_ARG(N > 0 && M > 0 && D > 0, "empty operand");
+  PG_CHECK_ARG(q0 >= 0 && qrows > 0 && q0 + qrows <= M, "query range outside Y");
+  PG_CHECK_ARG(ld >= N, "leading dimension too small");
+  PG_CHECK_ARG(p != 0.0, "p must be non-zero");
+  ElemParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.X = X; prm.N = N; prm.Y = Y; prm.q0 = q0; prm.qrows = qrows; prm.D = D;
+  prm.out = out; prm.ld = ld; prm.similarity = similarity;
+  const double root = 1.0 / p;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == PG_F16) {
+    // exp_scalar.to<Half>(): both exponents are rounded to fp16 before use
+    prm.p_f = __half2float(__float2half_rn(static_cast<float>(p)));
+    prm.root_f = __half2float(__float2half_rn(static_cast<float>(root)));
+    return launch_elem<__half, VK_F16, 0>(prm, pow_kind(prm.p_f), pow_kind(prm.root_f), s);
+  }
+  if (dtype == PG_F32) {
+    prm.p_f = static_cast<float>(p);
+    prm.root_f = static_cast<float>(root);
+    return launch_elem<float, VK_F32, 0>(prm, pow_kind(prm.p_f), pow_kind(prm.root_f), s);
+  }
+  if (dtype == PG_F64) {
+    prm.p_d = p;
+    prm.root_d = root;
+    return launch_elem<double, VK_F64, 0>(prm, pow_kind(p), pow_kind(root), s);
+  }
+  if (dtype == PG_I64) {
+    PG_CHECK_ARG(p == static_cast<double>(static_cast<int>(p)) && p > 0,
+                 "integer inputs need a positive integer p (promote to float32 for other exponents)");
+    prm.p_int = static_cast<int>(p);
+    prm.root_f = static_cast<float>(root);
+    // the integer power is exact; only the root kind matters for the instantiation choice
+    const int pkr = pow_kind(prm.root_f);
+    if (pkr == PK_SQRT) return launch_elem<long long, VK_I64, 0>(prm, PK_TWO, PK_SQRT, s);
+    if (pkr == PK_ONE) return launch_elem<long long, VK_I64, 0>(prm, PK_ONE, PK_ONE, s);
+    return launch_elem<long long, VK_I64, 0>(prm, PK_GENERAL, PK_GENERAL, s);
+  }
+  set_error("minkowski tile: unsupported dtype %d", dtype);
+  return PG_ERR_INVALID;
+}
+
+int pg_hamming_values_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_t q0, int64_t qrows, int D,
+                           int dtype, int weight, void* out, int64_t ld, void* stream) {
+  PG_CHECK_ARG(X && Y && out, "null pointer");
+  PG_CHECK_ARG(N > 0 && M > 0 && D > 0, "empty operand");
+  PG_CHECK_ARG(q0 >= 0 && qrows > 0 && q0 + qrows <= M, "query range outside Y");
+  PG_CHECK_ARG(ld >= N, "leading dimension too small");
+  ElemParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.X = X; prm.N = N; prm.Y = Y; prm.q0 = q0; prm.qrows = qrows; prm.D = D;
+  prm.out = out; prm.ld = ld; prm.weight = weight;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case PG_F16: return launch_elem<__half, VK_F16, 1>(prm, 0, 0, s);
+    case PG_F32: return launch_elem<float, VK_F32, 1>(prm, 0, 0, s);
+    case PG_F64: return launch_elem<double, VK_F64, 1>(prm, 0, 0, s);
+    case PG_I64: return launch_elem<long long, VK_I64, 1>(prm, 0, 0, s);
+  }
+  set_error("hamming values tile: unsupported dtype %d", dtype);
+  return PG_ERR_INVALID;
+}
+
+int pg_tile_topk(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld, int k, int drop, int descending,
+                 int64_t* out_idx, void* out_val, void* stream) {
+  PG_CHECK_ARG(tile && out_idx && out_val, "null pointer");
+  PG_CHECK_ARG(rows > 0 && N > 0 && ld >= N, "bad tile shape");
+  PG_CHECK_ARG(N < (1ll << 32), "row too long for 32-bit indices");
+  PG_CHECK_ARG(k >= 1 && drop >= 0, "k must be >= 1 and drop >= 0");
+  long long k1 = static_cast<long long>(k) + drop;
+  if (k1 > N) k1 = N;
+  int cap = 2;
+  while (cap < k1) cap <<= 1;
+  if (cap > 4096) { set_error("k=%d too large for the shared-memory sort (max 4096 incl. drop)", k); return PG_ERR_UNSUPPORTED; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define PG_TK(T)                                                                                              \
+  do {                                                                                                        \
+    const size_t smem = (sizeof(KeyOf<T>::K) + 4) * static_cast<size_t>(cap);                                 \
+    PG_CUDA(cudaFuncSetAttribute(tile_topk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    tile_topk_kernel<T><<<static_cast<unsigned>(rows), TK_THREADS, smem, s>>>(                                \
+        static_cast<const T*>(tile), N, ld, k, drop, descending, reinterpret_cast<long long*>(out_idx),        \
+        static_cast<T*>(out_val), cap);                                                                       \
+  } while (0)
+  switch (dtype) {
+    case PG_F16: PG_TK(__half); break;
+    case PG_F32: PG_TK(float); break;
+    case PG_F64: PG_TK(double); break;
+    case PG_I32: PG_TK(int); break;
+    case PG_I64: PG_TK(long long); break;
+    default: set_error("tile top-k: unsupported dtype %d", dtype); return PG_ERR_INVALID;
+  }
+#undef PG_TK
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_tile_threshold_count(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld, int cmp, double eps,
+                            int swap, int guard, int64_t* counts, void* stream) {
+  PG_CHECK_ARG(tile && counts, "null pointer");
+  PG_CHECK_ARG(rows > 0 && N > 0 && ld >= N, "bad tile shape");
+  ThreshParams tp;
+  int rc = fill_thresh(tp, dtype, cmp, eps, swap, guard);
+  if (rc != PG_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define PG_TC(T) \
+  tile_thresh_count_kernel<T><<<static_cast<unsigned>(rows), 256, 0, s>>>(static_cast<const T*>(tile), N, ld, tp, \
+                                                                          reinterpret_cast<long long*>(counts))
+  switch (dtype) {
+    case PG_U8: PG_TC(uint8_t); break;
+    case PG_F16: PG_TC(__half); break;
+    case PG_F32: PG_TC(float); break;
+    case PG_F64: PG_TC(double); break;
+    case PG_I32: PG_TC(int); break;
+    case PG_I64: PG_TC(long long); break;
+    default: set_error("tile threshold: unsupported dtype %d", dtype); return PG_ERR_INVALID;
+  }
+#undef PG_TC
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_tile_threshold_fill(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld, int cmp, double eps,
+                           int swap, int guard, const int64_t* indptr, int64_t* out_idx, void* out_val, void* stream) {
+  PG_CHECK_ARG(tile && indptr && out_idx, "null pointer");
+  PG_CHECK_ARG(rows > 0 && N > 0 && ld >= N, "bad tile shape");
+  ThreshParams tp;
+  int rc = fill_thresh(tp, dtype, cmp, eps, swap, guard);
+  if (rc != PG_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define PG_TF(T)                                                                                          \
+  tile_thresh_fill_kernel<T><<<static_cast<unsigned>(rows), 256, 0, s>>>(                                 \
+      static_cast<const T*>(tile), N, ld, tp, reinterpret_cast<const long long*>(indptr),                 \
+      reinterpret_cast<long long*>(out_idx), static_cast<T*>(out_val))
+  switch (dtype) {
+    case PG_U8: PG_TF(uint8_t); break;
+    case PG_F16: PG_TF(__half); break;
+    case PG_F32: PG_TF(float); break;
+    case PG_F64: PG_TF(double); break;
+    case PG_I32: PG_TF(int); break;
+    case PG_I64: PG_TF(long long); break;
+    default: set_error("tile threshold: unsupported dtype %d", dtype); return PG_ERR_INVALID;
+  }
+#undef PG_TF
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+}  // extern "C"

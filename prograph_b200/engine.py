@@ -1,0 +1,291 @@
+"""Device engine: torch owns memory and streams, every computation is a C-ABI call into
+libprograph_b200.so (hand-written sm_100a kernels).  No CPU fallback anywhere.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_PG_DTYPE = {
+    torch.uint8: L.U8, torch.int16: L.I16, torch.int32: L.I32, torch.int64: L.I64,
+    torch.float16: L.F16, torch.float32: L.F32, torch.float64: L.F64, torch.bool: L.U8,
+}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _host_u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class PackedTable:
+    """Bit-plane token table on the device: int32 tensor [rows_padded, planes, words]."""
+    __slots__ = ("data", "rows", "L", "planes", "words")
+
+    def __init__(self, data, rows, L_, planes, words):
+        self.data, self.rows, self.L, self.planes, self.words = data, rows, L_, planes, words
+
+    def row(self, i):
+        """One packed row (planes*words words) as a device tensor."""
+        return self.data[i].reshape(-1)
+
+
+class CudaEngine:
+    """One engine per process/GPU.  ``device`` defaults to ``cuda:LOCAL_RANK`` as set by the
+    launcher, i.e. the current torch device."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("prograph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+
+    # ---- plumbing -----------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=None):
+        """numpy / torch (any device) -> contiguous tensor on this engine's device."""
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        elif not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a))
+        if a.dtype == torch.bool:
+            a = a.to(torch.uint8)
+        a = a.to(self.device, non_blocking=True)
+        if dtype is not None and a.dtype != dtype:
+            a = a.to(dtype)
+        return a.contiguous()
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def launch_count(self, reset=False):
+        return int(self.lib.pg_launch_count(1 if reset else 0))
+
+    # ---- packed tables --------------------------------------------------------------
+    def packed_words(self, L_):
+        return int(self.lib.pg_packed_words(int(L_)))
+
+    def pack(self, tokens, planes=None, words=None):
+        """tokens: (N, L) integer-valued array/tensor.  Returns a PackedTable, raising
+        OverflowError when a value is negative, fractional or >= 2**planes."""
+        t = self.to_device(tokens)
+        if t.dim() != 2 or t.shape[0] == 0 or t.shape[1] == 0:
+            raise ValueError("pack expects a non-empty (N, L) array")
+        if t.dtype not in _PG_DTYPE or t.dtype == torch.bool:
+            t = t.to(torch.int64)
+        N, L_ = int(t.shape[0]), int(t.shape[1])
+        words = self.packed_words(L_) if words is None else int(words)
+        tries = (5, 8) if planes is None else (int(planes),)
+        flag = self.empty((1,), torch.int32)
+        for pl in tries:
+            rows_pad = int(self.lib.pg_packed_rows(N))
+            out = self.empty((rows_pad, pl, words), torch.int32)
+            flag.zero_()
+            L.check(self.lib.pg_pack_tokens(_ptr(t), _PG_DTYPE[t.dtype], N, L_, int(t.stride(0)), _ptr(out), pl, words,
+                                            _ptr(flag), self._stream()))
+            if int(flag.item()) == 0:
+                return PackedTable(out, N, L_, pl, words)
+        raise OverflowError("values are not integer tokens in [0, 256): the bit-plane path does not apply")
+
+    # ---- fused Hamming sweeps -----------------------------------------------------------
+    def _workspace(self, rows, stream_rows, words, k1):
+        nbytes = int(self.lib.pg_sweep_workspace_bytes(int(rows), int(stream_rows), int(words), int(k1)))
+        return self.empty((nbytes,), torch.uint8), nbytes
+
+    @staticmethod
+    def _check_pair(own, stream):
+        if own.planes != stream.planes or own.words != stream.words:
+            raise ValueError("packed operands must share planes and words")
+
+    def hamming_knn(self, own, row0, rows, stream, k, drop=1, similarity=False):
+        """prograph.py:755-765 for own rows [row0,row0+rows) against `stream`: sorted
+        positions [drop, drop+k) of every row in (distance, index) order."""
+        self._check_pair(own, stream)
+        weight = L.W_SIM_F32 if similarity else L.W_I64
+        idx = self.empty((rows, k), torch.int64)
+        w = self.empty((rows, k), torch.float32 if similarity else torch.int64)
+        ws, nbytes = self._workspace(rows, stream.rows, own.words, k + drop)
+        L.check(self.lib.pg_hamming_knn(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data), stream.rows,
+                                        own.planes, own.words, int(k), int(drop), weight, _ptr(idx), _ptr(w), _ptr(ws),
+                                        nbytes, self._stream()))
+        return idx, w
+
+    def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
+        """prograph.py:731-753 for own rows [row0,row0+rows): CSR (indptr, idx, w) of the
+        stream rows whose distance d has bit d set in `lut` (uint32 words, host)."""
+        self._check_pair(own, stream)
+        lut, lut_p = _host_u32(lut)
+        counts = self.empty((rows,), torch.int64)
+        ws, nbytes = self._workspace(rows, stream.rows, own.words, 1)
+        L.check(self.lib.pg_hamming_eps_count(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
+                                              stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(counts),
+                                              _ptr(ws), nbytes, self._stream()))
+        indptr = self.exclusive_scan(counts)
+        nnz = int(indptr[-1].item())
+        weight = L.W_SIM_F32 if similarity else L.W_I64
+        idx = self.empty((nnz,), torch.int64)
+        w = self.empty((nnz,), torch.float32 if similarity else torch.int64)
+        if nnz:
+            L.check(self.lib.pg_hamming_eps_fill(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
+                                                 stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(indptr),
+                                                 weight, _ptr(idx), _ptr(w), _ptr(ws), nbytes, self._stream()))
+        return indptr, idx, w
+
+    def hamming_tile(self, data, queries, q0=0, qrows=None, weight=L.W_I64):
+        """hamming.py:34-38: (qrows, N) distances of query rows [q0,q0+qrows) vs all data rows."""
+        self._check_pair(data, queries)
+        qrows = queries.rows - q0 if qrows is None else qrows
+        dt = {L.W_I64: torch.int64, L.W_SIM_F32: torch.float32, L.W_I32: torch.int32}[weight]
+        out = self.empty((qrows, data.rows), dt)
+        L.check(self.lib.pg_hamming_tile(_ptr(data.data), data.rows, _ptr(queries.data), queries.rows, int(q0),
+                                         int(qrows), data.planes, data.words, weight, _ptr(out), data.rows,
+                                         self._stream()))
+        return out
+
+    def exclusive_scan(self, counts):
+        out = self.empty((counts.numel() + 1,), torch.int64)
+        L.check(self.lib.pg_exclusive_scan_i64(_ptr(counts), counts.numel(), _ptr(out), self._stream()))
+        return out
+
+    # ---- element-wise tiles ----------------------------------------------------------------
+    def minkowski_tile(self, X, Y, q0, qrows, p=2, similarity=False):
+        """minkowski.py:36-40 on device tensors X (N,D), Y (M,D) of one dtype in
+        {float16, float32, float64, int64}."""
+        assert X.dtype == Y.dtype and X.shape[1] == Y.shape[1]
+        out_dt = {torch.float16: torch.float16, torch.float32: torch.float32, torch.int64: torch.float32,
+                  torch.float64: torch.float64}[X.dtype]
+        out = self.empty((qrows, X.shape[0]), out_dt)
+        L.check(self.lib.pg_minkowski_tile(_ptr(X), X.shape[0], _ptr(Y), Y.shape[0], int(q0), int(qrows), X.shape[1],
+                                           _PG_DTYPE[X.dtype], float(p), 1 if similarity else 0, _ptr(out), X.shape[0],
+                                           self._stream()))
+        return out
+
+    def hamming_values_tile(self, X, Y, q0, qrows, similarity=False):
+        """hamming.py:34-38 on arbitrary numeric values (not packable as tokens)."""
+        assert X.dtype == Y.dtype and X.shape[1] == Y.shape[1]
+        weight = L.W_SIM_F32 if similarity else L.W_I64
+        out = self.empty((qrows, X.shape[0]), torch.float32 if similarity else torch.int64)
+        L.check(self.lib.pg_hamming_values_tile(_ptr(X), X.shape[0], _ptr(Y), Y.shape[0], int(q0), int(qrows),
+                                                X.shape[1], _PG_DTYPE[X.dtype], weight, _ptr(out), X.shape[0],
+                                                self._stream()))
+        return out
+
+    # ---- tile consumers ----------------------------------------------------------------------
+    def tile_topk(self, tile, k, drop=1, descending=False):
+        rows, N = tile.shape
+        idx = self.empty((rows, k), torch.int64)
+        val = self.empty((rows, k), tile.dtype)
+        L.check(self.lib.pg_tile_topk(_ptr(tile), _PG_DTYPE[tile.dtype], rows, N, int(tile.stride(0)), int(k), int(drop),
+                                      1 if descending else 0, _ptr(idx), _ptr(val), self._stream()))
+        return idx, val
+
+    def tile_threshold(self, tile, cmp, eps, swap=False, guard=0, values=True):
+        """CSR of the tile entries passing the threshold test (see pg_tile_threshold_count)."""
+        rows, N = tile.shape
+        dt = _PG_DTYPE[tile.dtype]
+        counts = self.empty((rows,), torch.int64)
+        L.check(self.lib.pg_tile_threshold_count(_ptr(tile), dt, rows, N, int(tile.stride(0)), int(cmp), float(eps),
+                                                 1 if swap else 0, int(guard), _ptr(counts), self._stream()))
+        indptr = self.exclusive_scan(counts)
+        nnz = int(indptr[-1].item())
+        idx = self.empty((nnz,), torch.int64)
+        val = self.empty((nnz,), tile.dtype) if values else None
+        if nnz:
+            L.check(self.lib.pg_tile_threshold_fill(_ptr(tile), dt, rows, N, int(tile.stride(0)), int(cmp), float(eps),
+                                                    1 if swap else 0, int(guard), _ptr(indptr), _ptr(idx), _ptr(val),
+                                                    self._stream()))
+        return indptr, idx, val
+
+    # ---- masks ------------------------------------------------------------------------------
+    def mutant_bits(self, table, ref):
+        """ref: packed row tensor (planes*words int32) on the device."""
+        mut = self.empty((table.rows, table.words), torch.int32)
+        L.check(self.lib.pg_mutant_bits(_ptr(table.data), table.rows, table.planes, table.words, _ptr(ref), _ptr(mut),
+                                        self._stream()))
+        return mut
+
+    def mutant_bool(self, table, ref):
+        out = self.empty((table.rows, table.L), torch.uint8)
+        L.check(self.lib.pg_mutant_bool(_ptr(table.data), table.rows, table.planes, table.words, table.L, _ptr(ref),
+                                        _ptr(out), self._stream()))
+        return out
+
+    def mutant_any(self, mut):
+        out = self.empty((mut.shape[1],), torch.int32)
+        L.check(self.lib.pg_mutant_any(_ptr(mut), mut.shape[0], mut.shape[1], _ptr(out), self._stream()))
+        return out.cpu().numpy().view(np.uint32)
+
+    def select_rows(self, mut, dist_lut=None, inside=None, outside=None, pos_mode=0):
+        flag = self.empty((mut.shape[0],), torch.uint8)
+        lut_p, lut_n, keep = C.c_void_p(0), 0, []
+        if dist_lut is not None:
+            a, lut_p = _host_u32(dist_lut)
+            lut_n = len(a)
+            keep.append(a)
+        in_p = C.c_void_p(0)
+        if inside is not None:
+            b, in_p = _host_u32(inside)
+            keep.append(b)
+        out_p = C.c_void_p(0)
+        if outside is not None:
+            c, out_p = _host_u32(outside)
+            keep.append(c)
+        L.check(self.lib.pg_select_rows(_ptr(mut), mut.shape[0], mut.shape[1], lut_p, lut_n, in_p, out_p,
+                                        int(pos_mode), _ptr(flag), self._stream()))
+        return flag
+
+    def flag_indices(self, flag):
+        n = flag.numel()
+        out = self.empty((n,), torch.int64)
+        cnt = self.empty((1,), torch.int64)
+        L.check(self.lib.pg_flag_indices(_ptr(flag), n, _ptr(out), _ptr(cnt), self._stream()))
+        return out[: int(cnt.item())]
+
+    def distance_hist(self, mut):
+        hist = torch.zeros((mut.shape[1] * 32 + 1,), dtype=torch.int64, device=self.device)
+        L.check(self.lib.pg_distance_hist(_ptr(mut), mut.shape[0], mut.shape[1], _ptr(hist), self._stream()))
+        return hist.cpu().numpy()
+
+    # ---- measurement -------------------------------------------------------------------------
+    def int_peak(self, mix=0, iters=4096):
+        ops, ms = C.c_double(0), C.c_double(0)
+        L.check(self.lib.pg_measure_int_peak(int(mix), int(iters), C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+    def time_sweeps(self, enable=True):
+        self.lib.pg_time_sweeps(1 if enable else 0)
+
+    def sweep_time(self, reset=True):
+        ms, n = C.c_double(0), C.c_int64(0)
+        self.lib.pg_sweep_time(C.byref(ms), C.byref(n), 1 if reset else 0)
+        return ms.value, n.value
+
+
+_ENGINE = None
+
+
+def get_engine():
+    """The process-wide CUDA engine (created on first use)."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = CudaEngine()
+    return _ENGINE
+
+
+def set_engine(engine):
+    """Install another engine object (tests inject a checker-backed one to exercise the
+    host logic on machines without a GPU).  Returns the previous engine."""
+    global _ENGINE
+    prev, _ENGINE = _ENGINE, engine
+    return prev

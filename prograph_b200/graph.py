@@ -1,0 +1,294 @@
+"""Graph construction on the device: threshold (epsilon) and k-nearest-neighbour adjacency.
+
+Host-side mirror of ``Prograph.build_graph`` (prograph/prograph.py:656-765) and of the
+row batching / per-row list assembly around it (get_every_n :617-624, prod_neighbours
+:626-654, merge/fill :743-753).  The reference loops over batches of 8 query rows,
+materialises an (8, N, L) temporary per batch, sorts or scans it and copies every batch
+back to the host; here one fused sweep per build produces CSR arrays on the device and the
+per-row tuples the reference returns are O(N) views into them.
+
+Dispatch:
+  * ``distance is prograph_b200.distance.hamming`` and the representation is integer tokens
+    -> fused bit-plane sweeps (pg_hamming_knn / pg_hamming_eps_*), the N x N matrix never
+    exists;
+  * ``minkowski`` (or hamming on non-token values) -> element-wise tile kernels per row
+    block + the tile consumers (pg_tile_topk / pg_tile_threshold_*);
+  * any other callable honouring the ``fn(X, Y, similarity=...) -> (M, N)`` protocol is
+    called per row block exactly as the reference calls it and its device tile goes
+    through the same consumers.
+Rows are sharded across the ranks of an initialised torch.distributed group; every rank
+ends up with the whole graph (all-gather of the result shards).
+"""
+import functools
+import operator
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import shard as _shard
+from .distance.hamming import hamming, value_dtype
+from .distance.minkowski import minkowski, staged_dtype
+from .engine import get_engine
+
+_CMP_CODES = {operator.lt: L.LT, operator.le: L.LE, operator.eq: L.EQ,
+              operator.ne: L.NE, operator.ge: L.GE, operator.gt: L.GT}
+
+TILE_BUDGET_BYTES = 512 << 20   # materialised tile slab for the non-fused metrics
+
+
+# ---------------------------------------------------------------------------------
+# results
+# ---------------------------------------------------------------------------------
+class NeighbourTable:
+    """Adjacency in CSR form on the host: row r owns idx[indptr[r]:indptr[r+1]] (int64,
+    ascending for epsilon graphs, (distance, index) order for kNN) and the matching w."""
+
+    def __init__(self, indptr, idx, w):
+        self.indptr, self.idx, self.w = indptr, idx, w
+
+    @property
+    def n_rows(self):
+        return len(self.indptr) - 1
+
+    def degrees(self):
+        return np.diff(self.indptr)
+
+    def as_list(self):
+        """The reference's return value: a list of (indices, weights) tuples, one per row
+        (prograph.py:753,764).  Rows without neighbours carry two empty *int* arrays even for
+        float metrics (prograph.py:753)."""
+        ip, idx, w = self.indptr, self.idx, self.w
+        empty = (np.array([], dtype=int), np.array([], dtype=int))
+        out = [None] * self.n_rows
+        for r in range(self.n_rows):
+            a, b = ip[r], ip[r + 1]
+            out[r] = (idx[a:b], w[a:b]) if b > a else empty
+        return out
+
+
+class KnnTable:
+    """Fixed-degree kNN result: idx (N, k) int64 and w (N, k)."""
+
+    def __init__(self, idx, w):
+        self.idx, self.w = idx, w
+
+    @property
+    def n_rows(self):
+        return self.idx.shape[0]
+
+    def as_list(self):
+        return list(zip(self.idx, self.w))      # row views, prograph.py:764
+
+    def to_csr(self):
+        n, k = self.idx.shape
+        return NeighbourTable(np.arange(0, (n + 1) * k, k, dtype=np.int64), self.idx.reshape(-1), self.w.reshape(-1))
+
+
+# ---------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------
+def as_matrix(rep):
+    """A representation column (pandas Series of row arrays, list of rows, 2-D array or
+    tensor) as one 2-D array."""
+    if isinstance(rep, torch.Tensor):
+        return rep
+    if hasattr(rep, "to_numpy") and not isinstance(rep, np.ndarray):
+        rep = rep.to_numpy()
+    if isinstance(rep, np.ndarray) and rep.dtype != object:
+        out = rep
+    else:
+        out = np.stack([np.asarray(r) for r in rep])
+    if out.ndim == 1:
+        out = out.reshape(-1, 1)
+    return out
+
+
+def validate(eps, k):
+    """Argument checks of prograph.py:714-718 (truthiness: eps=0 and k=0 are rejected)."""
+    if operator.xor(bool(eps), bool(k)) is False:
+        raise ValueError("Epsilon or K must be provided, but both cannot be as they are different "
+                         "methods of graph construction.")
+    if k is not None and not isinstance(k, int):
+        raise TypeError("K must be provided as an integer.")
+
+
+def distance_lut(max_d, comp, eps, similarity, guard=True):
+    """Truth table over d = 0..max_d of the reference's edge test, evaluated with the same
+    torch expressions the reference applies to the distance tensor:
+        comp(d, eps) & (d > 0)                         prograph.py:736
+        comp(eps, s) & (s < 1),  s = 1/(1+d)           prograph.py:734 (similarity)
+    ``guard=False`` drops the second factor (calc_neighbours, prograph.py:544).  Returned as
+    uint32 words, bit d of the table = edge."""
+    d = torch.arange(max_d + 1, dtype=torch.int64)
+    if similarity:
+        s = 1 / (1 + d)
+        keep = comp(eps, s)
+        if guard:
+            keep = keep & (s < 1)
+    else:
+        keep = comp(d, eps)
+        if guard:
+            keep = keep & (d > 0)
+    keep = torch.as_tensor(keep)
+    if keep.shape != d.shape:
+        raise TypeError("comp must be an element-wise comparison such as operator.le")
+    bits = keep.to(torch.bool).numpy()
+    words = np.zeros((max_d + 1 + 31) // 32, dtype=np.uint32)
+    for i in np.nonzero(bits)[0]:
+        words[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    return words
+
+
+def _metric_kind(distance):
+    """('hamming'|'minkowski'|'callable', p)"""
+    fn, p = distance, 2
+    if isinstance(distance, functools.partial):
+        fn = distance.func
+        p = distance.keywords.get("p", distance.args[0] if distance.args else 2)
+        if len(distance.args) > 1 or set(distance.keywords) - {"p"}:
+            return "callable", None
+    if fn is hamming:
+        return "hamming", None
+    if fn is minkowski:
+        return "minkowski", p
+    return "callable", None
+
+
+def _to_host(t):
+    return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+# ---------------------------------------------------------------------------------
+# fused Hamming path
+# ---------------------------------------------------------------------------------
+def hamming_knn_device(eng, own, stream, k, similarity, row0, rows):
+    """kNN rows [row0,row0+rows) of `own` against `stream` (both PackedTable)."""
+    kk = min(k, stream.rows - 1)          # [:, 1:k+1] of a row of N entries
+    if kk <= 0:
+        wdt = torch.float32 if similarity else torch.int64
+        return eng.empty((rows, 0), torch.int64), eng.empty((rows, 0), wdt)
+    return eng.hamming_knn(own, row0, rows, stream, kk, drop=1, similarity=similarity)
+
+
+def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows):
+    return eng.hamming_eps(own, row0, rows, stream, lut, similarity=similarity)
+
+
+# ---------------------------------------------------------------------------------
+# tile path (minkowski, hamming on values, user callables)
+# ---------------------------------------------------------------------------------
+def _tile_rows(n_cols, itemsize, batch_size):
+    rows = max(1, TILE_BUDGET_BYTES // max(1, n_cols * itemsize))
+    return int(max(batch_size, min(rows, 4096)))
+
+
+def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows):
+    """Yield (b0, tile) with tile = distance(X, X[b0:b1]) on the device, (b1-b0, N)."""
+    n = X.shape[0]
+    if kind == "callable":
+        step = batch_size                  # the reference's own batching, prograph.py:731
+    else:
+        step = _tile_rows(n, 8, batch_size)
+    for b0 in range(row0, row0 + rows, step):
+        b1 = min(b0 + step, row0 + rows)
+        if kind == "minkowski":
+            tile = eng.minkowski_tile(X, X, b0, b1 - b0, p=p, similarity=similarity)
+        elif kind == "hamming":
+            tile = eng.hamming_values_tile(X, X, b0, b1 - b0, similarity=similarity)
+        else:
+            tile = torch.as_tensor(distance(X, X[b0:b1], similarity=similarity))
+            if not tile.is_cuda:
+                tile = tile.to(eng.device)
+            tile = tile.contiguous()
+            if tile.dtype == torch.bfloat16:
+                tile = tile.to(torch.float32)
+        yield b0, tile
+
+
+def _tile_knn(eng, tiles, k, similarity, n):
+    kk = min(k, n - 1)
+    idxs, ws = [], []
+    for _, tile in tiles:
+        if kk <= 0:
+            idxs.append(eng.empty((tile.shape[0], 0), torch.int64))
+            ws.append(eng.empty((tile.shape[0], 0), tile.dtype))
+            continue
+        i, w = eng.tile_topk(tile, kk, drop=1, descending=similarity)
+        idxs.append(i)
+        ws.append(w)
+    return torch.cat(idxs), torch.cat(ws)
+
+
+def _tile_eps(eng, tiles, eps, comp, similarity):
+    code = _CMP_CODES.get(comp)
+    counts, idxs, ws = [], [], []
+    for _, tile in tiles:
+        if code is not None:
+            ip, i, w = eng.tile_threshold(tile, code, eps, swap=similarity, guard=2 if similarity else 1)
+        else:
+            # arbitrary comparison callables are evaluated on the device tile by torch exactly as
+            # the reference does (prograph.py:734-736); the compaction is ours
+            mask = (comp(eps, tile) & (tile < 1)) if similarity else (comp(tile, eps) & (tile > 0))
+            ip, i, _ = eng.tile_threshold(mask.to(torch.uint8).contiguous(), L.NE, 0.0, values=False)
+            rows_of = torch.repeat_interleave(torch.arange(tile.shape[0], device=tile.device), ip[1:] - ip[:-1])
+            w = tile[rows_of, i]
+        counts.append(ip[1:] - ip[:-1])
+        idxs.append(i)
+        ws.append(w)
+    counts = torch.cat(counts)
+    indptr = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=counts.device)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    return indptr, torch.cat(idxs), torch.cat(ws)
+
+
+# ---------------------------------------------------------------------------------
+# public entry
+# ---------------------------------------------------------------------------------
+def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, comp=operator.le,
+                     batch_size=8, idxs=None, engine=None, group=None):
+    """Device implementation of ``Prograph.build_graph`` (prograph.py:656-765) on a
+    representation matrix.  Returns a NeighbourTable (epsilon) or KnnTable (k)."""
+    validate(eps, k)
+    if similarity and eps:
+        eps = 1 / (1 + eps)                                   # prograph.py:720-721
+    eng = engine if engine is not None else get_engine()
+    X = as_matrix(rep)
+    if idxs is not None:
+        X = X[idxs, :] if not isinstance(idxs, type(Ellipsis)) else X   # indices relative to the subset
+    if X.shape[0] == 0:
+        raise ValueError("empty representation")
+    n = X.shape[0]
+    kind, p = _metric_kind(distance)
+    rank, world = _shard.rank_world(group)
+    row0, rows = _shard.row_range(n, rank, world)
+
+    packed = None
+    if kind == "hamming":
+        try:
+            packed = eng.pack(X)
+            if packed.words > 8:
+                packed = None
+        except OverflowError:
+            packed = None
+
+    if packed is not None:
+        if eps:
+            lut = distance_lut(packed.words * 32, comp, eps, similarity)
+            part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
+        else:
+            part = hamming_knn_device(eng, packed, packed, k, similarity, row0, rows) if rows else None
+    else:
+        # prograph.py:726: every representation is rounded to fp16 before the metric sees it
+        Xh = eng.to_device(X).to(torch.float16)
+        tiles = _tiles(eng, Xh, kind, p, distance, similarity, batch_size, row0, rows)
+        if eps:
+            part = _tile_eps(eng, tiles, eps, comp, similarity) if rows else None
+        else:
+            part = _tile_knn(eng, tiles, k, similarity, n) if rows else None
+
+    if eps:
+        indptr, idx, w = _shard.gather_csr(part, n, rank, world, group, eng)
+        return NeighbourTable(_to_host(indptr), _to_host(idx), _to_host(w))
+    idx, w = _shard.gather_rows(part, n, rank, world, group, eng)
+    return KnnTable(_to_host(idx), _to_host(w))

@@ -1,0 +1,173 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, and the host
+logic (truth tables, CSR views, row sharding, result gathering over gloo) is right.  No
+kernel is launched here."""
+import operator
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from prograph_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "prograph_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pg_version() >= 100
+    # geometry helpers are pure host functions
+    assert [lib.pg_packed_words(L) for L in (1, 32, 33, 56, 65, 128, 129, 256, 257, 600)] == \
+        [1, 1, 2, 2, 4, 4, 8, 8, 16, 24]
+    assert lib.pg_packed_rows(1) == 512 and lib.pg_packed_rows(1_000_000) == 1_000_448
+    assert lib.pg_packed_bytes(1000, 256, 5) == 1024 * 5 * 8 * 4
+
+
+def test_argument_errors_map_to_reference_exceptions():
+    """Bad arguments are rejected on the host side of the ABI, before any launch."""
+    from prograph_b200 import _lib
+    lib = _lib.load()
+    rc = lib.pg_pack_tokens(None, 0, 10, 10, 10, None, 5, 1, None, None)
+    assert rc == _lib.ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    assert "null" in _lib.last_error()
+    rc = lib.pg_hamming_knn(None, 10, 0, 10, None, 10, 5, 8, 16, 1, 0, None, None, None, 0, None)
+    assert rc == _lib.ERR_INVALID
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from prograph_b200.engine import CudaEngine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CudaEngine()
+    import prograph_b200
+    with pytest.raises(RuntimeError):
+        prograph_b200.hamming(np.ones((2, 3)), np.ones((1, 3)))
+
+
+def test_clean_input_contract():
+    from prograph_b200 import clean_input
+    X, Y = clean_input(torch.tensor([4, 5, 6]), torch.tensor([[1, 2, 3, 4, 5]]))
+    assert X.shape == (1, 5) and Y.shape == (1, 5) and X[0, 3:].tolist() == [0, 0]
+    with pytest.raises(ValueError):
+        clean_input(torch.Tensor([4, 5, 6]), torch.Tensor())
+    with pytest.raises(ValueError):
+        clean_input(np.zeros((0, 3)), np.zeros((2, 3)))
+
+
+def test_validate_and_lut():
+    from prograph_b200.graph import validate, distance_lut
+    for bad in (dict(eps=None, k=None), dict(eps=1, k=2), dict(eps=0, k=None), dict(eps=None, k=0)):
+        with pytest.raises(ValueError):
+            validate(**bad)
+    with pytest.raises(TypeError):
+        validate(None, 0.5)
+    validate(1, None)
+    validate(None, 3)
+
+    def bits(words):
+        return [d for d in range(len(words) * 32) if (words[d >> 5] >> (d & 31)) & 1]
+    assert bits(distance_lut(64, operator.le, 2, False)) == [1, 2]
+    assert bits(distance_lut(64, operator.lt, 2, False)) == [1]
+    assert bits(distance_lut(64, operator.eq, 3, False)) == [3]
+    assert bits(distance_lut(64, operator.le, 1.5, False)) == [1]
+    assert bits(distance_lut(64, operator.ge, 63, False)) == [63, 64]
+    assert bits(distance_lut(64, operator.ne, 2, False)) == [d for d in range(1, 65) if d != 2]
+    assert bits(distance_lut(64, operator.eq, 0, False, guard=False)) == [0]
+    # similarity: eps already transformed, operands swapped, s < 1 guard (prograph.py:721,734)
+    assert bits(distance_lut(64, operator.le, 1 / (1 + 2), True)) == [1, 2]
+    assert bits(distance_lut(64, lambda a, b: a <= b, 2, False)) == [1, 2]
+    assert bits(distance_lut(64, lambda a, b: True, 2, False)) == list(range(1, 65))   # broadcasts like torch
+
+
+def test_tables_as_reference_lists():
+    from prograph_b200.graph import NeighbourTable, KnnTable
+    t = NeighbourTable(np.array([0, 2, 2, 3]), np.array([5, 7, 1]), np.array([1.5, 2.5, 0.5], dtype=np.float16))
+    lst = t.as_list()
+    assert len(lst) == 3 and lst[0][0].tolist() == [5, 7] and lst[0][1].dtype == np.float16
+    assert len(lst[1][0]) == 0 and lst[1][0].dtype == np.dtype(int) and lst[1][1].dtype == np.dtype(int)
+    assert np.shares_memory(lst[2][0], t.idx)
+    kt = KnnTable(np.arange(6).reshape(3, 2), np.ones((3, 2)))
+    assert [a.tolist() for a, _ in kt.as_list()] == [[0, 1], [2, 3], [4, 5]]
+    assert kt.to_csr().indptr.tolist() == [0, 2, 4, 6]
+
+
+def test_row_ranges_cover_everything():
+    from prograph_b200 import shard
+    for n in (1, 5, 8, 1000, 1_000_000, 999_999):
+        for world in (1, 2, 4, 8):
+            covered = []
+            for r in range(world):
+                r0, rows = shard.row_range(n, r, world)
+                if n < world or world == 1:
+                    assert (r0, rows) == (0, n)
+                else:
+                    covered.extend([(r0, rows)])
+            if covered:
+                assert covered[0][0] == 0 and sum(c[1] for c in covered) == n
+                for (a, an), (b, _) in zip(covered, covered[1:]):
+                    assert a + an == b
+    r0, rows = shard.row_range(1_000_000, 7, 8)
+    assert r0 % 512 == 0 and rows > 0
+    for n, world in ((5, 4), (9, 8), (2100, 4), (513, 2)):
+        assert all(shard.row_range(n, r, world)[1] > 0 for r in range(world))
+
+
+def _gloo_worker(rank, world, port, n, k, tmpdir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _cpu_engine import CheckerEngine
+    from prograph_b200.graph import build_neighbours
+    rng = np.random.default_rng(3)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    eng = CheckerEngine()
+    knn = build_neighbours(X, k=k, engine=eng)
+    eps = build_neighbours(X, eps=2, engine=eng)
+    sim = build_neighbours(X, eps=2, similarity=True, engine=eng)
+    np.savez(os.path.join(tmpdir, f"r{rank}.npz"), idx=knn.idx, w=knn.w, indptr=eps.indptr, eidx=eps.idx, ew=eps.w,
+             sindptr=sim.indptr, sidx=sim.idx, sw=sim.w, rows=np.array(eng.rows_seen))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [37, 1301])
+def test_sharded_build_over_gloo(tmp_path, n):
+    """world_size 2 on CPU: each rank computes only its row block (through a checker-backed
+    engine standing in for the CUDA one), the all-gathers rebuild the whole graph on both."""
+    import torch.multiprocessing as mp
+    from oracle import prograph_oracle as O
+    k, world = 5, 2
+    port = 29600 + (os.getpid() + n) % 300
+    mp.spawn(_gloo_worker, args=(world, port, n, k, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    D = O.hamming(X, X)
+    ri, rw = O.knn_from_distances(D, k)
+    indptr, eidx, ew = O.to_csr(O.build_graph(X, eps=2))
+    sindptr, sidx, sw = O.to_csr(O.build_graph(X, eps=2, similarity=True))
+    seen = []
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(z["idx"], ri)
+        np.testing.assert_array_equal(z["w"], rw)
+        np.testing.assert_array_equal(z["indptr"], indptr)
+        np.testing.assert_array_equal(z["eidx"], eidx)
+        np.testing.assert_array_equal(z["ew"], ew)
+        np.testing.assert_array_equal(z["sindptr"], sindptr)
+        np.testing.assert_array_equal(z["sidx"], sidx)
+        np.testing.assert_array_equal(z["sw"], sw)
+        seen.append(tuple(z["rows"]))
+    # the two ranks worked on disjoint row blocks that tile [0, n)
+    assert seen[0][0] == 0 and seen[0][0] + seen[0][1] == seen[1][0] and seen[1][0] + seen[1][1] == n
