@@ -6,7 +6,9 @@
 
 #include <cub/device/device_scan.cuh>
 
-#include "pg_sweep.cuh"
+#include <cstdlib>
+
+#include "pg_sweep_knn.cuh"
 
 namespace pg {
 
@@ -43,10 +45,10 @@ static int tile_cols_for(int words) { return 512 / words; }
 // Splits of the stream make the persistent grid's last wave short: aim for >= 32 items per
 // resident CTA, but keep >= 8 ring tiles per item so the own-row load and the list
 // write-back stay amortised.
-static Geometry make_geometry(long long rows, long long stream_rows, int words) {
+static Geometry make_geometry(long long rows, long long stream_rows, int words, int rows_per_cta = kConsumers) {
   Geometry g;
   g.tile_cols = tile_cols_for(words);
-  g.n_rowblocks = static_cast<int>(ceil_div(rows, kConsumers));
+  g.n_rowblocks = static_cast<int>(ceil_div(rows, rows_per_cta));
   g.n_tiles = static_cast<int>(ceil_div(stream_rows, g.tile_cols));
   const long long resident = static_cast<long long>(num_sms()) * 2;
   long long want = ceil_div(32 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
@@ -173,8 +175,10 @@ extern "C" {
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
   if (words > 8) words = 8;
-  const Geometry g = make_geometry(own_rows, stream_rows, words);
-  const size_t per_row = static_cast<size_t>(g.n_splits) * 8 * static_cast<size_t>(k1 > 1 ? k1 : 1);
+  const Geometry g1 = make_geometry(own_rows, stream_rows, words);
+  const Geometry g2 = make_geometry(own_rows, stream_rows, words, 2 * kConsumers);   // multi-row kNN variants
+  const int n_splits = g1.n_splits > g2.n_splits ? g1.n_splits : g2.n_splits;
+  const size_t per_row = static_cast<size_t>(n_splits) * 8 * static_cast<size_t>(k1 > 1 ? k1 : 1);
   return per_row * static_cast<size_t>(own_rows) + 256;
 }
 
@@ -187,7 +191,11 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   PG_CHECK_ARG(out_idx && out_w && workspace, "null output/workspace pointer");
   PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
   const int k1 = drop + k;
-  const Geometry g = make_geometry(rows, stream_rows, words);
+  // experiment knob: PG_KNN_VARIANT picks a kNN-specialised kernel (pg_sweep_knn.cuh)
+  int variant = 0;
+  if (const char* ev = std::getenv("PG_KNN_VARIANT")) variant = std::atoi(ev);
+  if (!(planes == 5 && words == 8)) variant = 0;
+  const Geometry g = make_geometry(rows, stream_rows, words, knn_variant_rows_per_cta(variant));
   const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   const size_t list_bytes = static_cast<size_t>(k1) * kConsumers * 8;
@@ -202,7 +210,8 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   SweepLaunch l{MODE_KNN, 0, weight, 0, list_bytes, static_cast<cudaStream_t>(stream)};
   {
     SweepTimer t(l.stream);
-    rc = dispatch(planes, words, prm, l);
+    rc = variant > 0 ? sweep_knn_variant(variant, planes, words, prm, list_bytes, l.stream)
+                     : dispatch(planes, words, prm, l);
   }
   if (rc != PG_OK) return rc;
   const int threads = 128;

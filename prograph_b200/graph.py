@@ -168,7 +168,28 @@ def hamming_knn_device(eng, own, stream, k, similarity, row0, rows):
     if kk <= 0:
         wdt = torch.float32 if similarity else torch.int64
         return eng.empty((rows, 0), torch.int64), eng.empty((rows, 0), wdt)
-    return eng.hamming_knn(own, row0, rows, stream, kk, drop=1, similarity=similarity)
+    try:
+        return eng.hamming_knn(own, row0, rows, stream, kk, drop=1, similarity=similarity)
+    except L.Unsupported:
+        return hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows)
+
+
+def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
+    """Same result through materialised int64 tiles + the tile top-k: used when k is too large
+    for the in-shared-memory lists of the fused sweep.  Ascending distance with index ties is
+    the same order as descending similarity, so the sort always runs on the distances."""
+    kk = min(k, stream.rows - 1)
+    step = max(512, (TILE_BUDGET_BYTES // (8 * stream.rows)) // 512 * 512)
+    idxs, ws = [], []
+    a0 = row0 // 512 * 512
+    for q0 in range(a0, row0 + rows, step):
+        qn = min(step, own.rows - q0)
+        tile = eng.hamming_tile(stream, own, q0, qn, weight=L.W_I64)
+        lo, hi = max(row0, q0) - q0, min(row0 + rows, q0 + qn) - q0
+        i, d = eng.tile_topk(tile[lo:hi], kk, drop=1, descending=False)
+        idxs.append(i)
+        ws.append(1 / (1 + d) if similarity else d)        # hamming.py:38, on the device
+    return torch.cat(idxs), torch.cat(ws)
 
 
 def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows):
