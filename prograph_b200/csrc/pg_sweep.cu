@@ -8,7 +8,7 @@
 
 #include <cstdlib>
 
-#include "pg_sweep_knn.cuh"
+#include "pg_sweep.cuh"
 
 namespace pg {
 
@@ -52,7 +52,11 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
   g.n_tiles = static_cast<int>(ceil_div(stream_rows, g.tile_cols));
   const long long resident = static_cast<long long>(num_sms()) * 2;
   long long want = ceil_div(32 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
-  long long max_splits = g.n_tiles / 8;
+  // every split restarts its kNN lists from empty: keep >= 16K stream rows (and >= 8 ring
+  // tiles) per split so that the cold start stays a small fraction of the item
+  long long max_splits = stream_rows / 16384;
+  if (max_splits > g.n_tiles / 8) max_splits = g.n_tiles / 8;
+  if (const char* ev = std::getenv("PG_SWEEP_SPLITS")) { want = std::atoll(ev); max_splits = g.n_tiles; }
   if (max_splits < 1) max_splits = 1;
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
@@ -191,15 +195,15 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   PG_CHECK_ARG(out_idx && out_w && workspace, "null output/workspace pointer");
   PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
   const int k1 = drop + k;
-  // experiment knob: PG_KNN_VARIANT picks a kNN-specialised kernel (pg_sweep_knn.cuh)
-  int variant = 0;
-  if (const char* ev = std::getenv("PG_KNN_VARIANT")) variant = std::atoi(ev);
-  if (!(planes == 5 && words == 8)) variant = 0;
-  const Geometry g = make_geometry(rows, stream_rows, words, knn_variant_rows_per_cta(variant));
+  // experiment knob: PG_KNN_VARIANT=1 runs two own rows per thread (planes 5, words 8 only)
+  int tm = 1;
+  if (const char* ev = std::getenv("PG_KNN_VARIANT")) tm = std::atoi(ev) == 1 ? 2 : 1;
+  if (!(planes == 5 && words == 8)) tm = 1;
+  const Geometry g = make_geometry(rows, stream_rows, words, kConsumers * tm);
   const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
-  const size_t list_bytes = static_cast<size_t>(k1) * kConsumers * 8;
-  if (list_bytes + 70 * 1024 > 227 * 1024) {
+  const size_t list_bytes = static_cast<size_t>(k1) * kConsumers * tm * 8;
+  if (k1 > 32 * kMaxListRounds || list_bytes + 70 * 1024 > 227 * 1024) {
     set_error("k=%d too large for the in-shared-memory lists of the fused sweep", k);
     return PG_ERR_UNSUPPORTED;
   }
@@ -208,10 +212,10 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   prm.part = static_cast<unsigned long long*>(workspace);
   prm.k1 = k1;
   SweepLaunch l{MODE_KNN, 0, weight, 0, list_bytes, static_cast<cudaStream_t>(stream)};
+  l.rows_per_thread = tm;
   {
     SweepTimer t(l.stream);
-    rc = variant > 0 ? sweep_knn_variant(variant, planes, words, prm, list_bytes, l.stream)
-                     : dispatch(planes, words, prm, l);
+    rc = dispatch(planes, words, prm, l);
   }
   if (rc != PG_OK) return rc;
   const int threads = 128;

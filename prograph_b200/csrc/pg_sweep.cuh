@@ -58,9 +58,11 @@ struct SweepParams {
   uint32_t lut[kMaxLutWords];
 };
 
-template <int P, int W>
-__device__ __forceinline__ int ham_row(const uint32_t (&q)[P * W], const uint32_t* __restrict__ col) {
-  uint32_t m[W];
+// Distances of TM own rows (registers) to one stream row (shared memory, broadcast loads).
+template <int P, int W, int TM>
+__device__ __forceinline__ void ham_rows(const uint32_t (&q)[TM][P * W], const uint32_t* __restrict__ col,
+                                         int (&d)[TM]) {
+  uint32_t m[TM][W];
   if constexpr (W % 4 == 0) {
     const uint4* c4 = reinterpret_cast<const uint4*>(col);
 #pragma unroll
@@ -69,16 +71,19 @@ __device__ __forceinline__ int ham_row(const uint32_t (&q)[P * W], const uint32_
       for (int h = 0; h < W / 4; ++h) {
         const uint4 v = c4[p * (W / 4) + h];
         const int w = h * 4;
-        if (p == 0) {
-          m[w + 0] = q[w + 0] ^ v.x;
-          m[w + 1] = q[w + 1] ^ v.y;
-          m[w + 2] = q[w + 2] ^ v.z;
-          m[w + 3] = q[w + 3] ^ v.w;
-        } else {
-          m[w + 0] |= q[p * W + w + 0] ^ v.x;
-          m[w + 1] |= q[p * W + w + 1] ^ v.y;
-          m[w + 2] |= q[p * W + w + 2] ^ v.z;
-          m[w + 3] |= q[p * W + w + 3] ^ v.w;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          if (p == 0) {
+            m[i][w + 0] = q[i][w + 0] ^ v.x;
+            m[i][w + 1] = q[i][w + 1] ^ v.y;
+            m[i][w + 2] = q[i][w + 2] ^ v.z;
+            m[i][w + 3] = q[i][w + 3] ^ v.w;
+          } else {
+            m[i][w + 0] |= q[i][p * W + w + 0] ^ v.x;
+            m[i][w + 1] |= q[i][p * W + w + 1] ^ v.y;
+            m[i][w + 2] |= q[i][p * W + w + 2] ^ v.z;
+            m[i][w + 3] |= q[i][p * W + w + 3] ^ v.w;
+          }
         }
       }
     }
@@ -87,12 +92,15 @@ __device__ __forceinline__ int ham_row(const uint32_t (&q)[P * W], const uint32_
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const uint2 v = c2[p];
-      if (p == 0) {
-        m[0] = q[0] ^ v.x;
-        m[1] = q[1] ^ v.y;
-      } else {
-        m[0] |= q[p * 2 + 0] ^ v.x;
-        m[1] |= q[p * 2 + 1] ^ v.y;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        if (p == 0) {
+          m[i][0] = q[i][0] ^ v.x;
+          m[i][1] = q[i][1] ^ v.y;
+        } else {
+          m[i][0] |= q[i][p * 2 + 0] ^ v.x;
+          m[i][1] |= q[i][p * 2 + 1] ^ v.y;
+        }
       }
     }
   } else {
@@ -101,15 +109,21 @@ __device__ __forceinline__ int ham_row(const uint32_t (&q)[P * W], const uint32_
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         const uint32_t v = col[p * W + w];
-        if (p == 0) m[w] = q[w] ^ v;
-        else m[w] |= q[p * W + w] ^ v;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          if (p == 0) m[i][w] = q[i][w] ^ v;
+          else m[i][w] |= q[i][p * W + w] ^ v;
+        }
       }
     }
   }
-  int d = 0;
 #pragma unroll
-  for (int w = 0; w < W; ++w) d += __popc(m[w]);
-  return d;
+  for (int i = 0; i < TM; ++i) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) s += __popc(m[i][w]);
+    d[i] = s;
+  }
 }
 
 __device__ __forceinline__ void write_weight(void* out_w, long long at, int d, int weight) {
@@ -118,26 +132,39 @@ __device__ __forceinline__ void write_weight(void* out_w, long long at, int d, i
   else reinterpret_cast<int*>(out_w)[at] = d;
 }
 
-// Sorted insertion into this thread's list (entries `stride` apart, ascending keys).
-// Precondition: key < list[k1-1].
-__device__ __forceinline__ unsigned knn_insert(unsigned long long* list, int stride, int k1,
-                                               unsigned long long key) {
-  int j = k1 - 1;
-  while (j > 0) {
-    const unsigned long long prev = list[(j - 1) * stride];
-    if (prev <= key) break;
-    list[j * stride] = prev;
-    --j;
+constexpr int kMaxListRounds = 3;  // sorted lists of up to 96 entries, one entry per lane and round
+
+// Warp-cooperative sorted insertion: the whole warp inserts `key` into the ascending list of
+// one own row (list[0..k1), contiguous in shared memory) and returns the distance word of
+// the new last entry.  All lanes must call it with the same arguments.  No divergent loop:
+// a ballot finds the insertion point, every lane rewrites its own slot.
+__device__ __forceinline__ unsigned knn_insert_coop(unsigned long long* list, int k1, unsigned long long key, int lane) {
+  unsigned long long cur[kMaxListRounds], prev[kMaxListRounds];
+  int pos = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxListRounds; ++r) {
+    const int j = lane + 32 * r;
+    const bool in = j < k1;
+    cur[r] = in ? list[j] : ~0ull;
+    prev[r] = (in && j > 0) ? list[j - 1] : 0ull;
+    pos += __popc(__ballot_sync(0xffffffffu, in && cur[r] < key));
   }
-  list[j * stride] = key;
-  return static_cast<unsigned>(list[(k1 - 1) * stride] >> 32);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < kMaxListRounds; ++r) {
+    const int j = lane + 32 * r;
+    if (j < k1 && j >= pos) list[j] = (j == pos) ? key : prev[r];
+  }
+  __syncwarp();
+  return static_cast<unsigned>(list[k1 - 1] >> 32);
 }
 
-template <int P, int W, int MODE, bool LUT, int WEIGHT>
-__global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_constant__ SweepParams prm) {
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT>
+__global__ void __launch_bounds__(kSweepThreads, TM == 1 ? 2 : 1) sweep_kernel(const __grid_constant__ SweepParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
   constexpr uint32_t STAGE_BYTES = BN * COLW * 4;
+  constexpr int ROWS_CTA = kConsumers * TM;
   static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -145,7 +172,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_co
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * STAGE_BYTES);
   uint64_t* empty = full + kStages;
   uint32_t* lut_s = reinterpret_cast<uint32_t*>(empty + kStages);
-  unsigned long long* lists = reinterpret_cast<unsigned long long*>(lut_s + kMaxLutWords);
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(lut_s + kMaxLutWords);  // [ROWS_CTA][k1]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -174,7 +201,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_co
         const int t0 = split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_wait_backoff(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           bulk_g2s(stage_mem + stage * (BN * COLW), prm.str + static_cast<size_t>(t) * BN * COLW, STAGE_BYTES,
                    &full[stage]);
@@ -189,34 +216,34 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_co
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int split = item / prm.n_rowblocks;
     const int rb = item - split * prm.n_rowblocks;
-    const long long r = static_cast<long long>(rb) * kConsumers + tid;  // row relative to own_row0
-    const bool valid = r < prm.rows;
-
-    uint32_t q[COLW];
-    {
-      const uint32_t* src = prm.own + static_cast<size_t>(prm.own_row0 + (valid ? r : 0)) * COLW;
+    long long r[TM];      // own rows relative to own_row0; lanes hold consecutive rows
+    bool valid[TM];
+    uint32_t q[TM][COLW];
+    unsigned tau[TM];     // kNN: distance word of the k1-th list entry (the filter threshold)
+    long long cnt[TM];    // count / fill cursor
 #pragma unroll
-      for (int i = 0; i < COLW; ++i) q[i] = valid ? __ldg(src + i) : 0u;
-    }
-
-    // per-mode state
-    unsigned tau = valid ? 0xffffffffu : 0u;   // kNN: distance of the k1-th list entry
-    long long cnt = 0;                          // count / fill cursor
-    unsigned long long* my_list = lists + tid;
-    int lo = prm.lo;
-    unsigned span = prm.span;
-    if constexpr (MODE == MODE_KNN) {
-      for (int j = 0; j < prm.k1; ++j) my_list[j * kConsumers] = ~0ull;
-    }
-    if constexpr (MODE == MODE_COUNT || MODE == MODE_FILL) {
-      if (!valid) { lo = 0x7fffffff; span = 0; }
-    }
-    if constexpr (MODE == MODE_FILL) {
-      if (valid) {
-        cnt = prm.indptr[r];
-        for (int s = 0; s < split; ++s) cnt += prm.split_counts[static_cast<size_t>(s) * prm.rows + r];
+    for (int i = 0; i < TM; ++i) {
+      r[i] = static_cast<long long>(rb) * ROWS_CTA + i * kConsumers + tid;
+      valid[i] = r[i] < prm.rows;
+      const uint32_t* src = prm.own + static_cast<size_t>(prm.own_row0 + (valid[i] ? r[i] : 0)) * COLW;
+#pragma unroll
+      for (int j = 0; j < COLW; ++j) q[i][j] = valid[i] ? __ldg(src + j) : 0u;
+      tau[i] = valid[i] ? 0xffffffffu : 0u;
+      cnt[i] = 0;
+      if constexpr (MODE == MODE_KNN) {
+        unsigned long long* mine = lists + static_cast<size_t>(i * kConsumers + tid) * prm.k1;
+        for (int j = 0; j < prm.k1; ++j) mine[j] = ~0ull;
+      }
+      if constexpr (MODE == MODE_FILL) {
+        if (valid[i]) {
+          cnt[i] = prm.indptr[r[i]];
+          for (int s = 0; s < split; ++s) cnt[i] += prm.split_counts[static_cast<size_t>(s) * prm.rows + r[i]];
+        }
       }
     }
+    int lo = prm.lo;
+    unsigned span = prm.span;
+    if constexpr (MODE == MODE_KNN) __syncwarp();
 
     const int t0 = split * prm.tiles_per_split;
     const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
@@ -227,27 +254,39 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_co
       const int ncols = static_cast<int>(min(static_cast<long long>(BN), prm.str_rows - col0));
 #pragma unroll 2
       for (int c = 0; c < ncols; ++c) {
-        const int d = ham_row<P, W>(q, tile + c * COLW);
-        if constexpr (MODE == MODE_KNN) {
-          if (static_cast<unsigned>(d) < tau) {
-            const unsigned long long key =
-                (static_cast<unsigned long long>(static_cast<unsigned>(d)) << 32) | static_cast<unsigned>(col0 + c);
-            tau = knn_insert(my_list, kConsumers, prm.k1, key);
+        int d[TM];
+        ham_rows<P, W, TM>(q, tile + c * COLW, d);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          if constexpr (MODE == MODE_KNN) {
+            // candidates are rare: a ballot, then the warp serves its candidates one by one
+            unsigned cand = __ballot_sync(0xffffffffu, static_cast<unsigned>(d[i]) < tau[i]);
+            while (cand) {
+              const int src = __ffs(cand) - 1;
+              cand &= cand - 1;
+              const unsigned dd = __shfl_sync(0xffffffffu, static_cast<unsigned>(d[i]), src);
+              const unsigned long long key =
+                  (static_cast<unsigned long long>(dd) << 32) | static_cast<unsigned>(col0 + c);
+              unsigned long long* lst =
+                  lists + static_cast<size_t>(i * kConsumers + (warp << 5) + src) * prm.k1;
+              const unsigned t_new = knn_insert_coop(lst, prm.k1, key, lane);
+              if (lane == src) tau[i] = t_new;
+            }
+          } else if constexpr (MODE == MODE_COUNT) {
+            if constexpr (LUT) cnt[i] += (lut_s[d[i] >> 5] >> (d[i] & 31)) & (valid[i] ? 1u : 0u);
+            else cnt[i] += (valid[i] && static_cast<unsigned>(d[i] - lo) <= span) ? 1 : 0;
+          } else if constexpr (MODE == MODE_FILL) {
+            bool hit;
+            if constexpr (LUT) hit = (lut_s[d[i] >> 5] >> (d[i] & 31)) & 1u;
+            else hit = static_cast<unsigned>(d[i] - lo) <= span;
+            if (hit && valid[i]) {
+              prm.out_idx[cnt[i]] = col0 + c;
+              write_weight(prm.out_w, cnt[i], d[i], WEIGHT);
+              ++cnt[i];
+            }
+          } else {  // MODE_TILE: out[stream * ld + own]
+            if (valid[i]) write_weight(prm.out, (col0 + c) * prm.ld + r[i], d[i], WEIGHT);
           }
-        } else if constexpr (MODE == MODE_COUNT) {
-          if constexpr (LUT) cnt += (lut_s[d >> 5] >> (d & 31)) & (valid ? 1u : 0u);
-          else cnt += (static_cast<unsigned>(d - lo) <= span) ? 1 : 0;
-        } else if constexpr (MODE == MODE_FILL) {
-          bool hit;
-          if constexpr (LUT) hit = ((lut_s[d >> 5] >> (d & 31)) & 1u) && valid;
-          else hit = static_cast<unsigned>(d - lo) <= span;
-          if (hit) {
-            prm.out_idx[cnt] = col0 + c;
-            write_weight(prm.out_w, cnt, d, WEIGHT);
-            ++cnt;
-          }
-        } else {  // MODE_TILE: out[stream * ld + own]
-          if (valid) write_weight(prm.out, (col0 + c) * prm.ld + r, d, WEIGHT);
         }
       }
       __syncwarp();
@@ -255,14 +294,19 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(const __grid_co
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 
-    if constexpr (MODE == MODE_KNN) {
-      if (valid) {
-        unsigned long long* dst = prm.part + static_cast<size_t>(split) * prm.k1 * prm.rows + r;
-        for (int j = 0; j < prm.k1; ++j) dst[static_cast<size_t>(j) * prm.rows] = my_list[j * kConsumers];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      if constexpr (MODE == MODE_KNN) {
+        if (valid[i]) {
+          const unsigned long long* mine = lists + static_cast<size_t>(i * kConsumers + tid) * prm.k1;
+          unsigned long long* dst = prm.part + static_cast<size_t>(split) * prm.k1 * prm.rows + r[i];
+          for (int j = 0; j < prm.k1; ++j) dst[static_cast<size_t>(j) * prm.rows] = mine[j];
+        }
+      } else if constexpr (MODE == MODE_COUNT) {
+        if (valid[i]) prm.split_counts[static_cast<size_t>(split) * prm.rows + r[i]] = cnt[i];
       }
-    } else if constexpr (MODE == MODE_COUNT) {
-      if (valid) prm.split_counts[static_cast<size_t>(split) * prm.rows + r] = cnt;
     }
+    if constexpr (MODE == MODE_KNN) __syncwarp();
   }
 }
 
@@ -276,8 +320,9 @@ struct SweepLaunch {
   int lut;     // 0 range test, 1 LUT
   int weight;  // pgWeight (tile: compile time; fill: runtime)
   int grid;    // 0 = let the launcher size a persistent grid
-  size_t list_bytes;  // kNN lists
+  size_t list_bytes;  // kNN lists (all own rows of a CTA)
   cudaStream_t stream;
+  int rows_per_thread = 1;  // 2 selects the two-rows-per-thread kNN instantiation (experiments)
 };
 
 template <int P, int W>
@@ -286,9 +331,9 @@ inline size_t sweep_smem_bytes(size_t list_bytes) {
          kMaxLutWords * 4 + list_bytes;
 }
 
-template <int P, int W, int MODE, bool LUT, int WEIGHT>
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT>
 int launch_one(const SweepParams& prm, const SweepLaunch& l) {
-  auto kern = sweep_kernel<P, W, MODE, LUT, WEIGHT>;
+  auto kern = sweep_kernel<P, W, TM, MODE, LUT, WEIGHT>;
   const size_t smem = sweep_smem_bytes<P, W>(l.list_bytes);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 0;
@@ -306,19 +351,23 @@ int launch_one(const SweepParams& prm, const SweepLaunch& l) {
 template <int P, int W>
 int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
   switch (l.mode) {
-    case MODE_KNN: return launch_one<P, W, MODE_KNN, false, 0>(prm, l);
+    case MODE_KNN:
+      if constexpr (P == 5 && W == 8) {
+        if (l.rows_per_thread == 2) return launch_one<P, W, 2, MODE_KNN, false, 0>(prm, l);
+      }
+      return launch_one<P, W, 1, MODE_KNN, false, 0>(prm, l);
     case MODE_COUNT:
-      return l.lut ? launch_one<P, W, MODE_COUNT, true, 0>(prm, l) : launch_one<P, W, MODE_COUNT, false, 0>(prm, l);
+      return l.lut ? launch_one<P, W, 1, MODE_COUNT, true, 0>(prm, l) : launch_one<P, W, 1, MODE_COUNT, false, 0>(prm, l);
     case MODE_FILL:
       if (l.weight == PG_W_SIM_F32)
-        return l.lut ? launch_one<P, W, MODE_FILL, true, PG_W_SIM_F32>(prm, l)
-                     : launch_one<P, W, MODE_FILL, false, PG_W_SIM_F32>(prm, l);
-      return l.lut ? launch_one<P, W, MODE_FILL, true, PG_W_I64>(prm, l)
-                   : launch_one<P, W, MODE_FILL, false, PG_W_I64>(prm, l);
+        return l.lut ? launch_one<P, W, 1, MODE_FILL, true, PG_W_SIM_F32>(prm, l)
+                     : launch_one<P, W, 1, MODE_FILL, false, PG_W_SIM_F32>(prm, l);
+      return l.lut ? launch_one<P, W, 1, MODE_FILL, true, PG_W_I64>(prm, l)
+                   : launch_one<P, W, 1, MODE_FILL, false, PG_W_I64>(prm, l);
     case MODE_TILE:
-      if (l.weight == PG_W_I64) return launch_one<P, W, MODE_TILE, false, PG_W_I64>(prm, l);
-      if (l.weight == PG_W_SIM_F32) return launch_one<P, W, MODE_TILE, false, PG_W_SIM_F32>(prm, l);
-      return launch_one<P, W, MODE_TILE, false, PG_W_I32>(prm, l);
+      if (l.weight == PG_W_I64) return launch_one<P, W, 1, MODE_TILE, false, PG_W_I64>(prm, l);
+      if (l.weight == PG_W_SIM_F32) return launch_one<P, W, 1, MODE_TILE, false, PG_W_SIM_F32>(prm, l);
+      return launch_one<P, W, 1, MODE_TILE, false, PG_W_I32>(prm, l);
   }
   set_error("bad sweep mode %d", l.mode);
   return PG_ERR_INVALID;
