@@ -86,14 +86,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
-// Producer-side wait: the lone producer lane sleeps between polls so that it does not eat
-// the issue slots of the consumer warps sharing its scheduler (ncu: the bare spin was 14 % of
-// all executed instructions).
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+// Producer-side wait: try_wait with a suspend-time hint parks the lone producer lane in
+// hardware until the phase completes (or ~20 us pass) instead of polling -- the bare spin was
+// 14 % of all executed instructions and stole issue slots from the consumer warps on its
+// scheduler (profiles/r1_ncu_notes.md).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(200);
-    if (++spins > (1u << 24)) __trap();
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    __nanosleep(1000);
+    if (++spins > (1u << 22)) __trap();
   }
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)

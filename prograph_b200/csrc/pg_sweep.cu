@@ -103,6 +103,7 @@ static void fill_common(SweepParams& prm, const Geometry& g, const uint32_t* own
   prm.n_splits = g.n_splits;
   prm.tiles_per_split = g.tiles_per_split;
   prm.n_tiles = g.n_tiles;
+  prm.one = 1u;
 }
 
 // A truth table over d = 0..L that is one contiguous run becomes a range test.
@@ -197,8 +198,10 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   const int k1 = drop + k;
   // experiment knob: PG_KNN_VARIANT=1 runs two own rows per thread (planes 5, words 8 only)
   int tm = 1;
-  if (const char* ev = std::getenv("PG_KNN_VARIANT")) tm = std::atoi(ev) == 1 ? 2 : 1;
-  if (!(planes == 5 && words == 8)) tm = 1;
+  int variant = 0;
+  if (const char* ev = std::getenv("PG_KNN_VARIANT")) variant = std::atoi(ev);
+  if (!(planes == 5 && words == 8)) variant = 0;
+  if (variant == 1) tm = 2;
   const Geometry g = make_geometry(rows, stream_rows, words, kConsumers * tm);
   const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
@@ -212,7 +215,7 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   prm.part = static_cast<unsigned long long*>(workspace);
   prm.k1 = k1;
   SweepLaunch l{MODE_KNN, 0, weight, 0, list_bytes, static_cast<cudaStream_t>(stream)};
-  l.rows_per_thread = tm;
+  l.rows_per_thread = variant == 3 ? 3 : tm;
   {
     SweepTimer t(l.stream);
     rc = dispatch(planes, words, prm, l);

@@ -42,6 +42,8 @@ struct SweepParams {
   const uint32_t* str;   // packed stream table (padded to kStreamRowPad rows)
   long long str_rows;    // valid stream rows
   int n_rowblocks, n_splits, tiles_per_split, n_tiles;
+  unsigned one;          // the constant 1, opaque to the compiler: `mad p, one, acc` keeps the
+                         // popcount sums on the FMA pipe (IMAD), off the LOP3-saturated ALU pipe
   // kNN
   unsigned long long* part;  // [n_splits][k1][rows] sorted partial lists, key = d<<32 | idx
   int k1;
@@ -58,10 +60,16 @@ struct SweepParams {
   uint32_t lut[kMaxLutWords];
 };
 
+__device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c) {
+  unsigned r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 // Distances of TM own rows (registers) to one stream row (shared memory, broadcast loads).
 template <int P, int W, int TM>
 __device__ __forceinline__ void ham_rows(const uint32_t (&q)[TM][P * W], const uint32_t* __restrict__ col,
-                                         int (&d)[TM]) {
+                                         int (&d)[TM], unsigned one) {
   uint32_t m[TM][W];
   if constexpr (W % 4 == 0) {
     const uint4* c4 = reinterpret_cast<const uint4*>(col);
@@ -119,10 +127,10 @@ __device__ __forceinline__ void ham_rows(const uint32_t (&q)[TM][P * W], const u
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    int s = 0;
+    unsigned s = __popc(m[i][0]);
 #pragma unroll
-    for (int w = 0; w < W; ++w) s += __popc(m[i][w]);
-    d[i] = s;
+    for (int w = 1; w < W; ++w) s = mad_u32(__popc(m[i][w]), one, s);
+    d[i] = static_cast<int>(s);
   }
 }
 
@@ -159,8 +167,8 @@ __device__ __forceinline__ unsigned knn_insert_coop(unsigned long long* list, in
   return static_cast<unsigned>(list[k1 - 1] >> 32);
 }
 
-template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT>
-__global__ void __launch_bounds__(kSweepThreads, TM == 1 ? 2 : 1) sweep_kernel(const __grid_constant__ SweepParams prm) {
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = (TM == 1 ? 2 : 1)>
+__global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid_constant__ SweepParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
   constexpr uint32_t STAGE_BYTES = BN * COLW * 4;
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(kSweepThreads, TM == 1 ? 2 : 1) sweep_kernel(c
         const int t0 = split * prm.tiles_per_split;
         const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait_backoff(&empty[stage], phase ^ 1u);
+          mbar_wait_suspended(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           bulk_g2s(stage_mem + stage * (BN * COLW), prm.str + static_cast<size_t>(t) * BN * COLW, STAGE_BYTES,
                    &full[stage]);
@@ -241,8 +249,9 @@ __global__ void __launch_bounds__(kSweepThreads, TM == 1 ? 2 : 1) sweep_kernel(c
         }
       }
     }
-    int lo = prm.lo;
-    unsigned span = prm.span;
+    const int lo = prm.lo;
+    const unsigned span = prm.span;
+    const unsigned one = prm.one;
     if constexpr (MODE == MODE_KNN) __syncwarp();
 
     const int t0 = split * prm.tiles_per_split;
@@ -252,26 +261,52 @@ __global__ void __launch_bounds__(kSweepThreads, TM == 1 ? 2 : 1) sweep_kernel(c
       const uint32_t* tile = stage_mem + stage * (BN * COLW);
       const long long col0 = static_cast<long long>(t) * BN;
       const int ncols = static_cast<int>(min(static_cast<long long>(BN), prm.str_rows - col0));
+      // serve the kNN candidates of one stream row: rare, so a ballot first, then the warp
+      // inserts them one by one (warp-uniform control flow)
+      auto serve = [&](int i, int dv, long long col) {
+        unsigned cand = __ballot_sync(0xffffffffu, static_cast<unsigned>(dv) < tau[i]);
+        while (cand) {
+          const int src = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const unsigned dd = __shfl_sync(0xffffffffu, static_cast<unsigned>(dv), src);
+          const unsigned long long key = (static_cast<unsigned long long>(dd) << 32) | static_cast<unsigned>(col);
+          unsigned long long* lst = lists + static_cast<size_t>(i * kConsumers + (warp << 5) + src) * prm.k1;
+          const unsigned t_new = knn_insert_coop(lst, prm.k1, key, lane);
+          if (lane == src) tau[i] = t_new;
+        }
+      };
+      int c = 0;
+      if constexpr (MODE == MODE_KNN) {
+        // four stream rows per vote: one min + one compare + one vote per group keeps the
+        // per-pair overhead on the ALU pipe near zero
+#pragma unroll 1
+        for (; c + 4 <= ncols; c += 4) {
+          int d0[TM], d1[TM], d2[TM], d3[TM];
+          ham_rows<P, W, TM>(q, tile + (c + 0) * COLW, d0, one);
+          ham_rows<P, W, TM>(q, tile + (c + 1) * COLW, d1, one);
+          ham_rows<P, W, TM>(q, tile + (c + 2) * COLW, d2, one);
+          ham_rows<P, W, TM>(q, tile + (c + 3) * COLW, d3, one);
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            const unsigned best = min(min(static_cast<unsigned>(d0[i]), static_cast<unsigned>(d1[i])),
+                                      min(static_cast<unsigned>(d2[i]), static_cast<unsigned>(d3[i])));
+            if (__any_sync(0xffffffffu, best < tau[i])) {
+              serve(i, d0[i], col0 + c + 0);
+              serve(i, d1[i], col0 + c + 1);
+              serve(i, d2[i], col0 + c + 2);
+              serve(i, d3[i], col0 + c + 3);
+            }
+          }
+        }
+      }
 #pragma unroll 2
-      for (int c = 0; c < ncols; ++c) {
+      for (; c < ncols; ++c) {
         int d[TM];
-        ham_rows<P, W, TM>(q, tile + c * COLW, d);
+        ham_rows<P, W, TM>(q, tile + c * COLW, d, one);
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           if constexpr (MODE == MODE_KNN) {
-            // candidates are rare: a ballot, then the warp serves its candidates one by one
-            unsigned cand = __ballot_sync(0xffffffffu, static_cast<unsigned>(d[i]) < tau[i]);
-            while (cand) {
-              const int src = __ffs(cand) - 1;
-              cand &= cand - 1;
-              const unsigned dd = __shfl_sync(0xffffffffu, static_cast<unsigned>(d[i]), src);
-              const unsigned long long key =
-                  (static_cast<unsigned long long>(dd) << 32) | static_cast<unsigned>(col0 + c);
-              unsigned long long* lst =
-                  lists + static_cast<size_t>(i * kConsumers + (warp << 5) + src) * prm.k1;
-              const unsigned t_new = knn_insert_coop(lst, prm.k1, key, lane);
-              if (lane == src) tau[i] = t_new;
-            }
+            serve(i, d[i], col0 + c);
           } else if constexpr (MODE == MODE_COUNT) {
             if constexpr (LUT) cnt[i] += (lut_s[d[i] >> 5] >> (d[i] & 31)) & (valid[i] ? 1u : 0u);
             else cnt[i] += (valid[i] && static_cast<unsigned>(d[i] - lo) <= span) ? 1 : 0;
@@ -331,9 +366,9 @@ inline size_t sweep_smem_bytes(size_t list_bytes) {
          kMaxLutWords * 4 + list_bytes;
 }
 
-template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT>
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = (TM == 1 ? 2 : 1)>
 int launch_one(const SweepParams& prm, const SweepLaunch& l) {
-  auto kern = sweep_kernel<P, W, TM, MODE, LUT, WEIGHT>;
+  auto kern = sweep_kernel<P, W, TM, MODE, LUT, WEIGHT, MINB>;
   const size_t smem = sweep_smem_bytes<P, W>(l.list_bytes);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 0;
@@ -354,6 +389,7 @@ int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
     case MODE_KNN:
       if constexpr (P == 5 && W == 8) {
         if (l.rows_per_thread == 2) return launch_one<P, W, 2, MODE_KNN, false, 0>(prm, l);
+        if (l.rows_per_thread == 3) return launch_one<P, W, 1, MODE_KNN, false, 0, 3>(prm, l);   // 3 CTAs / SM
       }
       return launch_one<P, W, 1, MODE_KNN, false, 0>(prm, l);
     case MODE_COUNT:
