@@ -110,6 +110,14 @@ __device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t pari
     if (++spins > (1u << 22)) __trap();
   }
 }
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ unsigned atom_add_acq_rel_cta(unsigned* addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -201,7 +201,7 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   int variant = 0;
   if (const char* ev = std::getenv("PG_KNN_VARIANT")) variant = std::atoi(ev);
   if (!(planes == 5 && words == 8)) variant = 0;
-  if (variant == 1) tm = 2;
+  if (variant == 1 || variant == 4) tm = 2;
   const Geometry g = make_geometry(rows, stream_rows, words, kConsumers * tm);
   const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
@@ -215,7 +215,7 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   prm.part = static_cast<unsigned long long*>(workspace);
   prm.k1 = k1;
   SweepLaunch l{MODE_KNN, 0, weight, 0, list_bytes, static_cast<cudaStream_t>(stream)};
-  l.rows_per_thread = variant == 3 ? 3 : tm;
+  l.rows_per_thread = variant == 3 ? 3 : (variant == 4 ? 4 : tm);
   {
     SweepTimer t(l.stream);
     rc = dispatch(planes, words, prm, l);

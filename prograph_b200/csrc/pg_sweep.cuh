@@ -7,10 +7,13 @@
 // Mapping ("own rows in registers, stream rows by broadcast"):
 //   * a CTA owns 256 "own" rows, one per consumer thread; the thread keeps its row's
 //     P bit planes x W words (P*W registers) for the whole sweep;
-//   * the "stream" table is swept through a 4-stage shared-memory ring filled by one
-//     producer lane with 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier);
-//     every consumer reads the same stream row at the same time, so shared-memory
-//     reads are pure broadcasts (one wavefront per 128-bit load, no bank conflicts);
+//   * the "stream" table is swept through a 4-stage shared-memory ring filled with 1-D
+//     bulk async copies (TMA engine, cp.async.bulk + mbarrier).  There is no producer warp:
+//     the warp that finishes a stage last re-arms its barrier and issues the copy of the
+//     tile four positions ahead, so nobody ever polls for a free slot;
+//   * every thread reads the same stream row at the same time, so shared-memory reads are
+//     pure broadcasts (two wavefronts per 128-bit load, no bank conflicts) shared by the
+//     TM own rows of the thread;
 //   * per pair and 32 residues: 5 LOP3 (xor/or fold of the planes) + 1 POPC + 1 IADD;
 //   * the epilogue sees (own row, stream row, distance) in ascending stream order and
 //     never writes the distance matrix: kNN keeps a sorted (distance,index) list per
@@ -23,8 +26,8 @@
 namespace pg {
 
 constexpr int kConsumerWarps = 8;
-constexpr int kConsumers = kConsumerWarps * 32;  // own rows per CTA
-constexpr int kSweepThreads = kConsumers + 32;   // + one producer warp
+constexpr int kConsumers = kConsumerWarps * 32;  // threads per CTA; each owns TM rows
+constexpr int kSweepThreads = kConsumers;
 constexpr int kStages = 4;
 constexpr int kMaxLutWords = 64;                 // distances up to 2047
 
@@ -167,7 +170,26 @@ __device__ __forceinline__ unsigned knn_insert_coop(unsigned long long* list, in
   return static_cast<unsigned>(list[k1 - 1] >> 32);
 }
 
-template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = (TM == 1 ? 2 : 1)>
+// Position of a CTA in its sequence of (work item, ring tile) pairs.
+struct SweepCursor {
+  int item, t, t1;
+  __device__ __forceinline__ void start(int it, const SweepParams& prm) {
+    item = it;
+    if (item < prm.n_rowblocks * prm.n_splits) {
+      const int split = item / prm.n_rowblocks;
+      t = split * prm.tiles_per_split;
+      t1 = min(t + prm.tiles_per_split, prm.n_tiles);
+    } else {
+      t = t1 = 0;
+    }
+  }
+  __device__ __forceinline__ bool valid(const SweepParams& prm) const { return item < prm.n_rowblocks * prm.n_splits; }
+  __device__ __forceinline__ void advance(const SweepParams& prm, int stride) {
+    if (++t == t1) start(item + stride, prm);
+  }
+};
+
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = 2>
 __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid_constant__ SweepParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
@@ -178,49 +200,40 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* stage_mem = reinterpret_cast<uint32_t*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * STAGE_BYTES);
-  uint64_t* empty = full + kStages;
-  uint32_t* lut_s = reinterpret_cast<uint32_t*>(empty + kStages);
+  unsigned* done = reinterpret_cast<unsigned*>(full + kStages);   // warps finished with a stage
+  uint32_t* lut_s = reinterpret_cast<uint32_t*>(full + 2 * kStages);
   unsigned long long* lists = reinterpret_cast<unsigned long long*>(lut_s + kMaxLutWords);  // [ROWS_CTA][k1]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  // lookahead cursor: the tile that goes into a stage when its current tile has been consumed
+  SweepCursor la;
+  la.start(blockIdx.x, prm);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
+      done[s] = 0;
     }
     fence_mbar_init();
   }
   if (LUT && tid < kMaxLutWords) lut_s[tid] = prm.lut[tid];
   __syncthreads();
+#pragma unroll 1
+  for (int s = 0; s < kStages; ++s) {   // prologue: fill the ring
+    if (tid == 0 && la.valid(prm)) {
+      mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+      bulk_g2s(stage_mem + s * (BN * COLW), prm.str + static_cast<size_t>(la.t) * BN * COLW, STAGE_BYTES, &full[s]);
+    }
+    if (la.valid(prm)) la.advance(prm, gridDim.x);
+  }
 
   const int n_items = prm.n_rowblocks * prm.n_splits;
   int stage = 0;
   uint32_t phase = 0;
 
-  if (warp == kConsumerWarps) {
-    // ---------------- producer: one lane feeds the ring -----------------
-    if (lane == 0) {
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item / prm.n_rowblocks;
-        const int t0 = split * prm.tiles_per_split;
-        const int t1 = min(t0 + prm.tiles_per_split, prm.n_tiles);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait_suspended(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          bulk_g2s(stage_mem + stage * (BN * COLW), prm.str + static_cast<size_t>(t) * BN * COLW, STAGE_BYTES,
-                   &full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumers ------------------------------------------
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int split = item / prm.n_rowblocks;
     const int rb = item - split * prm.n_rowblocks;
@@ -324,8 +337,20 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
           }
         }
       }
+      // done with this stage: the last warp to get here refills it with the lookahead tile
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (lane == 0) {
+        if (atom_add_acq_rel_cta(&done[stage], 1u) == kConsumerWarps - 1) {
+          done[stage] = 0;
+          if (la.valid(prm)) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            bulk_g2s(stage_mem + stage * (BN * COLW), prm.str + static_cast<size_t>(la.t) * BN * COLW,
+                     STAGE_BYTES, &full[stage]);
+          }
+        }
+      }
+      if (la.valid(prm)) la.advance(prm, gridDim.x);
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 
@@ -363,10 +388,10 @@ struct SweepLaunch {
 template <int P, int W>
 inline size_t sweep_smem_bytes(size_t list_bytes) {
   return static_cast<size_t>(kStages) * TileCols<W>::value * P * W * 4 + 2 * kStages * sizeof(uint64_t) +
-         kMaxLutWords * 4 + list_bytes;
+         kMaxLutWords * 4 + list_bytes;   // ring + barriers/counters + lut + kNN lists
 }
 
-template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = (TM == 1 ? 2 : 1)>
+template <int P, int W, int TM, int MODE, bool LUT, int WEIGHT, int MINB = 2>
 int launch_one(const SweepParams& prm, const SweepLaunch& l) {
   auto kern = sweep_kernel<P, W, TM, MODE, LUT, WEIGHT, MINB>;
   const size_t smem = sweep_smem_bytes<P, W>(l.list_bytes);
@@ -388,8 +413,9 @@ int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
   switch (l.mode) {
     case MODE_KNN:
       if constexpr (P == 5 && W == 8) {
-        if (l.rows_per_thread == 2) return launch_one<P, W, 2, MODE_KNN, false, 0>(prm, l);
+        if (l.rows_per_thread == 2) return launch_one<P, W, 2, MODE_KNN, false, 0, 2>(prm, l);
         if (l.rows_per_thread == 3) return launch_one<P, W, 1, MODE_KNN, false, 0, 3>(prm, l);   // 3 CTAs / SM
+        if (l.rows_per_thread == 4) return launch_one<P, W, 2, MODE_KNN, false, 0, 1>(prm, l);   // 1 CTA / SM
       }
       return launch_one<P, W, 1, MODE_KNN, false, 0>(prm, l);
     case MODE_COUNT:
