@@ -82,8 +82,14 @@ __global__ void pack_kernel(const T* __restrict__ tokens, long long N, int L, lo
 // ---- integer pipe peak probe ------------------------------------------------------------
 // Register-only loops with the instruction mix of the Hamming inner loop; the achieved
 // lane-op rate is the "speed of light" the sweep kernel's roofline fraction is quoted on.
+__device__ __forceinline__ unsigned probe_mad(unsigned a, unsigned b, unsigned c) {
+  unsigned r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 template <int MIX>
-__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t seed, unsigned one) {
   uint32_t a[8], b[5];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters,
   uint32_t acc = 0;
   for (int it = 0; it < iters; ++it) {
     if (MIX == 0) {
-      // per "word": 5 LOP3 + 1 POPC + 1 IADD, 8 independent words like W=8
+      // per "word": 5 LOP3 + 1 POPC + 1 add (as IMAD on the FMA pipe, exactly like the sweep
+      // kernel's inner loop), 8 independent words like W=8
       uint32_t m[8];
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
@@ -103,9 +110,11 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters,
         m[w] |= a[(w + 4) & 7] ^ b[4];
       }
 #pragma unroll
-      for (int w = 0; w < 8; ++w) acc += __popc(m[w]);
+      for (int w = 0; w < 8; ++w) acc = probe_mad(__popc(m[w]), one, acc);
+      if ((it & 15) == 15) {
 #pragma unroll
-      for (int i = 0; i < 5; ++i) b[i] = b[i] * 3u + acc;  // keep the stream operand changing (IMAD, other pipe)
+        for (int i = 0; i < 5; ++i) b[i] = b[i] * 3u + acc;  // keep the stream operand changing
+      }
     } else if (MIX == 1) {
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
@@ -205,9 +214,9 @@ int pg_measure_int_peak(int mix, int iters, double* lane_ops_per_s, double* ms_o
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     PG_CUDA(cudaEventRecord(a, 0));
-    if (mix == 0) int_peak_kernel<0><<<blocks, threads>>>(out, iters, 12345u + rep);
-    else if (mix == 1) int_peak_kernel<1><<<blocks, threads>>>(out, iters, 12345u + rep);
-    else int_peak_kernel<2><<<blocks, threads>>>(out, iters, 12345u + rep);
+    if (mix == 0) int_peak_kernel<0><<<blocks, threads>>>(out, iters, 12345u + rep, 1u);
+    else if (mix == 1) int_peak_kernel<1><<<blocks, threads>>>(out, iters, 12345u + rep, 1u);
+    else int_peak_kernel<2><<<blocks, threads>>>(out, iters, 12345u + rep, 1u);
     PG_CUDA(cudaEventRecord(b, 0));
     PG_CUDA(cudaEventSynchronize(b));
     float ms = 0;

@@ -39,6 +39,8 @@ class CudaEngine:
     """One engine per process/GPU.  ``device`` defaults to ``cuda:LOCAL_RANK`` as set by the
     launcher, i.e. the current torch device."""
 
+    sharded_pack = True   # packed row shards can be all-gathered into one table (graph.pack_table)
+
     def __init__(self, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("prograph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

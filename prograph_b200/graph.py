@@ -162,6 +162,38 @@ def _to_host(t):
 # ---------------------------------------------------------------------------------
 # fused Hamming path
 # ---------------------------------------------------------------------------------
+def pack_table(eng, X, rank, world, group):
+    """Bit-plane table of the whole representation on this rank's GPU.
+
+    Single rank: one pack of the whole matrix.  Several ranks with tile-aligned row blocks:
+    every rank uploads and packs only its own rows and the packed shards are all-gathered
+    (NCCL over NVLink) straight into one table -- 160 B per sequence instead of each rank
+    pushing the whole token matrix through its PCIe link."""
+    n = X.shape[0]
+    if (world <= 1 or n < world or not _shard.is_tile_aligned(n, world)
+            or not getattr(eng, "sharded_pack", False)):
+        return eng.pack(X)
+    row0, rows = _shard.row_range(n, rank, world)
+    per = _shard.rows_per_rank(n, world)
+    mine = eng.to_device(X[row0:row0 + rows])
+    # the ranks must agree on the plane count: take it from the global token range
+    lim = torch.stack([mine.max().to(torch.float64), (-mine.min()).to(torch.float64)])
+    torch.distributed.all_reduce(lim, op=torch.distributed.ReduceOp.MAX, group=group)
+    hi, lo = float(lim[0]), -float(lim[1])
+    if lo < 0 or hi >= 256:
+        raise OverflowError("values are not integer tokens in [0, 256)")
+    planes = 5 if hi < 32 else 8
+    part = eng.pack(mine, planes=planes)
+    words = part.words
+    shard_buf = torch.zeros((per, planes, words), dtype=torch.int32, device=part.data.device)
+    shard_buf[: min(per, part.data.shape[0])] = part.data[:per]
+    full = torch.empty((world * per, planes, words), dtype=torch.int32, device=part.data.device)
+    torch.distributed.all_gather_into_tensor(full, shard_buf, group=group)
+    from .engine import PackedTable
+    return PackedTable(full, n, part.L, planes, words)
+
+
+
 def hamming_knn_device(eng, own, stream, k, similarity, row0, rows):
     """kNN rows [row0,row0+rows) of `own` against `stream` (both PackedTable)."""
     kk = min(k, stream.rows - 1)          # [:, 1:k+1] of a row of N entries
@@ -287,7 +319,7 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     packed = None
     if kind == "hamming":
         try:
-            packed = eng.pack(X)
+            packed = pack_table(eng, X, rank, world, group)
             if packed.words > 8:
                 packed = None
         except OverflowError:
