@@ -177,7 +177,7 @@ def pack_table(eng, X, rank, world, group):
     per = _shard.rows_per_rank(n, world)
     mine = eng.to_device(X[row0:row0 + rows])
     # the ranks must agree on the plane count: take it from the global token range
-    lim = torch.stack([mine.max().to(torch.float64), (-mine.min()).to(torch.float64)])
+    lim = torch.stack([mine.max().to(torch.float64), -(mine.min().to(torch.float64))])
     torch.distributed.all_reduce(lim, op=torch.distributed.ReduceOp.MAX, group=group)
     hi, lo = float(lim[0]), -float(lim[1])
     if lo < 0 or hi >= 256:
