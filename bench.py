@@ -174,6 +174,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic_bytes(n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, per launch, from the
+    committed `ncu --set full` capture of this exact configuration (profiles/); None otherwise."""
+    if n != 1_000_000 or world != 1:
+        return None
+    path = os.path.join(ROOT, "profiles", "r1_ncu_sweep_r1d.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    try:
+        for line in open(path):
+            parts = [p.strip().strip('"') for p in line.split(",")]
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(parts[2]) * scale.get(parts[1], 1.0)
+    except OSError:
+        return None
+    return total or None
+
+
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
@@ -276,13 +294,13 @@ def run_b200(args):
         roofline = {
             "bound": "int-alu", "kernel": "pg::sweep_kernel<5,8,KNN>", "achieved": achieved / 1e12,
             "peak": peak_ops / 1e12, "unit": "Tlane-op/s", "frac": achieved / peak_ops,
-            "peak_source": "measured live: pg_measure_int_peak(mix 5 LOP3:1 POPC:1 IADD), register-only kernel",
+            "peak_source": "measured live: pg_measure_int_peak (register-only kernel, 5 LOP3 : 1 POPC : 1 IMAD like the sweep)",
             "lane_ops_per_pair": lane_ops_per_pair, "pairs_per_launch": pairs_per_launch,
             "kernel_ms": avg_ms, "kernel_launches": sweep_launches,
             "kernel_share_of_step": sweep_ms / ms_total,
             "gpairs_per_s_kernel": pairs_per_launch / (avg_ms * 1e-3) / 1e9,
             "lop3_peak_tlops": lop_ops / 1e12, "popc_peak_tlops": popc_ops / 1e12,
-            "traffic": None,
+            "traffic": ncu_traffic_bytes(n, world),
             "hbm": {"algorithmic_bytes_per_launch": hbm_algo, "achieved_gbs": hbm_algo / (avg_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
