@@ -138,6 +138,33 @@ int pg_hamming_values_tile(const void* X, int64_t N, const void* Y, int64_t M, i
                            int D, int dtype, int weight, void* out, int64_t ld, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Minkowski p=2 on integer tokens as a tensor-core contraction (tcgen05 kind::i8, TMEM
+ * accumulators): S = |x|^2 + |y|^2 - 2 x.y is exact in int32 and the reference's rounding
+ * chain (minkowski.py:36-40) is a function of S alone.
+ *   value_kind 0: fp16 chain  d = fp16(sqrt(fp16(S)))   (the dtype build_graph stages, prograph.py:726)
+ *   value_kind 1: int64 tokens d = sqrtf(float(S))       (float32 result)
+ * Operand tables: uint8 rows in K-major 8x16-byte core-matrix order
+ *   byte(r, k) = ((r/8)*(K/16) + k/16)*128 + (r%8)*16 + k%16,  K = pg_gemm_width(L),
+ * padded to pg_gemm_rows(N) rows, plus int32 squared norms per row (pad rows: 0x3fffffff).
+ * ------------------------------------------------------------------------- */
+int     pg_gemm_width(int L);
+int64_t pg_gemm_rows(int64_t N);
+int pg_gemm_pack(const void* tokens, int dtype, int64_t N, int L, int64_t ld,
+                 uint8_t* table, int32_t* norms, int K, int max_token, int* flag, void* stream);
+/* *flag is set when a value is not an integer in [0, max_token] (<= 255; the fp16 chain needs <= 45 so that
+ * every squared difference is exact in fp16) */
+/* out[m*ld + n] (fp16 for value_kind 0, float32 for 1): queries A (M rows) x dataset B (N rows) */
+int pg_minkowski2_gemm_tile(const uint8_t* A, const int32_t* normA, int64_t M,
+                            const uint8_t* B, const int32_t* normB, int64_t N, int K,
+                            int value_kind, int similarity, void* out, int64_t ld, void* stream);
+/* fused kNN (prograph.py:755-765 with distance=minkowski): sorted positions [drop, drop+k) of every
+ * query row in (value, index) order -- descending value for similarity; out_val fp16 / float32 */
+int pg_minkowski2_gemm_knn(const uint8_t* A, const int32_t* normA, int64_t M,
+                           const uint8_t* B, const int32_t* normB, int64_t N, int K,
+                           int value_kind, int similarity, int k, int drop,
+                           int64_t* out_idx, void* out_val, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Consumers of a materialised (rows x N) tile: used for Minkowski, for user supplied
  * distance callables (README.md:48) and for single-row queries.
  * ------------------------------------------------------------------------- */

@@ -45,6 +45,11 @@ SIGNATURES = {
     "pg_exclusive_scan_i64": (_i, [_vp, _i64, _vp, _vp]),
     "pg_minkowski_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _dbl, _i, _vp, _i64, _vp]),
     "pg_hamming_values_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i64, _vp]),
+    "pg_gemm_width": (_i, [_i]),
+    "pg_gemm_rows": (_i64, [_i64]),
+    "pg_gemm_pack": (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _vp]),
+    "pg_minkowski2_gemm_tile": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp]),
+    "pg_minkowski2_gemm_knn": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pg_tile_topk": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "pg_tile_threshold_count": (_i, [_vp, _i, _i64, _i64, _i64, _i, _dbl, _i, _i, _vp, _vp]),
     "pg_tile_threshold_fill": (_i, [_vp, _i, _i64, _i64, _i64, _i, _dbl, _i, _i, _vp, _vp, _vp, _vp]),

@@ -1,0 +1,476 @@
+// Minkowski p=2 on integer tokens as an int8 tensor-core contraction (tcgen05, sm_100a).
+//
+// For integer-valued rows the reference's  pow(sum(pow(X - Y, 2)), 1/2)  (minkowski.py:36)
+// depends only on the exact integer  S = |x|^2 + |y|^2 - 2 x.y :
+//   * int64 tokens  : d = sqrtf(float(S))                         (float32 result)
+//   * fp16 staging  : d = fp16(sqrtf(fp16(S)))  (prograph.py:726; every term of the chain is an
+//                     exactly representable integer, the fp32 sum is exact)
+// and x.y is a plain GEMM with K = L: the one metric on this path that really is a dense
+// contraction.  It runs here as  tcgen05.mma.cta_group::1.kind::i8  (uint8 x uint8 -> int32,
+// exact) with the accumulator in TMEM:
+//   * operands are stored in HBM already in the K-major, no-swizzle core-matrix layout the
+//     MMA reads from shared memory (8 rows x 16 bytes per core matrix), so tiles are moved
+//     with 1-D bulk async copies (cp.async.bulk + mbarrier), no tensor map needed;
+//   * one CTA = 128 query rows (A tile, resident) against the whole dataset streamed in
+//     128-row B tiles through a 4-stage ring; M=128, N=128, K=32 per instruction;
+//   * two 128-column TMEM accumulators: the MMA of tile t+1 overlaps the epilogue of tile t;
+//   * warp roles: 4 epilogue warps (thread = TMEM lane = query row), 1 producer lane,
+//     1 MMA-issuing lane (which also owns the TMEM allocation);
+//   * epilogues: materialised tile (minkowski.py:36-40) or fused kNN: a candidate test in
+//     S-space against a per-row integer threshold (min + one vote per 32 columns), rare
+//     warp-cooperative insertion into a sorted (value, index) list in shared memory; the
+//     N x N matrix never reaches HBM.
+#include "pg_sweep.cuh"   // knn_insert_coop, kMaxListRounds
+
+namespace pg {
+
+constexpr int GM = 128;         // query rows per CTA (MMA M)
+constexpr int GN = 128;         // dataset rows per B tile (MMA N)
+constexpr int GSTAGES = 4;
+constexpr int GTHREADS = 192;   // 4 epilogue warps + producer warp + MMA warp
+constexpr int PAD_NORM = 0x3fffffff;
+
+enum GemmValue { GV_F16 = 0, GV_F32 = 1 };     // which rounding chain turns S into the distance
+enum GemmMode { GM_TILE = 0, GM_KNN = 1 };
+
+// ---- tcgen05 / TMEM PTX -----------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous (128 B); LBO = distance between the
+// two core matrices an MMA reads along K, SBO = distance between 8-row groups (cute/arch/
+// mma_sm100_desc.hpp, canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;   // descriptor version for sm_100
+  return d;          // layout_type (bits 61-63) = 0: SWIZZLE_NONE
+}
+
+// ---- S -> value -> ordered key -------------------------------------------------------------
+template <int VK>
+__device__ __forceinline__ uint32_t value_bits(int S, bool similarity) {
+  const float s = static_cast<float>(S);
+  if (VK == GV_F16) {
+    const float sh = __half2float(__float2half_rn(s));
+    __half d = __float2half_rn(sqrtf(sh));
+    if (similarity) d = __float2half_rn(__fdiv_rn(1.0f, __half2float(__float2half_rn(1.0f + __half2float(d)))));
+    return static_cast<uint32_t>(__half_as_ushort(d));
+  } else {
+    float d = sqrtf(s);
+    if (similarity) d = __fdiv_rn(1.0f, 1.0f + d);
+    return __float_as_uint(d);
+  }
+}
+// values are non-negative: their bit patterns order like the values; similarities sort descending
+__device__ __forceinline__ uint32_t order_key(uint32_t bits, bool similarity) { return similarity ? ~bits : bits; }
+
+// Smallest S in [0, 2^25] whose key is >= tau_key (keys are monotone non-decreasing in S): a
+// warp-cooperative 32-ary search, 5 rounds.  All lanes call it with the same tau_key.
+// Invariant: every S below `base` has key < tau_key.
+template <int VK>
+__device__ __forceinline__ int s_threshold(uint32_t tau_key, bool similarity, int lane) {
+  int base = 0;
+#pragma unroll 1
+  for (int step = 1 << 20;; step >>= 5) {
+    const int probe = base + lane * step;
+    const bool ge = order_key(value_bits<VK>(probe, similarity), similarity) >= tau_key;
+    const unsigned b = __ballot_sync(0xffffffffu, ge);
+    const int first = b ? __ffs(b) - 1 : 32;      // first probe that reaches tau_key
+    if (first == 0) return base;
+    if (step == 1) return base + first;
+    base += (first - 1) * step + 1;                // answer lies in (probe[first-1], probe[first]]
+  }
+}
+
+struct GemmParams {
+  const uint8_t* A; const int* normA; long long M;       // queries (own rows)
+  const uint8_t* B; const int* normB; long long N;       // dataset (stream rows)
+  int K;                                                 // padded width, multiple of 32
+  int similarity;
+  // tile
+  void* out; long long ld;
+  // kNN
+  int k1, k, drop;
+  long long* out_idx; void* out_val;
+};
+
+template <int VK, int MODE>
+__global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int K = prm.K;
+  const uint32_t tile_bytes = GM * K;                     // A and B tiles have the same shape
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tile_bytes * (1 + GSTAGES));
+  uint64_t* full = bars;                  // [GSTAGES] B tile landed
+  uint64_t* empty = bars + GSTAGES;       // [GSTAGES] MMAs reading the stage have completed
+  uint64_t* acc_full = bars + 2 * GSTAGES;    // [2] accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + 2;         // [2] epilogue has drained the accumulator
+  uint64_t* a_full = acc_empty + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [GM][k1]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const long long row0 = static_cast<long long>(blockIdx.x) * GM;
+  const int n_tiles = static_cast<int>((prm.N + GN - 1) / GN);
+  const bool sim = prm.similarity != 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    mbar_init(a_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_holder, 2 * GN);          // 256 columns: two fp32/int32 accumulators
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, tile_bytes);
+      bulk_g2s(sA, prm.A + static_cast<size_t>(row0) * K, tile_bytes, a_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_suspended(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], tile_bytes);
+        bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes, prm.B + static_cast<size_t>(t) * GN * K, tile_bytes,
+                 &full[stage]);
+        if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      // instruction descriptor: D=S32, A=B=UINT8, K-major both, N=128, M=128
+      const uint32_t idesc = (2u << 4) | (static_cast<uint32_t>(GN >> 3) << 17) | (static_cast<uint32_t>(GM >> 4) << 24);
+      const uint32_t sbo = static_cast<uint32_t>(K / 16) * 128u;
+      mbar_wait_suspended(a_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int acc = t & 1;
+        mbar_wait_suspended(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
+        mbar_wait_suspended(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA);
+        const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(stage) * tile_bytes);
+        for (int j = 0; j < K / 32; ++j) {
+          umma_i8(tmem_base + acc * GN, umma_desc(a_addr + j * 256, 128, sbo), umma_desc(b_addr + j * 256, 128, sbo),
+                  idesc, j > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);       // the stage may be refilled once these MMAs have read it
+        umma_commit(&acc_full[acc]);      // ... and the accumulator is complete
+        if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread = TMEM lane = query row ----------------
+    const long long row = row0 + tid;
+    const bool valid = row < prm.M;
+    const int nq = valid ? prm.normA[row] : 0;
+    unsigned long long* my_list = lists + static_cast<size_t>(tid) * prm.k1;
+    int tprime = valid ? 0x7fffffff : static_cast<int>(0x80000000);   // candidate iff (nx - 2 dot) < tprime
+    if (MODE == GM_KNN) {
+      for (int j = 0; j < prm.k1; ++j) my_list[j] = ~0ull;
+      __syncwarp();
+    }
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = t & 1;
+      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const long long col_tile = static_cast<long long>(t) * GN;
+#pragma unroll 1
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t dot[32];
+        tmem_ld32(tmem_base + lane_base + acc * GN + c * 32, dot);
+        const long long col0 = col_tile + c * 32;
+        int v[32];   // nx - 2 dot  (S = nq + v)
+        const int4* np = reinterpret_cast<const int4*>(prm.normB + col0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int4 nx = __ldg(np + g);
+          v[4 * g + 0] = nx.x - 2 * static_cast<int>(dot[4 * g + 0]);
+          v[4 * g + 1] = nx.y - 2 * static_cast<int>(dot[4 * g + 1]);
+          v[4 * g + 2] = nx.z - 2 * static_cast<int>(dot[4 * g + 2]);
+          v[4 * g + 3] = nx.w - 2 * static_cast<int>(dot[4 * g + 3]);
+        }
+        if (MODE == GM_TILE) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < prm.N) {
+                const uint32_t bits = value_bits<VK>(nq + v[j], sim);
+                const size_t at = static_cast<size_t>(row) * prm.ld + col0 + j;
+                if (VK == GV_F16) static_cast<unsigned short*>(prm.out)[at] = static_cast<unsigned short>(bits);
+                else static_cast<uint32_t*>(prm.out)[at] = bits;
+              }
+            }
+          }
+        } else {
+          int best = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) best = min(best, v[j]);
+          if (__any_sync(0xffffffffu, best < tprime)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              unsigned cand = __ballot_sync(0xffffffffu, v[j] < tprime);
+              while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int S = __shfl_sync(0xffffffffu, nq + v[j], src);
+                const uint32_t key32 = order_key(value_bits<VK>(S, sim), sim);
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(key32) << 32) | static_cast<unsigned>(col0 + j);
+                unsigned long long* lst = lists + static_cast<size_t>(warp * 32 + src) * prm.k1;
+                const uint32_t tau = knn_insert_coop(lst, prm.k1, key, lane);
+                const int thr = s_threshold<VK>(tau, sim, lane);     // candidates: S < thr
+                const int src_nq = __shfl_sync(0xffffffffu, nq, src);
+                if (lane == src) tprime = thr - src_nq;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+    if (MODE == GM_KNN && valid) {
+      for (int j = 0; j < prm.k; ++j) {
+        const int src_pos = prm.drop + j;
+        const size_t at = static_cast<size_t>(row) * prm.k + j;
+        const unsigned long long key = src_pos < prm.k1 ? my_list[src_pos] : ~0ull;
+        if (key == ~0ull) {
+          prm.out_idx[at] = -1;
+          if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = 0;
+          else static_cast<uint32_t*>(prm.out_val)[at] = 0;
+        } else {
+          uint32_t bits = static_cast<uint32_t>(key >> 32);
+          if (sim) bits = ~bits;
+          prm.out_idx[at] = static_cast<long long>(key & 0xffffffffull);
+          if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = static_cast<unsigned short>(bits);
+          else static_cast<uint32_t*>(prm.out_val)[at] = bits;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 2 * GN);
+}
+
+// ---- operand packing: tokens -> K-major core-matrix layout + squared norms -----------------
+template <typename T>
+__global__ void gemm_pack_kernel(const T* __restrict__ tokens, long long N, int L, long long ld, uint8_t* __restrict__ table,
+                                 int* __restrict__ norms, long long rows_padded, int K, int max_token,
+                                 int* __restrict__ flag) {
+  // one thread per (row, 16-byte chunk)
+  const int chunks = K / 16;
+  const long long total = rows_padded * chunks;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / chunks;
+    const int ch = static_cast<int>(i - row * chunks);
+    uint32_t w[4] = {0, 0, 0, 0};
+    int sq = 0;
+    if (row < N) {
+      for (int b = 0; b < 16; ++b) {
+        const int l = ch * 16 + b;
+        if (l < L) {
+          const double val = static_cast<double>(tokens[static_cast<size_t>(row) * ld + l]);
+          const int tok = static_cast<int>(val);
+          if (val != static_cast<double>(tok) || tok < 0 || tok > max_token) { atomicExch(flag, 1); continue; }
+          w[b >> 2] |= static_cast<uint32_t>(tok) << (8 * (b & 3));
+          sq += tok * tok;
+        }
+      }
+      if (sq) atomicAdd(norms + row, sq);
+    } else if (ch == 0) {
+      norms[row] = PAD_NORM;     // pad rows can never be candidates
+    }
+    uint4* dst = reinterpret_cast<uint4*>(table + ((row >> 3) * chunks + ch) * 128 + (row & 7) * 16);
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+template <>
+__global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long long N, int L, long long ld,
+                                         uint8_t* __restrict__ table, int* __restrict__ norms, long long rows_padded,
+                                         int K, int max_token, int* __restrict__ flag) {
+  const int chunks = K / 16;
+  const long long total = rows_padded * chunks;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / chunks;
+    const int ch = static_cast<int>(i - row * chunks);
+    uint32_t w[4] = {0, 0, 0, 0};
+    int sq = 0;
+    if (row < N) {
+      for (int b = 0; b < 16; ++b) {
+        const int l = ch * 16 + b;
+        if (l < L) {
+          const float val = __half2float(tokens[static_cast<size_t>(row) * ld + l]);
+          const int tok = static_cast<int>(val);
+          if (val != static_cast<float>(tok) || tok < 0 || tok > max_token) { atomicExch(flag, 1); continue; }
+          w[b >> 2] |= static_cast<uint32_t>(tok) << (8 * (b & 3));
+          sq += tok * tok;
+        }
+      }
+      if (sq) atomicAdd(norms + row, sq);
+    } else if (ch == 0) {
+      norms[row] = PAD_NORM;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(table + ((row >> 3) * chunks + ch) * 128 + (row & 7) * 16);
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+static size_t gemm_smem_bytes(int K, int k1) {
+  return static_cast<size_t>(GM) * K * (1 + GSTAGES) + (2 * GSTAGES + 5) * sizeof(uint64_t) + 16 +
+         static_cast<size_t>(GM) * k1 * 8;
+}
+
+template <int VK, int MODE>
+static int launch_gemm(const GemmParams& prm, cudaStream_t s) {
+  auto kern = mink_gemm_kernel<VK, MODE>;
+  const size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0);
+  if (smem > 227 * 1024) { set_error("minkowski GEMM: k or row width too large for shared memory (%zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const unsigned grid = static_cast<unsigned>(ceil_div(prm.M, GM));
+  kern<<<grid, GTHREADS, smem, s>>>(prm);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_gemm_width(int L) { return L <= 0 ? 0 : (L + 31) / 32 * 32; }
+int64_t pg_gemm_rows(int64_t N) { return N <= 0 ? 0 : round_up(N, GM); }
+
+int pg_gemm_pack(const void* tokens, int dtype, int64_t N, int L, int64_t ld, uint8_t* table, int32_t* norms, int K,
+                 int max_token, int* flag, void* stream) {
+  PG_CHECK_ARG(tokens && table && norms && flag, "null pointer");
+  PG_CHECK_ARG(N > 0 && L > 0 && ld >= L, "bad shape");
+  PG_CHECK_ARG(K % 32 == 0 && K >= L, "K must be a multiple of 32 and >= L");
+  PG_CHECK_ARG(max_token >= 1 && max_token <= 255, "max_token must be in [1,255]");
+  const long long rows_padded = pg_gemm_rows(N);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_CUDA(cudaMemsetAsync(norms, 0, sizeof(int32_t) * rows_padded, s));
+  const long long total = rows_padded * (K / 16);
+  long long blocks = ceil_div(total, 256);
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+#define PG_GP(T)                                                                                               \
+  gemm_pack_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const T*>(tokens), N, L, ld, table, \
+                                                                     norms, rows_padded, K, max_token, flag)
+  switch (dtype) {
+    case PG_U8: PG_GP(uint8_t); break;
+    case PG_I16: PG_GP(int16_t); break;
+    case PG_I32: PG_GP(int32_t); break;
+    case PG_I64: PG_GP(long long); break;
+    case PG_F16: PG_GP(__half); break;
+    case PG_F32: PG_GP(float); break;
+    case PG_F64: PG_GP(double); break;
+    default: set_error("unsupported token dtype %d", dtype); return PG_ERR_INVALID;
+  }
+#undef PG_GP
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+static int gemm_common(GemmParams& prm, const uint8_t* A, const int32_t* normA, int64_t M, const uint8_t* B,
+                       const int32_t* normB, int64_t N, int K, int value_kind, int similarity) {
+  PG_CHECK_ARG(A && normA && B && normB, "null operand");
+  PG_CHECK_ARG(M > 0 && N > 0 && N < (1ll << 32), "bad operand sizes");
+  PG_CHECK_ARG(value_kind == GV_F16 || value_kind == GV_F32, "bad value kind %d", value_kind);
+  if (K % 32 != 0 || K < 32 || K > 256) {
+    set_error("minkowski GEMM supports rows of up to 256 tokens (K=%d)", K);
+    return PG_ERR_UNSUPPORTED;
+  }
+  memset(&prm, 0, sizeof(prm));
+  prm.A = A; prm.normA = normA; prm.M = M;
+  prm.B = B; prm.normB = normB; prm.N = N;
+  prm.K = K;
+  prm.similarity = similarity;
+  return PG_OK;
+}
+
+int pg_minkowski2_gemm_tile(const uint8_t* A, const int32_t* normA, int64_t M, const uint8_t* B, const int32_t* normB,
+                            int64_t N, int K, int value_kind, int similarity, void* out, int64_t ld, void* stream) {
+  GemmParams prm;
+  int rc = gemm_common(prm, A, normA, M, B, normB, N, K, value_kind, similarity);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(out && ld >= N, "bad output");
+  prm.out = out;
+  prm.ld = ld;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return value_kind == GV_F16 ? launch_gemm<GV_F16, GM_TILE>(prm, s) : launch_gemm<GV_F32, GM_TILE>(prm, s);
+}
+
+int pg_minkowski2_gemm_knn(const uint8_t* A, const int32_t* normA, int64_t M, const uint8_t* B, const int32_t* normB,
+                           int64_t N, int K, int value_kind, int similarity, int k, int drop, int64_t* out_idx,
+                           void* out_val, void* stream) {
+  GemmParams prm;
+  int rc = gemm_common(prm, A, normA, M, B, normB, N, K, value_kind, similarity);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(out_idx && out_val && k >= 1 && drop >= 0, "bad kNN arguments");
+  if (k + drop > 32 * kMaxListRounds) { set_error("k=%d too large for the fused lists", k); return PG_ERR_UNSUPPORTED; }
+  prm.k = k;
+  prm.drop = drop;
+  prm.k1 = k + drop;
+  prm.out_idx = reinterpret_cast<long long*>(out_idx);
+  prm.out_val = out_val;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return value_kind == GV_F16 ? launch_gemm<GV_F16, GM_KNN>(prm, s) : launch_gemm<GV_F32, GM_KNN>(prm, s);
+}
+
+}  // extern "C"

@@ -35,6 +35,15 @@ class PackedTable:
         return self.data[i].reshape(-1)
 
 
+class GemmTable:
+    """uint8 token rows in the K-major core-matrix order the tcgen05 kernel reads, plus the
+    int32 squared norm of every row (pg_gemm_pack)."""
+    __slots__ = ("data", "norms", "rows", "L", "K", "max_token")
+
+    def __init__(self, data, norms, rows, L_, K, max_token):
+        self.data, self.norms, self.rows, self.L, self.K, self.max_token = data, norms, rows, L_, K, max_token
+
+
 class CudaEngine:
     """One engine per process/GPU.  ``device`` defaults to ``cuda:LOCAL_RANK`` as set by the
     launcher, i.e. the current torch device."""
@@ -182,6 +191,52 @@ class CudaEngine:
                                                 X.shape[1], _PG_DTYPE[X.dtype], weight, _ptr(out), X.shape[0],
                                                 self._stream()))
         return out
+
+    # ---- Minkowski p=2 on integer tokens: tcgen05 int8 contraction ---------------------------
+    GEMM_MAX_WIDTH = 256
+
+    def gemm_pack(self, tokens, max_token=255, K=None):
+        """(N, L) integer-valued tokens -> GemmTable; OverflowError if a value is not an integer
+        in [0, max_token]; Unsupported for rows wider than the kernel handles."""
+        t = self.to_device(tokens)
+        if t.dim() != 2 or t.shape[0] == 0 or t.shape[1] == 0:
+            raise ValueError("gemm_pack expects a non-empty (N, L) array")
+        if t.dtype not in _PG_DTYPE or t.dtype == torch.bool:
+            t = t.to(torch.int64)
+        N, L_ = int(t.shape[0]), int(t.shape[1])
+        K = int(self.lib.pg_gemm_width(L_)) if K is None else int(K)
+        if K > self.GEMM_MAX_WIDTH:
+            raise L.Unsupported("rows wider than 256 tokens take the element-wise kernel")
+        rows_pad = int(self.lib.pg_gemm_rows(N))
+        data = self.empty((rows_pad * K,), torch.uint8)
+        norms = self.empty((rows_pad,), torch.int32)
+        flag = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        L.check(self.lib.pg_gemm_pack(_ptr(t), _PG_DTYPE[t.dtype], N, L_, int(t.stride(0)), _ptr(data), _ptr(norms), K,
+                                      int(max_token), _ptr(flag), self._stream()))
+        if int(flag.item()):
+            raise OverflowError(f"values are not integer tokens in [0, {max_token}]")
+        return GemmTable(data, norms, N, L_, K, max_token)
+
+    def minkowski2_gemm_tile(self, data, queries, value_kind, similarity=False):
+        """(M, N) Minkowski p=2 matrix of integer-token tables (minkowski.py:36-40);
+        value_kind 0 -> fp16 chain, 1 -> float32 root of the exact integer sum."""
+        assert data.K == queries.K
+        out = self.empty((queries.rows, data.rows), torch.float16 if value_kind == 0 else torch.float32)
+        L.check(self.lib.pg_minkowski2_gemm_tile(_ptr(queries.data), _ptr(queries.norms), queries.rows, _ptr(data.data),
+                                                 _ptr(data.norms), data.rows, data.K, int(value_kind),
+                                                 1 if similarity else 0, _ptr(out), data.rows, self._stream()))
+        return out
+
+    def minkowski2_gemm_knn(self, data, queries, k, drop, value_kind, similarity=False):
+        """Fused Minkowski p=2 kNN of every query row against `data` (prograph.py:755-765)."""
+        assert data.K == queries.K
+        idx = self.empty((queries.rows, k), torch.int64)
+        val = self.empty((queries.rows, k), torch.float16 if value_kind == 0 else torch.float32)
+        L.check(self.lib.pg_minkowski2_gemm_knn(_ptr(queries.data), _ptr(queries.norms), queries.rows, _ptr(data.data),
+                                                _ptr(data.norms), data.rows, data.K, int(value_kind),
+                                                1 if similarity else 0, int(k), int(drop), _ptr(idx), _ptr(val),
+                                                self._stream()))
+        return idx, val
 
     # ---- tile consumers ----------------------------------------------------------------------
     def tile_topk(self, tile, k, drop=1, descending=False):
