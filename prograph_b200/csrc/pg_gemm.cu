@@ -14,8 +14,10 @@
 //   * one CTA = 128 query rows (A tile, resident) against the whole dataset streamed in
 //     128-row B tiles through a 4-stage ring; M=128, N=128, K=32 per instruction;
 //   * two 128-column TMEM accumulators: the MMA of tile t+1 overlaps the epilogue of tile t;
-//   * warp roles: 4 epilogue warps (thread = TMEM lane = query row), 1 producer lane,
-//     1 MMA-issuing lane (which also owns the TMEM allocation);
+//   * warp roles: 8 epilogue warps in two groups that alternate tiles (thread = TMEM lane =
+//     query row, each group keeps its own lists, merged at the end), 1 producer lane,
+//     1 MMA-issuing lane (which also owns the TMEM allocation); the dataset norms ride along
+//     with the B tiles into a small shared-memory ring;
 //   * epilogues: materialised tile (minkowski.py:36-40) or fused kNN: a candidate test in
 //     S-space against a per-row integer threshold (min + one vote per 32 columns), rare
 //     warp-cooperative insertion into a sorted (value, index) list in shared memory; the
@@ -27,7 +29,10 @@ namespace pg {
 constexpr int GM = 128;         // query rows per CTA (MMA M)
 constexpr int GN = 128;         // dataset rows per B tile (MMA N)
 constexpr int GSTAGES = 4;
-constexpr int GTHREADS = 192;   // 4 epilogue warps + producer warp + MMA warp
+constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp + MMA warp
+constexpr int GPROD_WARP = 8;
+constexpr int GMMA_WARP = 9;
+constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
 constexpr int PAD_NORM = 0x3fffffff;
 
 enum GemmValue { GV_F16 = 0, GV_F32 = 1 };     // which rounding chain turns S into the distance
@@ -133,6 +138,19 @@ struct GemmParams {
   long long* out_idx; void* out_val;
 };
 
+// Single-lane waits of the producer / MMA issuer: poll with a short sleep (try_wait with a
+// suspend-time hint was measured to wake only at the time limit).
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 template <int VK, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -140,14 +158,15 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const uint32_t tile_bytes = GM * K;                     // A and B tiles have the same shape
   uint8_t* sA = smem;
   uint8_t* sB = smem + tile_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tile_bytes * (1 + GSTAGES));
-  uint64_t* full = bars;                  // [GSTAGES] B tile landed
+  int* sNorm = reinterpret_cast<int*>(smem + tile_bytes * (1 + GSTAGES));        // [GNORM_SLOTS][GN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + GNORM_SLOTS * GN);
+  uint64_t* full = bars;                  // [GSTAGES] B tile (+ its norms) landed
   uint64_t* empty = bars + GSTAGES;       // [GSTAGES] MMAs reading the stage have completed
   uint64_t* acc_full = bars + 2 * GSTAGES;    // [2] accumulator ready for the epilogue
   uint64_t* acc_empty = acc_full + 2;         // [2] epilogue has drained the accumulator
   uint64_t* a_full = acc_empty + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
-  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [GM][k1]
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [2][GM][k1]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -162,13 +181,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
     mbar_init(a_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_holder, 2 * GN);          // 256 columns: two fp32/int32 accumulators
+  if (warp == GMMA_WARP) tmem_alloc(tmem_holder, 2 * GN);  // 256 columns: two int32 accumulators
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 4) {
+  if (warp == GPROD_WARP) {
     // ---------------- producer ----------------
     if (lane == 0) {
       mbar_arrive_expect_tx(a_full, tile_bytes);
@@ -176,26 +195,29 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_suspended(&empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full[stage], tile_bytes);
+        mbar_wait_poll(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], tile_bytes + GN * 4);
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes, prm.B + static_cast<size_t>(t) * GN * K, tile_bytes,
                  &full[stage]);
+        // the norms of tile t live in slot t % GNORM_SLOTS until the epilogue of tile t is done;
+        // slot reuse (tile t + 8) is ordered behind MMA t+4, i.e. behind the epilogue of tile t+2
+        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t) * GN, GN * 4, &full[stage]);
         if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == GMMA_WARP) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       // instruction descriptor: D=S32, A=B=UINT8, K-major both, N=128, M=128
       const uint32_t idesc = (2u << 4) | (static_cast<uint32_t>(GN >> 3) << 17) | (static_cast<uint32_t>(GM >> 4) << 24);
       const uint32_t sbo = static_cast<uint32_t>(K / 16) * 128u;
-      mbar_wait_suspended(a_full, 0);
+      mbar_wait_poll(a_full, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int acc = t & 1;
-        mbar_wait_suspended(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
-        mbar_wait_suspended(&full[stage], phase);
+        mbar_wait_poll(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
+        mbar_wait_poll(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA);
         const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(stage) * tile_bytes);
@@ -209,32 +231,36 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       }
     }
   } else {
-    // ---------------- epilogue: thread = TMEM lane = query row ----------------
-    const long long row = row0 + tid;
+    // ---------------- epilogue: two warp groups alternate tiles; thread = TMEM lane = query row ---
+    const int group = warp >> 2;                 // 0: even tiles (accumulator 0), 1: odd tiles
+    const int r_loc = tid & (GM - 1);            // query row within the CTA
+    const int qwarp = warp & 3;                  // TMEM lane quarter this warp may read
+    const long long row = row0 + r_loc;
     const bool valid = row < prm.M;
     const int nq = valid ? prm.normA[row] : 0;
-    unsigned long long* my_list = lists + static_cast<size_t>(tid) * prm.k1;
+    unsigned long long* my_list = lists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
     int tprime = valid ? 0x7fffffff : static_cast<int>(0x80000000);   // candidate iff (nx - 2 dot) < tprime
     if (MODE == GM_KNN) {
       for (int j = 0; j < prm.k1; ++j) my_list[j] = ~0ull;
       __syncwarp();
     }
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int acc = t & 1;
+    const uint32_t lane_base = static_cast<uint32_t>(qwarp * 32) << 16;
+    for (int t = group; t < n_tiles; t += 2) {
+      const int acc = group;
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
       const long long col_tile = static_cast<long long>(t) * GN;
+      const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
 #pragma unroll 1
       for (int c = 0; c < GN / 32; ++c) {
         uint32_t dot[32];
         tmem_ld32(tmem_base + lane_base + acc * GN + c * 32, dot);
         const long long col0 = col_tile + c * 32;
         int v[32];   // nx - 2 dot  (S = nq + v)
-        const int4* np = reinterpret_cast<const int4*>(prm.normB + col0);
+        const int4* np = reinterpret_cast<const int4*>(nrm + c * 32);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const int4 nx = __ldg(np + g);
+          const int4 nx = np[g];
           v[4 * g + 0] = nx.x - 2 * static_cast<int>(dot[4 * g + 0]);
           v[4 * g + 1] = nx.y - 2 * static_cast<int>(dot[4 * g + 1]);
           v[4 * g + 2] = nx.z - 2 * static_cast<int>(dot[4 * g + 2]);
@@ -242,13 +268,35 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         }
         if (MODE == GM_TILE) {
           if (valid) {
+            const size_t at = static_cast<size_t>(row) * prm.ld + col0;
+            if (VK == GV_F16) {
+              unsigned short* o = static_cast<unsigned short*>(prm.out) + at;
+              if (col0 + 32 <= prm.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < prm.N) {
-                const uint32_t bits = value_bits<VK>(nq + v[j], sim);
-                const size_t at = static_cast<size_t>(row) * prm.ld + col0 + j;
-                if (VK == GV_F16) static_cast<unsigned short*>(prm.out)[at] = static_cast<unsigned short>(bits);
-                else static_cast<uint32_t*>(prm.out)[at] = bits;
+                for (int g = 0; g < 4; ++g) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    w[e] = value_bits<VK>(nq + v[8 * g + 2 * e], sim) | (value_bits<VK>(nq + v[8 * g + 2 * e + 1], sim) << 16);
+                  reinterpret_cast<uint4*>(o)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < prm.N) o[j] = static_cast<unsigned short>(value_bits<VK>(nq + v[j], sim));
+              }
+            } else {
+              uint32_t* o = static_cast<uint32_t*>(prm.out) + at;
+              if (col0 + 32 <= prm.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  reinterpret_cast<uint4*>(o)[g] =
+                      make_uint4(value_bits<VK>(nq + v[4 * g + 0], sim), value_bits<VK>(nq + v[4 * g + 1], sim),
+                                 value_bits<VK>(nq + v[4 * g + 2], sim), value_bits<VK>(nq + v[4 * g + 3], sim));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < prm.N) o[j] = value_bits<VK>(nq + v[j], sim);
               }
             }
           }
@@ -267,7 +315,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
                 const uint32_t key32 = order_key(value_bits<VK>(S, sim), sim);
                 const unsigned long long key =
                     (static_cast<unsigned long long>(key32) << 32) | static_cast<unsigned>(col0 + j);
-                unsigned long long* lst = lists + static_cast<size_t>(warp * 32 + src) * prm.k1;
+                unsigned long long* lst = lists + (static_cast<size_t>(group) * GM + qwarp * 32 + src) * prm.k1;
                 const uint32_t tau = knn_insert_coop(lst, prm.k1, key, lane);
                 const int thr = s_threshold<VK>(tau, sim, lane);     // candidates: S < thr
                 const int src_nq = __shfl_sync(0xffffffffu, nq, src);
@@ -281,28 +329,38 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-    if (MODE == GM_KNN && valid) {
-      for (int j = 0; j < prm.k; ++j) {
-        const int src_pos = prm.drop + j;
-        const size_t at = static_cast<size_t>(row) * prm.k + j;
-        const unsigned long long key = src_pos < prm.k1 ? my_list[src_pos] : ~0ull;
-        if (key == ~0ull) {
-          prm.out_idx[at] = -1;
-          if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = 0;
-          else static_cast<uint32_t*>(prm.out_val)[at] = 0;
-        } else {
-          uint32_t bits = static_cast<uint32_t>(key >> 32);
-          if (sim) bits = ~bits;
-          prm.out_idx[at] = static_cast<long long>(key & 0xffffffffull);
-          if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = static_cast<unsigned short>(bits);
-          else static_cast<uint32_t*>(prm.out_val)[at] = bits;
+    if (MODE == GM_KNN) {
+      // merge the two groups' lists of every row (both ascending, keys unique) and write out
+      named_barrier_sync(1, 8 * 32);
+      if (group == 0 && valid) {
+        const unsigned long long* la = lists + static_cast<size_t>(r_loc) * prm.k1;
+        const unsigned long long* lb = lists + (static_cast<size_t>(GM) + r_loc) * prm.k1;
+        int ia = 0, ib = 0;
+        for (int j = 0; j < prm.drop + prm.k; ++j) {
+          const unsigned long long ka = ia < prm.k1 ? la[ia] : ~0ull;
+          const unsigned long long kb = ib < prm.k1 ? lb[ib] : ~0ull;
+          const unsigned long long key = ka < kb ? ka : kb;
+          if (ka < kb) ++ia; else ++ib;
+          if (j < prm.drop) continue;
+          const size_t at = static_cast<size_t>(row) * prm.k + (j - prm.drop);
+          if (key == ~0ull) {
+            prm.out_idx[at] = -1;
+            if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = 0;
+            else static_cast<uint32_t*>(prm.out_val)[at] = 0;
+          } else {
+            uint32_t bits = static_cast<uint32_t>(key >> 32);
+            if (sim) bits = ~bits;
+            prm.out_idx[at] = static_cast<long long>(key & 0xffffffffull);
+            if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[at] = static_cast<unsigned short>(bits);
+            else static_cast<uint32_t*>(prm.out_val)[at] = bits;
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 2 * GN);
+  if (warp == GMMA_WARP) tmem_dealloc(tmem_base, 2 * GN);
 }
 
 // ---- operand packing: tokens -> K-major core-matrix layout + squared norms -----------------
@@ -371,8 +429,8 @@ __global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long
 }
 
 static size_t gemm_smem_bytes(int K, int k1) {
-  return static_cast<size_t>(GM) * K * (1 + GSTAGES) + (2 * GSTAGES + 5) * sizeof(uint64_t) + 16 +
-         static_cast<size_t>(GM) * k1 * 8;
+  return static_cast<size_t>(GM) * K * (1 + GSTAGES) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 5) * sizeof(uint64_t) +
+         16 + 2 * static_cast<size_t>(GM) * k1 * 8;
 }
 
 template <int VK, int MODE>

@@ -17,8 +17,29 @@ def staged_dtype(X, Y, p):
     return torch.float32
 
 
+def gemm_value_kind(dt):
+    """Rounding chain of the tensor-core path for a compute dtype: 0 = fp16 chain (needs tokens
+    <= 31 so that every squared difference is an exact fp16 integer), 1 = float32 root of the
+    exact integer sum (int64 and float32 inputs), None = not applicable."""
+    if dt == torch.float16:
+        return 0, 31
+    if dt in (torch.int64, torch.float32):
+        return 1, 255
+    return None, None
+
+
 def minkowski_matrix(eng, X, Y, p=2, similarity=False):
+    from .. import _lib as L
     dt = staged_dtype(X, Y, p)
+    kind, max_token = gemm_value_kind(dt)
+    if float(p) == 2.0 and kind is not None and X.shape[1] <= eng.GEMM_MAX_WIDTH:
+        # p=2 on integer-valued rows is an exact int8 contraction: tensor cores (pg_gemm.cu)
+        try:
+            tx = eng.gemm_pack(X, max_token=max_token)
+            ty = eng.gemm_pack(Y, max_token=max_token, K=tx.K)
+            return eng.minkowski2_gemm_tile(tx, ty, kind, similarity=similarity)
+        except (OverflowError, L.Unsupported):
+            pass
     Xd, Yd = eng.to_device(X, dt), eng.to_device(Y, dt)
     return eng.minkowski_tile(Xd, Yd, 0, Yd.shape[0], p=p, similarity=similarity)
 

@@ -236,7 +236,7 @@ def _tile_rows(n_cols, itemsize, batch_size):
     return int(max(batch_size, min(rows, 4096)))
 
 
-def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows):
+def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows, gemm=None):
     """Yield (b0, tile) with tile = distance(X, X[b0:b1]) on the device, (b1-b0, N)."""
     n = X.shape[0]
     if kind == "callable":
@@ -245,7 +245,10 @@ def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows):
         step = _tile_rows(n, 8, batch_size)
     for b0 in range(row0, row0 + rows, step):
         b1 = min(b0 + step, row0 + rows)
-        if kind == "minkowski":
+        if gemm is not None:
+            q = eng.gemm_pack(X[b0:b1], max_token=gemm.max_token, K=gemm.K)
+            tile = eng.minkowski2_gemm_tile(gemm, q, 0, similarity=similarity)
+        elif kind == "minkowski":
             tile = eng.minkowski_tile(X, X, b0, b1 - b0, p=p, similarity=similarity)
         elif kind == "hamming":
             tile = eng.hamming_values_tile(X, X, b0, b1 - b0, similarity=similarity)
@@ -334,11 +337,29 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     else:
         # prograph.py:726: every representation is rounded to fp16 before the metric sees it
         Xh = eng.to_device(X).to(torch.float16)
-        tiles = _tiles(eng, Xh, kind, p, distance, similarity, batch_size, row0, rows)
-        if eps:
-            part = _tile_eps(eng, tiles, eps, comp, similarity) if rows else None
-        else:
-            part = _tile_knn(eng, tiles, k, similarity, n) if rows else None
+        gemm = None
+        if kind == "minkowski" and float(p) == 2.0 and Xh.shape[1] <= getattr(eng, "GEMM_MAX_WIDTH", 0):
+            # integer tokens <= 31: the fp16 chain is a function of the exact integer
+            # |x|^2 + |y|^2 - 2 x.y  ->  int8 tensor-core contraction (pg_gemm.cu)
+            try:
+                gemm = eng.gemm_pack(Xh, max_token=31)
+            except (OverflowError, L.Unsupported):
+                gemm = None
+        part = None
+        if gemm is not None and not eps and rows:
+            kk = min(k, n - 1)
+            if kk > 0:
+                try:
+                    q = gemm if (row0 == 0 and rows == n) else eng.gemm_pack(Xh[row0:row0 + rows], max_token=31, K=gemm.K)
+                    part = eng.minkowski2_gemm_knn(gemm, q, kk, 1, 0, similarity=similarity)
+                except L.Unsupported:
+                    part = None
+        if part is None:
+            tiles = _tiles(eng, Xh, kind, p, distance, similarity, batch_size, row0, rows, gemm=gemm)
+            if eps:
+                part = _tile_eps(eng, tiles, eps, comp, similarity) if rows else None
+            else:
+                part = _tile_knn(eng, tiles, k, similarity, n) if rows else None
 
     if eps:
         indptr, idx, w = _shard.gather_csr(part, n, rank, world, group, eng)
