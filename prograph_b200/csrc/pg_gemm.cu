@@ -64,7 +64,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// issue only: the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -75,7 +77,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // K-major, no swizzle: core matrix = 8 rows x 16 B contiguous (128 B); LBO = distance between the
@@ -137,6 +138,26 @@ struct GemmParams {
   int k1, k, drop;
   long long* out_idx; void* out_val;
 };
+
+// Rare path of the fused kNN, kept out of line so that the 32 call sites of a chunk stay small
+// (inlined, the insertion + threshold search blew the instruction cache: ~5700 clk per insert).
+// `cand`: lanes whose row has a candidate in this column; `S` = this lane's exact integer sum.
+// Returns the lane's updated threshold (tprime = thr_S - nq).
+template <int VK>
+__device__ __noinline__ int gemm_knn_serve(unsigned cand, int S, unsigned col, unsigned long long* warp_lists, int k1,
+                                           bool sim, int lane, int nq, int tprime) {
+  while (cand) {
+    const int src = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const int s_src = __shfl_sync(0xffffffffu, S, src);
+    const uint32_t key32 = order_key(value_bits<VK>(s_src, sim), sim);
+    const unsigned long long key = (static_cast<unsigned long long>(key32) << 32) | col;
+    const uint32_t tau = knn_insert_coop(warp_lists + static_cast<size_t>(src) * k1, k1, key, lane);
+    const int thr = s_threshold<VK>(tau, sim, lane);     // candidates: S < thr
+    if (lane == src) tprime = thr - nq;
+  }
+  return tprime;
+}
 
 // Single-lane waits of the producer / MMA issuer: poll with a short sleep (try_wait with a
 // suspend-time hint was measured to wake only at the time limit).
@@ -251,10 +272,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       tc_fence_after();
       const long long col_tile = static_cast<long long>(t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
-#pragma unroll 1
+      uint32_t dotbuf[2][32];
+      tmem_ld32_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
+#pragma unroll
       for (int c = 0; c < GN / 32; ++c) {
-        uint32_t dot[32];
-        tmem_ld32(tmem_base + lane_base + acc * GN + c * 32, dot);
+        uint32_t (&dot)[32] = dotbuf[c & 1];
+        tmem_ld_wait();
+        if (c + 1 < GN / 32) tmem_ld32_issue(tmem_base + lane_base + acc * GN + (c + 1) * 32, dotbuf[(c + 1) & 1]);
         const long long col0 = col_tile + c * 32;
         int v[32];   // nx - 2 dot  (S = nq + v)
         const int4* np = reinterpret_cast<const int4*>(nrm + c * 32);
@@ -301,26 +325,19 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
             }
           }
         } else {
-          int best = v[0];
+          // tree minimum of the 32 values (a linear chain would serialise 31 dependent mins)
+          int m8[8];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) best = min(best, v[j]);
+          for (int g = 0; g < 8; ++g) m8[g] = min(min(v[4 * g], v[4 * g + 1]), min(v[4 * g + 2], v[4 * g + 3]));
+          const int best = min(min(min(m8[0], m8[1]), min(m8[2], m8[3])), min(min(m8[4], m8[5]), min(m8[6], m8[7])));
           if (__any_sync(0xffffffffu, best < tprime)) {
+            unsigned long long* warp_lists = lists + (static_cast<size_t>(group) * GM + qwarp * 32) * prm.k1;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              unsigned cand = __ballot_sync(0xffffffffu, v[j] < tprime);
-              while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const int S = __shfl_sync(0xffffffffu, nq + v[j], src);
-                const uint32_t key32 = order_key(value_bits<VK>(S, sim), sim);
-                const unsigned long long key =
-                    (static_cast<unsigned long long>(key32) << 32) | static_cast<unsigned>(col0 + j);
-                unsigned long long* lst = lists + (static_cast<size_t>(group) * GM + qwarp * 32 + src) * prm.k1;
-                const uint32_t tau = knn_insert_coop(lst, prm.k1, key, lane);
-                const int thr = s_threshold<VK>(tau, sim, lane);     // candidates: S < thr
-                const int src_nq = __shfl_sync(0xffffffffu, nq, src);
-                if (lane == src) tprime = thr - src_nq;
-              }
+              const unsigned cand = __ballot_sync(0xffffffffu, v[j] < tprime);
+              if (cand)
+                tprime = gemm_knn_serve<VK>(cand, nq + v[j], static_cast<unsigned>(col0 + j), warp_lists, prm.k1, sim,
+                                            lane, nq, tprime);
             }
           }
         }
