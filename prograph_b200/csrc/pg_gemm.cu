@@ -32,6 +32,7 @@ constexpr int GSTAGES = 4;
 constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp + MMA warp
 constexpr int GPROD_WARP = 8;
 constexpr int GMMA_WARP = 9;
+constexpr int GPROD_LANES = 8;  // lanes of the producer warp that each copy a slice of a B tile
 constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
 constexpr int PAD_NORM = 0x3fffffff;
 
@@ -210,21 +211,30 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
 
   if (warp == GPROD_WARP) {
     // ---------------- producer ----------------
+    // GPROD_LANES lanes each issue a slice of the tile so that several bulk requests are in flight
+    // (measured neutral against one 32 KB request; the kernel is not copy-bound, see
+    // profiles/r1_ncu_notes.md).
     if (lane == 0) {
       mbar_arrive_expect_tx(a_full, tile_bytes);
       bulk_g2s(sA, prm.A + static_cast<size_t>(row0) * K, tile_bytes, a_full);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
+    }
+    const uint32_t slice = tile_bytes / GPROD_LANES;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      if (lane == 0) {
         mbar_wait_poll(&empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&full[stage], tile_bytes + GN * 4);
-        bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes, prm.B + static_cast<size_t>(t) * GN * K, tile_bytes,
-                 &full[stage]);
         // the norms of tile t live in slot t % GNORM_SLOTS until the epilogue of tile t is done;
         // slot reuse (tile t + 8) is ordered behind MMA t+4, i.e. behind the epilogue of tile t+2
         bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t) * GN, GN * 4, &full[stage]);
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (lane < GPROD_LANES) {
+        bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
+                 prm.B + static_cast<size_t>(t) * GN * K + lane * slice, slice, &full[stage]);
+      }
+      if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == GMMA_WARP) {
     // ---------------- MMA issuer ----------------
