@@ -144,6 +144,7 @@ class CudaEngine:
                                               _ptr(ws), nbytes, self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
+        self._check_edge_budget(nnz)
         weight = L.W_SIM_F32 if similarity else L.W_I64
         idx = self.empty((nnz,), torch.int64)
         w = self.empty((nnz,), torch.float32 if similarity else torch.int64)
@@ -163,6 +164,15 @@ class CudaEngine:
                                          int(qrows), data.planes, data.words, weight, _ptr(out), data.rows,
                                          self._stream()))
         return out
+
+    def _check_edge_budget(self, nnz):
+        """An epsilon graph can be dense (the reference would run out of host memory the same way):
+        refuse before allocating instead of taking the GPU down."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        need = nnz * 16
+        if need > 0.9 * (free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)):
+            raise MemoryError(f"the requested graph has {nnz} edges ({need / 2**30:.1f} GiB as int64 index/weight "
+                              f"pairs) and does not fit in device memory; lower eps or build a kNN graph")
 
     def exclusive_scan(self, counts):
         out = self.empty((counts.numel() + 1,), torch.int64)
@@ -256,6 +266,7 @@ class CudaEngine:
                                                  1 if swap else 0, int(guard), _ptr(counts), self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
+        self._check_edge_budget(nnz)
         idx = self.empty((nnz,), torch.int64)
         val = self.empty((nnz,), tile.dtype) if values else None
         if nnz:

@@ -84,9 +84,13 @@ def main():
     tabm = eng.pack(M)
     ms, _ = timed(lambda: eng.hamming_knn(tabm, 0, n4, tabm, 16, drop=1), reps=1)
     rec("C4-M", f"hamming kNN k=16, N={n4}", float(n4) * n4, ms)
-    lut = distance_lut(256, operator.le, 2, False)
+    lut = distance_lut(256, operator.le, 1, False)
     ms, (ip, _, _) = timed(lambda: eng.hamming_eps(tabm, 0, n4, tabm, lut), reps=1)
-    rec("C4-M", f"hamming eps=2 graph, N={n4}", float(n4) * n4 * 2, ms, nnz=int(ip[-1]), note="pairs counts both sweeps")
+    rec("C4-M", f"hamming eps=1 graph, N={n4}", float(n4) * n4 * 2, ms, nnz=int(ip[-1]), note="pairs counts both sweeps")
+    try:
+        eng.hamming_eps(tabm, 0, n4, tabm, distance_lut(256, operator.le, 2, False))
+    except MemoryError as e:
+        print("C4-M eps=2:", e, flush=True)
 
     # ---- C5 ---------------------------------------------------------------------------------
     nq = 16384 if args.quick else 100_000
@@ -105,6 +109,20 @@ def main():
     rec("C5", f"hamming materialised tile 1024 x {n4} int64", 1024.0 * n4, ms, out_gbs=round(1024.0 * n4 * 8 / ms / 1e6, 1))
     ms, _ = timed(lambda: eng.hamming_tile(tabm, tq, 0, 1024, weight=L.W_SIM_F32))
     rec("C5", f"hamming similarity tile 1024 x {n4} float32", 1024.0 * n4, ms, out_gbs=round(1024.0 * n4 * 4 / ms / 1e6, 1))
+    # Minkowski p=2 on the integer tokens: tcgen05 int8 contraction
+    gm = eng.gemm_pack(M, max_token=31)
+    gq = eng.gemm_pack(Q, max_token=31, K=gm.K)
+    for kind, name in ((1, "int64 tokens -> float32"), (0, "fp16 chain")):
+        ms, _ = timed(lambda: eng.minkowski2_gemm_knn(gm, gq, 1, 0, kind), reps=1)
+        rec("C5", f"minkowski p=2 nearest neighbour {nq} x {n4}, {name}, tcgen05", float(nq) * n4, ms)
+    ms, _ = timed(lambda: eng.minkowski2_gemm_knn(gm, gq, 16, 0, 1, similarity=True), reps=1)
+    rec("C5", f"minkowski p=2 similarity top-16 {nq} x {n4}, tcgen05", float(nq) * n4, ms)
+    ms, _ = timed(lambda: eng.minkowski2_gemm_knn(gm, gm, 16, 1, 0), reps=1)
+    rec("C4-M", f"minkowski p=2 kNN k=16 graph N={n4}, fp16 chain, tcgen05", float(n4) * n4, ms)
+    g1k = eng.gemm_pack(Q[:8192], max_token=31, K=gm.K)
+    ms, _ = timed(lambda: eng.minkowski2_gemm_tile(gm, g1k, 1), reps=1)
+    rec("C5", f"minkowski p=2 tile 8192 x {n4} float32, tcgen05", 8192.0 * n4, ms, out_gbs=round(8192.0 * n4 * 4 / ms / 1e6, 1))
+    del g1k
     Md = torch.from_numpy(M.astype(np.int64)).cuda()
     Qd = torch.from_numpy(Q[:1024].astype(np.int64)).cuda()
     for p, sim in ((2, False), (2, True), (1, False), (3, False)):
