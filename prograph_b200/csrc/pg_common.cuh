@@ -42,6 +42,8 @@ void count_launch();
   } while (0)
 
 int num_sms();
+// stream-ordered scratch for CUB; the pool keeps its memory between calls
+cudaError_t temp_alloc(void** ptr, size_t bytes, cudaStream_t s);
 
 // ---- geometry of the packed table -------------------------------------------
 constexpr int kStreamRowPad = 512;  // packed tables are padded to a multiple of this many rows

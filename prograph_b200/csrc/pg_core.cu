@@ -28,6 +28,22 @@ int num_sms() {
   return cached[dev];
 }
 
+cudaError_t temp_alloc(void** ptr, size_t bytes, cudaStream_t s) {
+  static bool tuned[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !tuned[dev]) {
+    // default release threshold is 0: every free + sync would hand the memory back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned[dev] = true;
+  }
+  return cudaMallocAsync(ptr, bytes < 16 ? 16 : bytes, s);
+}
+
 // ---- pack: [N][L] tokens -> [rows_padded][planes][words] bit planes ------------------
 // One warp per row; lane j holds residue 32w+j, one ballot per plane builds the word.
 // Replaces the fp16 staging of prograph.py:726 for integer tokens (HBM-bound: reads the

@@ -170,7 +170,7 @@ int pg_flag_indices(const uint8_t* flag, int64_t N, int64_t* out_idx, int64_t* c
   PG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, flag, reinterpret_cast<long long*>(out_idx),
                                      reinterpret_cast<long long*>(count_out), static_cast<int>(N), s));
   void* tmp = nullptr;
-  PG_CUDA(cudaMallocAsync(&tmp, tmp_bytes, s));
+  PG_CUDA(temp_alloc(&tmp, tmp_bytes, s));
   cudaError_t e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, ids, flag, reinterpret_cast<long long*>(out_idx),
                                              reinterpret_cast<long long*>(count_out), static_cast<int>(N), s);
   count_launch();

@@ -316,7 +316,7 @@ int pg_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stre
   PG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out + 1, static_cast<int>(n),
                                         static_cast<cudaStream_t>(stream)));
   void* tmp = nullptr;
-  PG_CUDA(cudaMallocAsync(&tmp, tmp_bytes, static_cast<cudaStream_t>(stream)));
+  PG_CUDA(temp_alloc(&tmp, tmp_bytes, static_cast<cudaStream_t>(stream)));
   cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, in, out + 1, static_cast<int>(n),
                                                 static_cast<cudaStream_t>(stream));
   count_launch();
