@@ -51,7 +51,7 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
   g.n_rowblocks = static_cast<int>(ceil_div(rows, rows_per_cta));
   g.n_tiles = static_cast<int>(ceil_div(stream_rows, g.tile_cols));
   const long long resident = static_cast<long long>(num_sms()) * 2;
-  long long want = ceil_div(32 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
+  long long want = ceil_div(16 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
   // every split restarts its kNN lists from empty: keep >= 16K stream rows (and >= 8 ring
   // tiles) per split so that the cold start stays a small fraction of the item
   long long max_splits = stream_rows / 16384;
@@ -68,7 +68,7 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
 static int dispatch(int planes, int words, const SweepParams& prm, const SweepLaunch& l) {
 #define PG_CASE(P, W) \
   if (planes == P && words == W) return sweep_p##P##_w##W(prm, l);
-  PG_CASE(5, 1) PG_CASE(5, 2) PG_CASE(5, 4) PG_CASE(5, 8)
+  PG_CASE(5, 1) PG_CASE(5, 2) PG_CASE(5, 4) PG_CASE(5, 8) PG_CASE(5, 16)
   PG_CASE(8, 1) PG_CASE(8, 2) PG_CASE(8, 4) PG_CASE(8, 8)
 #undef PG_CASE
   set_error("fused sweep supports planes in {5,8} and words in {1,2,4,8}; got planes=%d words=%d", planes, words);
@@ -84,8 +84,10 @@ static int check_common(const void* own, long long own_rows, long long row0, lon
   PG_CHECK_ARG(stream_rows < (1ll << 32), "stream table too large for 32-bit indices");
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(str) & 15) == 0, "stream table must be 16-byte aligned");
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(own) & 15) == 0, "own table must be 16-byte aligned");
-  if (!((planes == 5 || planes == 8) && (words == 1 || words == 2 || words == 4 || words == 8))) {
-    set_error("fused sweep supports planes in {5,8} and words in {1,2,4,8}; got planes=%d words=%d", planes, words);
+  if (!(((planes == 5 || planes == 8) && (words == 1 || words == 2 || words == 4 || words == 8)) ||
+        (planes == 5 && words == 16))) {
+    set_error("fused sweep supports planes in {5,8} x words in {1,2,4,8} and planes=5, words=16; got planes=%d words=%d",
+              planes, words);
     return PG_ERR_UNSUPPORTED;
   }
   return PG_OK;
@@ -179,7 +181,7 @@ extern "C" {
 
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
-  if (words > 8) words = 8;
+  if (words > 16) words = 16;
   const Geometry g1 = make_geometry(own_rows, stream_rows, words);
   const Geometry g2 = make_geometry(own_rows, stream_rows, words, 2 * kConsumers);   // multi-row kNN variants
   const int n_splits = g1.n_splits > g2.n_splits ? g1.n_splits : g2.n_splits;

@@ -437,7 +437,7 @@ int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
 
 // defined in pg_sweep_inst.cu, one per (P, W)
 #define PG_DECL_SWEEP(P, W) int sweep_p##P##_w##W(const SweepParams& prm, const SweepLaunch& l);
-PG_DECL_SWEEP(5, 1) PG_DECL_SWEEP(5, 2) PG_DECL_SWEEP(5, 4) PG_DECL_SWEEP(5, 8)
+PG_DECL_SWEEP(5, 1) PG_DECL_SWEEP(5, 2) PG_DECL_SWEEP(5, 4) PG_DECL_SWEEP(5, 8) PG_DECL_SWEEP(5, 16)
 PG_DECL_SWEEP(8, 1) PG_DECL_SWEEP(8, 2) PG_DECL_SWEEP(8, 4) PG_DECL_SWEEP(8, 8)
 #undef PG_DECL_SWEEP
 
