@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <cmath>
 
 #include "pg_sweep.cuh"
 
@@ -42,25 +43,43 @@ struct Geometry {
 
 static int tile_cols_for(int words) { return 512 / words; }
 
-// Splits of the stream make the persistent grid's last wave short: aim for >= 32 items per
-// resident CTA, but keep >= 8 ring tiles per item so the own-row load and the list
-// write-back stay amortised.
-static Geometry make_geometry(long long rows, long long stream_rows, int words, int rows_per_cta = kConsumers) {
+// Splits of the stream shorten the persistent grid's last wave, but every split restarts its
+// kNN lists from empty.  Pick the split count that minimises a small cost model (in units of
+// "stream rows swept by one CTA"): waves(S) * (cols/S + c_ins * k1 * (1 + ln(cols/(S*k1)))),
+// c_ins ~ 18 = a warp-cooperative insertion stalls its 32 rows for about 0.6 stream rows
+// (measured: profiles/r1_ncu_notes.md).  k1 = 0 (count / fill / tile) only balances the waves.
+static Geometry make_geometry(long long rows, long long stream_rows, int words, int rows_per_cta = kConsumers,
+                              int k1 = 17) {
   Geometry g;
   g.tile_cols = tile_cols_for(words);
   g.n_rowblocks = static_cast<int>(ceil_div(rows, rows_per_cta));
   g.n_tiles = static_cast<int>(ceil_div(stream_rows, g.tile_cols));
-  const long long resident = static_cast<long long>(num_sms()) * 2;
-  long long want = ceil_div(16 * resident, g.n_rowblocks > 0 ? g.n_rowblocks : 1);
-  // every split restarts its kNN lists from empty: keep >= 16K stream rows (and >= 8 ring
-  // tiles) per split so that the cold start stays a small fraction of the item
-  long long max_splits = stream_rows / 16384;
-  if (max_splits > g.n_tiles / 8) max_splits = g.n_tiles / 8;
-  if (const char* ev = std::getenv("PG_SWEEP_SPLITS")) { want = std::atoll(ev); max_splits = g.n_tiles; }
+  const double resident = static_cast<double>(num_sms()) * 2;
+  long long max_splits = g.n_tiles / 8;      // keep >= 8 ring tiles per item
+  if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;
-  if (want > max_splits) want = max_splits;
-  if (want < 1) want = 1;
-  g.tiles_per_split = static_cast<int>(ceil_div(g.n_tiles, want));
+  long long best_s = 1;
+  double best_cost = 1e300;
+  for (long long s = 1; s <= max_splits; ++s) {
+    const long long tps = ceil_div(g.n_tiles, s);
+    const long long real_s = ceil_div(g.n_tiles, tps);
+    const double cols = static_cast<double>(tps) * g.tile_cols;
+    double waves = static_cast<double>(g.n_rowblocks) * real_s / resident;
+    waves = waves < 1.0 ? 1.0 : static_cast<double>(static_cast<long long>(waves + 0.999999));
+    double item = cols + 64.0;               // fixed per-item cost: own-row load, list write-back
+    if (k1 > 0) {
+      const double ratio = cols / k1;
+      item += 18.0 * k1 * (1.0 + (ratio > 1.0 ? log(ratio) : 0.0));
+    }
+    const double cost = waves * item;
+    if (cost < best_cost * 0.999) { best_cost = cost; best_s = s; }
+  }
+  if (const char* ev = std::getenv("PG_SWEEP_SPLITS")) {
+    best_s = std::atoll(ev);
+    if (best_s < 1) best_s = 1;
+    if (best_s > g.n_tiles) best_s = g.n_tiles;
+  }
+  g.tiles_per_split = static_cast<int>(ceil_div(g.n_tiles, best_s));
   g.n_splits = static_cast<int>(ceil_div(g.n_tiles, g.tiles_per_split));
   return g;
 }
@@ -182,9 +201,15 @@ extern "C" {
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
   if (words > 16) words = 16;
-  const Geometry g1 = make_geometry(own_rows, stream_rows, words);
-  const Geometry g2 = make_geometry(own_rows, stream_rows, words, 2 * kConsumers);   // multi-row kNN variants
-  const int n_splits = g1.n_splits > g2.n_splits ? g1.n_splits : g2.n_splits;
+  // the largest split count any sweep of this shape may choose (kNN with k1 entries, the
+  // count / fill passes, the two-rows-per-thread kNN variants)
+  int n_splits = 1;
+  for (int rpc = kConsumers; rpc <= 2 * kConsumers; rpc += kConsumers) {
+    const int a = make_geometry(own_rows, stream_rows, words, rpc, 0).n_splits;
+    const int b = make_geometry(own_rows, stream_rows, words, rpc, k1 > 0 ? k1 : 1).n_splits;
+    n_splits = a > n_splits ? a : n_splits;
+    n_splits = b > n_splits ? b : n_splits;
+  }
   const size_t per_row = static_cast<size_t>(n_splits) * 8 * static_cast<size_t>(k1 > 1 ? k1 : 1);
   return per_row * static_cast<size_t>(own_rows) + 256;
 }
@@ -204,7 +229,7 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
   if (const char* ev = std::getenv("PG_KNN_VARIANT")) variant = std::atoi(ev);
   if (!(planes == 5 && words == 8)) variant = 0;
   if (variant == 1 || variant == 4) tm = 2;
-  const Geometry g = make_geometry(rows, stream_rows, words, kConsumers * tm);
+  const Geometry g = make_geometry(rows, stream_rows, words, kConsumers * tm, k1);
   const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   const size_t list_bytes = static_cast<size_t>(k1) * kConsumers * tm * 8;
@@ -239,7 +264,7 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   PG_CHECK_ARG(lut_host && lut_words >= 1 && lut_words <= kMaxLutWords, "lut_words must be in [1,%d]", kMaxLutWords);
   PG_CHECK_ARG(lut_words * 32 > words * 32, "lut must cover distances 0..%d", words * 32);
   PG_CHECK_ARG(workspace, "null workspace");
-  const Geometry g = make_geometry(rows, stream_rows, words);
+  const Geometry g = make_geometry(rows, stream_rows, words, kConsumers, 0);
   const size_t need = static_cast<size_t>(g.n_splits) * rows * 8;
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   SweepParams prm;
@@ -295,7 +320,7 @@ int pg_hamming_tile(const uint32_t* data, int64_t data_rows, const uint32_t* que
   if (rc != PG_OK) return rc;
   PG_CHECK_ARG(out && ld >= data_rows, "bad output / leading dimension");
   PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
-  Geometry g = make_geometry(data_rows, qrows, words);
+  Geometry g = make_geometry(data_rows, qrows, words, kConsumers, 0);
   g.n_splits = 1;  // every (own, stream) pair is written exactly once; splits only add launches
   g.tiles_per_split = g.n_tiles;
   SweepParams prm;
