@@ -84,6 +84,12 @@ int pg_pack_tokens(const void* tokens, int dtype, int64_t N, int L, int64_t ld,
 /* size in bytes of the workspace the fused sweeps need (split partials) */
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1);
 
+/* workspace of the two epsilon passes: per-split row counts plus, when it fits, room for the
+ * first 32 hits of every (split,row): sparse graphs (e.g. the default eps=1 graph of
+ * Prograph.__init__, prograph.py:140-141) are then finished by a compaction kernel instead of
+ * a second sweep */
+size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words);
+
 /* kNN (prograph.py:755-765: sort each row, keep sorted positions drop..drop+k-1).
  * For every own row r in [row0,row0+rows): the first (drop+k) stream rows in
  * (distance, index) order; positions [drop, drop+k) are written:

@@ -184,13 +184,47 @@ __global__ void knn_finalize_kernel(const unsigned long long* __restrict__ part,
 }
 
 __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, int n_splits, long long rows,
-                                  long long* __restrict__ counts) {
+                                  long long* __restrict__ counts, int* __restrict__ overflow) {
   const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (r >= rows) return;
   long long s = 0;
-  for (int i = 0; i < n_splits; ++i) s += split_counts[static_cast<size_t>(i) * rows + r];
+  bool over = false;
+  for (int i = 0; i < n_splits; ++i) {
+    const long long c = split_counts[static_cast<size_t>(i) * rows + r];
+    over |= c > kEpsCapture;
+    s += c;
+  }
   counts[r] = s;
+  if (over && overflow) *overflow = 1;       // some (split,row) had more hits than the capture holds
 }
+
+// Fill from the captures of the count pass (every (split,row) had <= kEpsCapture hits): row r's
+// edges are the splits' captured hits in split order, i.e. ascending stream index.
+__global__ void eps_from_capture_kernel(const unsigned long long* __restrict__ capture,
+                                        const long long* __restrict__ split_counts, int n_splits, long long rows,
+                                        const long long* __restrict__ indptr, int weight,
+                                        long long* __restrict__ out_idx, void* out_w) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  long long at = indptr[r];
+  for (int s = 0; s < n_splits; ++s) {
+    const int c = static_cast<int>(split_counts[static_cast<size_t>(s) * rows + r]);
+    const unsigned long long* src = capture + (static_cast<size_t>(s) * rows + r) * kEpsCapture;
+    for (int j = 0; j < c; ++j) {
+      const unsigned long long e = src[j];
+      out_idx[at] = static_cast<long long>(e & 0xffffffffull);
+      write_weight(out_w, at, static_cast<int>(e >> 32), weight);
+      ++at;
+    }
+  }
+}
+
+// eps workspace: [split counts: n_splits*rows int64][overflow flag, 256 B][captures: n_splits*rows*kEpsCapture u64]
+static size_t eps_counts_bytes(const Geometry& g, long long rows) { return static_cast<size_t>(g.n_splits) * rows * 8; }
+static size_t eps_capture_bytes(const Geometry& g, long long rows) {
+  return static_cast<size_t>(g.n_splits) * rows * kEpsCapture * 8;
+}
+constexpr size_t kEpsCaptureLimit = 8ull << 30;   // do not spend more than 8 GiB on captures
 
 }  // namespace pg
 
@@ -212,6 +246,14 @@ size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words
   }
   const size_t per_row = static_cast<size_t>(n_splits) * 8 * static_cast<size_t>(k1 > 1 ? k1 : 1);
   return per_row * static_cast<size_t>(own_rows) + 256;
+}
+
+size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) {
+  if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
+  const Geometry g = make_geometry(own_rows, stream_rows, words > 16 ? 16 : words, kConsumers, 0);
+  size_t bytes = eps_counts_bytes(g, own_rows) + 256;
+  if (eps_capture_bytes(g, own_rows) <= kEpsCaptureLimit) bytes += eps_capture_bytes(g, own_rows);
+  return bytes;
 }
 
 int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows, const uint32_t* stream_tab,
@@ -265,11 +307,33 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   PG_CHECK_ARG(lut_words * 32 > words * 32, "lut must cover distances 0..%d", words * 32);
   PG_CHECK_ARG(workspace, "null workspace");
   const Geometry g = make_geometry(rows, stream_rows, words, kConsumers, 0);
-  const size_t need = static_cast<size_t>(g.n_splits) * rows * 8;
+  const size_t need = eps_counts_bytes(g, rows);
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  const bool capturing = workspace_bytes >= need + 256 + eps_capture_bytes(g, rows);
+  int* overflow = reinterpret_cast<int*>(static_cast<char*>(workspace) + need);
+  unsigned long long* capture = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + need + 256);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
   SweepParams prm;
   fill_common(prm, g, own, row0, rows, stream_tab, stream_rows);
   prm.split_counts = static_cast<long long*>(workspace);
+  if (mode == MODE_COUNT && capturing) {
+    prm.capture = capture;
+    PG_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), cs));
+  }
+  if (mode == MODE_FILL && capturing) {
+    // the count pass kept every hit unless a (split,row) overflowed its capture
+    int over = 1;
+    PG_CUDA(cudaMemcpyAsync(&over, overflow, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    PG_CUDA(cudaStreamSynchronize(cs));
+    if (!over) {
+      const int threads = 128;
+      eps_from_capture_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, cs>>>(
+          capture, prm.split_counts, g.n_splits, rows, reinterpret_cast<const long long*>(indptr), weight,
+          reinterpret_cast<long long*>(out_idx), out_w);
+      PG_LAUNCH_CHECK();
+      return PG_OK;
+    }
+  }
   for (int i = 0; i < lut_words; ++i) prm.lut[i] = lut_host[i];
   const bool ranged = lut_as_range(lut_host, lut_words, &prm.lo, &prm.span);
   SweepLaunch l{mode, ranged ? 0 : 1, weight, 0, 0, static_cast<cudaStream_t>(stream)};
@@ -286,7 +350,7 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   if (mode == MODE_COUNT) {
     const int threads = 256;
     sum_splits_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
-        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts));
+        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts), capturing ? overflow : nullptr);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;

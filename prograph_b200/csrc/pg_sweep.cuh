@@ -30,6 +30,7 @@ constexpr int kConsumers = kConsumerWarps * 32;  // threads per CTA; each owns T
 constexpr int kSweepThreads = kConsumers;
 constexpr int kStages = 4;
 constexpr int kMaxLutWords = 64;                 // distances up to 2047
+constexpr int kEpsCapture = 32;                  // hits per (split, row) kept by the count pass
 
 enum SweepMode { MODE_KNN = 0, MODE_COUNT = 1, MODE_FILL = 2, MODE_TILE = 3 };
 
@@ -54,6 +55,7 @@ struct SweepParams {
   int lo;                 // range test (unsigned)(d - lo) <= span when !LUT
   unsigned span;
   long long* split_counts;  // [n_splits][rows]
+  unsigned long long* capture;  // count pass: first kEpsCapture hits of every (split,row), d<<32|idx; or null
   const long long* indptr;  // [rows+1]                          (fill)
   long long* out_idx;       // edges                              (fill)
   void* out_w;
@@ -242,8 +244,10 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
     uint32_t q[TM][COLW];
     unsigned tau[TM];     // kNN: distance word of the k1-th list entry (the filter threshold)
     long long cnt[TM];    // count / fill cursor
+    unsigned long long* cap[TM];
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
+      cap[i] = nullptr;
       r[i] = static_cast<long long>(rb) * ROWS_CTA + i * kConsumers + tid;
       valid[i] = r[i] < prm.rows;
       const uint32_t* src = prm.own + static_cast<size_t>(prm.own_row0 + (valid[i] ? r[i] : 0)) * COLW;
@@ -254,6 +258,10 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
       if constexpr (MODE == MODE_KNN) {
         unsigned long long* mine = lists + static_cast<size_t>(i * kConsumers + tid) * prm.k1;
         for (int j = 0; j < prm.k1; ++j) mine[j] = ~0ull;
+      }
+      if constexpr (MODE == MODE_COUNT) {
+        if (valid[i] && prm.capture != nullptr)
+          cap[i] = prm.capture + (static_cast<size_t>(split) * prm.rows + r[i]) * kEpsCapture;
       }
       if constexpr (MODE == MODE_FILL) {
         if (valid[i]) {
@@ -321,8 +329,16 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
           if constexpr (MODE == MODE_KNN) {
             serve(i, d[i], col0 + c);
           } else if constexpr (MODE == MODE_COUNT) {
-            if constexpr (LUT) cnt[i] += (lut_s[d[i] >> 5] >> (d[i] & 31)) & (valid[i] ? 1u : 0u);
-            else cnt[i] += (valid[i] && static_cast<unsigned>(d[i] - lo) <= span) ? 1 : 0;
+            bool hit;
+            if constexpr (LUT) hit = (lut_s[d[i] >> 5] >> (d[i] & 31)) & 1u;
+            else hit = static_cast<unsigned>(d[i] - lo) <= span;
+            if (hit && valid[i]) {
+              // sparse graphs: keep the first hits so that the fill sweep can be skipped
+              if (cap[i] != nullptr && cnt[i] < kEpsCapture)
+                cap[i][cnt[i]] = (static_cast<unsigned long long>(static_cast<unsigned>(d[i])) << 32) |
+                                 static_cast<unsigned>(col0 + c);
+              ++cnt[i];
+            }
           } else if constexpr (MODE == MODE_FILL) {
             bool hit;
             if constexpr (LUT) hit = (lut_s[d[i] >> 5] >> (d[i] & 31)) & 1u;

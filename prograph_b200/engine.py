@@ -138,7 +138,8 @@ class CudaEngine:
         self._check_pair(own, stream)
         lut, lut_p = _host_u32(lut)
         counts = self.empty((rows,), torch.int64)
-        ws, nbytes = self._workspace(rows, stream.rows, own.words, 1)
+        nbytes = int(self.lib.pg_eps_workspace_bytes(int(rows), int(stream.rows), int(own.words)))
+        ws = self.empty((nbytes,), torch.uint8)
         L.check(self.lib.pg_hamming_eps_count(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
                                               stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(counts),
                                               _ptr(ws), nbytes, self._stream()))
