@@ -5,6 +5,8 @@
 #include <mutex>
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <cstdlib>
 #include <cmath>
@@ -118,6 +120,8 @@ static void fill_common(SweepParams& prm, const Geometry& g, const uint32_t* own
   prm.own = own;
   prm.own_row0 = row0;
   prm.rows = rows;
+  prm.row_map = nullptr;
+  prm.rows_total = rows;
   prm.str = str;
   prm.str_rows = stream_rows;
   prm.n_rowblocks = g.n_rowblocks;
@@ -184,7 +188,7 @@ __global__ void knn_finalize_kernel(const unsigned long long* __restrict__ part,
 }
 
 __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, int n_splits, long long rows,
-                                  long long* __restrict__ counts, int* __restrict__ overflow) {
+                                  long long* __restrict__ counts, uint8_t* __restrict__ over_flag) {
   const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (r >= rows) return;
   long long s = 0;
@@ -195,17 +199,18 @@ __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, in
     s += c;
   }
   counts[r] = s;
-  if (over && overflow) *overflow = 1;       // some (split,row) had more hits than the capture holds
+  if (over_flag) over_flag[r] = over ? 1 : 0;   // some split of this row had more hits than the capture holds
 }
 
-// Fill from the captures of the count pass (every (split,row) had <= kEpsCapture hits): row r's
-// edges are the splits' captured hits in split order, i.e. ascending stream index.
+// Fill from the captures of the count pass: row r's edges are the splits' captured hits in
+// split order, i.e. ascending stream index.  Rows with an overflowed capture are left to the
+// fill sweep over the overflow rows.
 __global__ void eps_from_capture_kernel(const unsigned long long* __restrict__ capture,
                                         const long long* __restrict__ split_counts, int n_splits, long long rows,
-                                        const long long* __restrict__ indptr, int weight,
-                                        long long* __restrict__ out_idx, void* out_w) {
+                                        const uint8_t* __restrict__ over_flag, const long long* __restrict__ indptr,
+                                        int weight, long long* __restrict__ out_idx, void* out_w) {
   const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows) return;
+  if (r >= rows || over_flag[r]) return;
   long long at = indptr[r];
   for (int s = 0; s < n_splits; ++s) {
     const int c = static_cast<int>(split_counts[static_cast<size_t>(s) * rows + r]);
@@ -219,12 +224,15 @@ __global__ void eps_from_capture_kernel(const unsigned long long* __restrict__ c
   }
 }
 
-// eps workspace: [split counts: n_splits*rows int64][overflow flag, 256 B][captures: n_splits*rows*kEpsCapture u64]
+// eps workspace: [split counts: n_splits*rows int64][header 256 B: number of overflow rows]
+//                [overflow flag per row, padded][overflow row list: rows int64][captures: n_splits*rows*kEpsCapture u64]
 static size_t eps_counts_bytes(const Geometry& g, long long rows) { return static_cast<size_t>(g.n_splits) * rows * 8; }
 static size_t eps_capture_bytes(const Geometry& g, long long rows) {
   return static_cast<size_t>(g.n_splits) * rows * kEpsCapture * 8;
 }
 constexpr size_t kEpsCaptureLimit = 8ull << 30;   // do not spend more than 8 GiB on captures
+static size_t eps_flag_bytes(long long rows) { return static_cast<size_t>(round_up(rows, 256)); }
+static size_t eps_list_bytes(long long rows) { return static_cast<size_t>(rows) * 8; }
 
 }  // namespace pg
 
@@ -252,7 +260,8 @@ size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) 
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
   const Geometry g = make_geometry(own_rows, stream_rows, words > 16 ? 16 : words, kConsumers, 0);
   size_t bytes = eps_counts_bytes(g, own_rows) + 256;
-  if (eps_capture_bytes(g, own_rows) <= kEpsCaptureLimit) bytes += eps_capture_bytes(g, own_rows);
+  if (eps_capture_bytes(g, own_rows) <= kEpsCaptureLimit && own_rows < (1ll << 31))
+    bytes += eps_flag_bytes(own_rows) + eps_list_bytes(own_rows) + eps_capture_bytes(g, own_rows);
   return bytes;
 }
 
@@ -309,30 +318,32 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   const Geometry g = make_geometry(rows, stream_rows, words, kConsumers, 0);
   const size_t need = eps_counts_bytes(g, rows);
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
-  const bool capturing = workspace_bytes >= need + 256 + eps_capture_bytes(g, rows);
-  int* overflow = reinterpret_cast<int*>(static_cast<char*>(workspace) + need);
-  unsigned long long* capture = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + need + 256);
+  const size_t aux = 256 + eps_flag_bytes(rows) + eps_list_bytes(rows);
+  const bool capturing = workspace_bytes >= need + aux + eps_capture_bytes(g, rows);
+  char* wsb = static_cast<char*>(workspace);
+  long long* n_over_dev = reinterpret_cast<long long*>(wsb + need);
+  uint8_t* over_flag = reinterpret_cast<uint8_t*>(wsb + need + 256);
+  long long* over_rows = reinterpret_cast<long long*>(wsb + need + 256 + eps_flag_bytes(rows));
+  unsigned long long* capture = reinterpret_cast<unsigned long long*>(wsb + need + aux);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   SweepParams prm;
   fill_common(prm, g, own, row0, rows, stream_tab, stream_rows);
   prm.split_counts = static_cast<long long*>(workspace);
-  if (mode == MODE_COUNT && capturing) {
-    prm.capture = capture;
-    PG_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), cs));
-  }
+  if (mode == MODE_COUNT && capturing) prm.capture = capture;
+  long long n_over = -1;     // fill: -1 = sweep every row, otherwise the number of overflow rows
   if (mode == MODE_FILL && capturing) {
-    // the count pass kept every hit unless a (split,row) overflowed its capture
-    int over = 1;
-    PG_CUDA(cudaMemcpyAsync(&over, overflow, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    PG_CUDA(cudaMemcpyAsync(&n_over, n_over_dev, sizeof(long long), cudaMemcpyDeviceToHost, cs));
     PG_CUDA(cudaStreamSynchronize(cs));
-    if (!over) {
-      const int threads = 128;
-      eps_from_capture_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, cs>>>(
-          capture, prm.split_counts, g.n_splits, rows, reinterpret_cast<const long long*>(indptr), weight,
-          reinterpret_cast<long long*>(out_idx), out_w);
-      PG_LAUNCH_CHECK();
-      return PG_OK;
-    }
+    const int threads = 128;
+    eps_from_capture_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, cs>>>(
+        capture, prm.split_counts, g.n_splits, rows, over_flag, reinterpret_cast<const long long*>(indptr), weight,
+        reinterpret_cast<long long*>(out_idx), out_w);
+    PG_LAUNCH_CHECK();
+    if (n_over == 0) return PG_OK;
+    // second sweep over the overflow rows only, with the count pass's split structure
+    prm.row_map = over_rows;
+    prm.rows = n_over;
+    prm.n_rowblocks = static_cast<int>(ceil_div(n_over, kConsumers));
   }
   for (int i = 0; i < lut_words; ++i) prm.lut[i] = lut_host[i];
   const bool ranged = lut_as_range(lut_host, lut_words, &prm.lo, &prm.span);
@@ -350,8 +361,22 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   if (mode == MODE_COUNT) {
     const int threads = 256;
     sum_splits_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
-        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts), capturing ? overflow : nullptr);
+        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts), capturing ? over_flag : nullptr);
     PG_LAUNCH_CHECK();
+    if (capturing) {
+      // list of the rows whose capture overflowed (they get a fill sweep of their own)
+      thrust::counting_iterator<long long> ids(0);
+      size_t tmp_bytes = 0;
+      PG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, over_flag, over_rows, n_over_dev,
+                                         static_cast<int>(rows), l.stream));
+      void* tmp = nullptr;
+      PG_CUDA(temp_alloc(&tmp, tmp_bytes, l.stream));
+      cudaError_t e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, ids, over_flag, over_rows, n_over_dev,
+                                                 static_cast<int>(rows), l.stream);
+      count_launch();
+      cudaFreeAsync(tmp, l.stream);
+      if (e != cudaSuccess) { set_error("cub select failed: %s", cudaGetErrorString(e)); return PG_ERR_CUDA; }
+    }
   }
   return PG_OK;
 }

@@ -30,7 +30,7 @@ constexpr int kConsumers = kConsumerWarps * 32;  // threads per CTA; each owns T
 constexpr int kSweepThreads = kConsumers;
 constexpr int kStages = 4;
 constexpr int kMaxLutWords = 64;                 // distances up to 2047
-constexpr int kEpsCapture = 32;                  // hits per (split, row) kept by the count pass
+constexpr int kEpsCapture = 128;                  // hits per (split, row) kept by the count pass
 
 enum SweepMode { MODE_KNN = 0, MODE_COUNT = 1, MODE_FILL = 2, MODE_TILE = 3 };
 
@@ -42,7 +42,9 @@ struct TileCols {  // stream rows per ring stage: 64 rows of 8 words (2 KB per p
 struct SweepParams {
   const uint32_t* own;   // packed table holding the own rows
   long long own_row0;    // first own row to process
-  long long rows;        // number of own rows to process
+  long long rows;        // number of own rows to process (length of row_map when it is set)
+  const long long* row_map;  // optional: the own rows to process, relative to own_row0 (fill of a row subset)
+  long long rows_total;      // row stride of split_counts / capture / part (= rows unless row_map is set)
   const uint32_t* str;   // packed stream table (padded to kStreamRowPad rows)
   long long str_rows;    // valid stream rows
   int n_rowblocks, n_splits, tiles_per_split, n_tiles;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
       cap[i] = nullptr;
       r[i] = static_cast<long long>(rb) * ROWS_CTA + i * kConsumers + tid;
       valid[i] = r[i] < prm.rows;
+      if (prm.row_map != nullptr && valid[i]) r[i] = prm.row_map[r[i]];
       const uint32_t* src = prm.own + static_cast<size_t>(prm.own_row0 + (valid[i] ? r[i] : 0)) * COLW;
 #pragma unroll
       for (int j = 0; j < COLW; ++j) q[i][j] = valid[i] ? __ldg(src + j) : 0u;
@@ -261,12 +264,12 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
       }
       if constexpr (MODE == MODE_COUNT) {
         if (valid[i] && prm.capture != nullptr)
-          cap[i] = prm.capture + (static_cast<size_t>(split) * prm.rows + r[i]) * kEpsCapture;
+          cap[i] = prm.capture + (static_cast<size_t>(split) * prm.rows_total + r[i]) * kEpsCapture;
       }
       if constexpr (MODE == MODE_FILL) {
         if (valid[i]) {
           cnt[i] = prm.indptr[r[i]];
-          for (int s = 0; s < split; ++s) cnt[i] += prm.split_counts[static_cast<size_t>(s) * prm.rows + r[i]];
+          for (int s = 0; s < split; ++s) cnt[i] += prm.split_counts[static_cast<size_t>(s) * prm.rows_total + r[i]];
         }
       }
     }
@@ -375,11 +378,11 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
       if constexpr (MODE == MODE_KNN) {
         if (valid[i]) {
           const unsigned long long* mine = lists + static_cast<size_t>(i * kConsumers + tid) * prm.k1;
-          unsigned long long* dst = prm.part + static_cast<size_t>(split) * prm.k1 * prm.rows + r[i];
-          for (int j = 0; j < prm.k1; ++j) dst[static_cast<size_t>(j) * prm.rows] = mine[j];
+          unsigned long long* dst = prm.part + static_cast<size_t>(split) * prm.k1 * prm.rows_total + r[i];
+          for (int j = 0; j < prm.k1; ++j) dst[static_cast<size_t>(j) * prm.rows_total] = mine[j];
         }
       } else if constexpr (MODE == MODE_COUNT) {
-        if (valid[i]) prm.split_counts[static_cast<size_t>(split) * prm.rows + r[i]] = cnt[i];
+        if (valid[i]) prm.split_counts[static_cast<size_t>(split) * prm.rows_total + r[i]] = cnt[i];
       }
     }
     if constexpr (MODE == MODE_KNN) __syncwarp();
