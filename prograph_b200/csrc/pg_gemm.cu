@@ -13,7 +13,8 @@
 //     with 1-D bulk async copies (cp.async.bulk + mbarrier), no tensor map needed;
 //   * one CTA = 128 query rows (A tile, resident) against the whole dataset streamed in
 //     128-row B tiles through a 4-stage ring; M=128, N=128, K=32 per instruction;
-//   * two 128-column TMEM accumulators: the MMA of tile t+1 overlaps the epilogue of tile t;
+//   * four 128-column TMEM accumulators (all of TMEM), two per epilogue group: the MMAs run up
+//     to two tiles ahead of each group's epilogue;
 //   * warp roles: 8 epilogue warps in two groups that alternate tiles (thread = TMEM lane =
 //     query row, each group keeps its own lists, merged at the end), 1 producer lane,
 //     1 MMA-issuing lane (which also owns the TMEM allocation); the dataset norms ride along
@@ -33,6 +34,7 @@ constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp
 constexpr int GPROD_WARP = 8;
 constexpr int GMMA_WARP = 9;
 constexpr int GPROD_LANES = 8;  // lanes of the producer warp that each copy a slice of a B tile
+constexpr int GACC = 4;         // TMEM accumulators (4 x 128 columns = all 512): two per epilogue group
 constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
 constexpr int PAD_NORM = 0x3fffffff;
 
@@ -110,28 +112,11 @@ __device__ __forceinline__ uint32_t value_bits(int S, bool similarity) {
 // values are non-negative: their bit patterns order like the values; similarities sort descending
 __device__ __forceinline__ uint32_t order_key(uint32_t bits, bool similarity) { return similarity ? ~bits : bits; }
 
-// Smallest S in [0, 2^25] whose key is >= tau_key (keys are monotone non-decreasing in S): a
-// warp-cooperative 32-ary search, 5 rounds.  All lanes call it with the same tau_key.
-// Invariant: every S below `base` has key < tau_key.
-template <int VK>
-__device__ __forceinline__ int s_threshold(uint32_t tau_key, bool similarity, int lane) {
-  int base = 0;
-#pragma unroll 1
-  for (int step = 1 << 20;; step >>= 5) {
-    const int probe = base + lane * step;
-    const bool ge = order_key(value_bits<VK>(probe, similarity), similarity) >= tau_key;
-    const unsigned b = __ballot_sync(0xffffffffu, ge);
-    const int first = b ? __ffs(b) - 1 : 32;      // first probe that reaches tau_key
-    if (first == 0) return base;
-    if (step == 1) return base + first;
-    base += (first - 1) * step + 1;                // answer lies in (probe[first-1], probe[first]]
-  }
-}
-
 struct GemmParams {
   const uint8_t* A; const int* normA; long long M;       // queries (own rows)
   const uint8_t* B; const int* normB; long long N;       // dataset (stream rows)
   int K;                                                 // padded width, multiple of 32
+  int stages;                                            // depth of the B ring (3 or 4)
   int similarity;
   // tile
   void* out; long long ld;
@@ -140,22 +125,56 @@ struct GemmParams {
   long long* out_idx; void* out_val;
 };
 
+// Warp-cooperative sorted insertion of (key, S) into one row's list (see knn_insert_coop in
+// pg_sweep.cuh); the exact integer sum S travels with its key so that the candidate threshold
+// is simply the S of the last entry.  Precondition: key < list[k1-1].
+__device__ __forceinline__ int knn_insert_coop_s(unsigned long long* list, int* slist, int k1,
+                                                 unsigned long long key, int S, int lane) {
+  unsigned long long cur[kMaxListRounds], prev[kMaxListRounds];
+  int sprev[kMaxListRounds];
+  int pos = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxListRounds; ++r) {
+    const int j = lane + 32 * r;
+    const bool in = j < k1;
+    cur[r] = in ? list[j] : ~0ull;
+    prev[r] = (in && j > 0) ? list[j - 1] : 0ull;
+    sprev[r] = (in && j > 0) ? slist[j - 1] : 0;
+    pos += __popc(__ballot_sync(0xffffffffu, in && cur[r] < key));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < kMaxListRounds; ++r) {
+    const int j = lane + 32 * r;
+    if (j < k1 && j >= pos) {
+      list[j] = (j == pos) ? key : prev[r];
+      slist[j] = (j == pos) ? S : sprev[r];
+    }
+  }
+  __syncwarp();
+  return slist[k1 - 1];
+}
+
 // Rare path of the fused kNN, kept out of line so that the 32 call sites of a chunk stay small
-// (inlined, the insertion + threshold search blew the instruction cache: ~5700 clk per insert).
-// `cand`: lanes whose row has a candidate in this column; `S` = this lane's exact integer sum.
-// Returns the lane's updated threshold (tprime = thr_S - nq).
+// (inlined, the insertion blew the instruction cache: ~5700 clk per insert).
+// `cand`: lanes whose row may have a candidate in this column (S below the S of the row's last
+// list entry -- a superset of the true candidates because the key is monotone in S); the exact
+// test is the lexicographic comparison of the full key with the last entry.
+// Returns the lane's updated threshold (tprime = S_last - nq).
 template <int VK>
-__device__ __noinline__ int gemm_knn_serve(unsigned cand, int S, unsigned col, unsigned long long* warp_lists, int k1,
-                                           bool sim, int lane, int nq, int tprime) {
+__device__ __noinline__ int gemm_knn_serve(unsigned cand, int S, unsigned col, unsigned long long* warp_lists,
+                                           int* warp_slists, int k1, bool sim, int lane, int nq, int tprime) {
   while (cand) {
     const int src = __ffs(cand) - 1;
     cand &= cand - 1;
     const int s_src = __shfl_sync(0xffffffffu, S, src);
     const uint32_t key32 = order_key(value_bits<VK>(s_src, sim), sim);
     const unsigned long long key = (static_cast<unsigned long long>(key32) << 32) | col;
-    const uint32_t tau = knn_insert_coop(warp_lists + static_cast<size_t>(src) * k1, k1, key, lane);
-    const int thr = s_threshold<VK>(tau, sim, lane);     // candidates: S < thr
-    if (lane == src) tprime = thr - nq;
+    unsigned long long* lst = warp_lists + static_cast<size_t>(src) * k1;
+    if (key < lst[k1 - 1]) {
+      const int s_last = knn_insert_coop_s(lst, warp_slists + static_cast<size_t>(src) * k1, k1, key, s_src, lane);
+      if (lane == src) tprime = s_last - nq;
+    }
   }
   return tprime;
 }
@@ -180,15 +199,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const uint32_t tile_bytes = GM * K;                     // A and B tiles have the same shape
   uint8_t* sA = smem;
   uint8_t* sB = smem + tile_bytes;
-  int* sNorm = reinterpret_cast<int*>(smem + tile_bytes * (1 + GSTAGES));        // [GNORM_SLOTS][GN]
+  const int n_stages = prm.stages;
+  int* sNorm = reinterpret_cast<int*>(smem + tile_bytes * (1 + n_stages));        // [GNORM_SLOTS][GN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + GNORM_SLOTS * GN);
   uint64_t* full = bars;                  // [GSTAGES] B tile (+ its norms) landed
   uint64_t* empty = bars + GSTAGES;       // [GSTAGES] MMAs reading the stage have completed
-  uint64_t* acc_full = bars + 2 * GSTAGES;    // [2] accumulator ready for the epilogue
-  uint64_t* acc_empty = acc_full + 2;         // [2] epilogue has drained the accumulator
-  uint64_t* a_full = acc_empty + 2;
+  uint64_t* acc_full = bars + 2 * GSTAGES;    // [GACC] accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + GACC;      // [GACC] epilogue has drained the accumulator
+  uint64_t* a_full = acc_empty + GACC;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
   unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [2][GM][k1]
+  int* slists = reinterpret_cast<int*>(lists + 2 * GM * prm.k1);                        // [2][GM][k1] exact sums
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -198,12 +219,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const bool sim = prm.similarity != 0;
 
   if (tid == 0) {
-    for (int s = 0; s < GSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < GACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
     mbar_init(a_full, 1);
     fence_mbar_init();
   }
-  if (warp == GMMA_WARP) tmem_alloc(tmem_holder, 2 * GN);  // 256 columns: two int32 accumulators
+  if (warp == GMMA_WARP) tmem_alloc(tmem_holder, GACC * GN);  // all 512 columns: four int32 accumulators
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -234,7 +255,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
                  prm.B + static_cast<size_t>(t) * GN * K + lane * slice, slice, &full[stage]);
       }
-      if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == GMMA_WARP) {
     // ---------------- MMA issuer ----------------
@@ -246,8 +267,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int acc = t & 1;
-        mbar_wait_poll(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
+        const int acc = t & (GACC - 1);
+        mbar_wait_poll(&acc_empty[acc], ((t / GACC) & 1) ^ 1u);
         mbar_wait_poll(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA);
@@ -258,7 +279,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         }
         umma_commit(&empty[stage]);       // the stage may be refilled once these MMAs have read it
         umma_commit(&acc_full[acc]);      // ... and the accumulator is complete
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -272,13 +293,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
     unsigned long long* my_list = lists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
     int tprime = valid ? 0x7fffffff : static_cast<int>(0x80000000);   // candidate iff (nx - 2 dot) < tprime
     if (MODE == GM_KNN) {
-      for (int j = 0; j < prm.k1; ++j) my_list[j] = ~0ull;
+      int* my_slist = slists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
+      for (int j = 0; j < prm.k1; ++j) { my_list[j] = ~0ull; my_slist[j] = 0x7fffffff; }
       __syncwarp();
     }
     const uint32_t lane_base = static_cast<uint32_t>(qwarp * 32) << 16;
     for (int t = group; t < n_tiles; t += 2) {
-      const int acc = group;
-      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      const int acc = t & (GACC - 1);       // group g drains accumulators g and g+2 in turn
+      mbar_wait(&acc_full[acc], (t / GACC) & 1);
       tc_fence_after();
       const long long col_tile = static_cast<long long>(t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
@@ -342,12 +364,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
           const int best = min(min(min(m8[0], m8[1]), min(m8[2], m8[3])), min(min(m8[4], m8[5]), min(m8[6], m8[7])));
           if (__any_sync(0xffffffffu, best < tprime)) {
             unsigned long long* warp_lists = lists + (static_cast<size_t>(group) * GM + qwarp * 32) * prm.k1;
+            int* warp_slists = slists + (static_cast<size_t>(group) * GM + qwarp * 32) * prm.k1;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const unsigned cand = __ballot_sync(0xffffffffu, v[j] < tprime);
               if (cand)
-                tprime = gemm_knn_serve<VK>(cand, nq + v[j], static_cast<unsigned>(col0 + j), warp_lists, prm.k1, sim,
-                                            lane, nq, tprime);
+                tprime = gemm_knn_serve<VK>(cand, nq + v[j], static_cast<unsigned>(col0 + j), warp_lists, warp_slists,
+                                            prm.k1, sim, lane, nq, tprime);
             }
           }
         }
@@ -387,7 +410,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == GMMA_WARP) tmem_dealloc(tmem_base, 2 * GN);
+  if (warp == GMMA_WARP) tmem_dealloc(tmem_base, GACC * GN);
 }
 
 // ---- operand packing: tokens -> K-major core-matrix layout + squared norms -----------------
@@ -455,15 +478,20 @@ __global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long
   }
 }
 
-static size_t gemm_smem_bytes(int K, int k1) {
-  return static_cast<size_t>(GM) * K * (1 + GSTAGES) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 5) * sizeof(uint64_t) +
-         16 + 2 * static_cast<size_t>(GM) * k1 * 8;
+static size_t gemm_smem_bytes(int K, int k1, int stages) {
+  return static_cast<size_t>(GM) * K * (1 + stages) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 2 * GACC + 1) * sizeof(uint64_t) +
+         16 + 2 * static_cast<size_t>(GM) * k1 * 12;
 }
 
 template <int VK, int MODE>
-static int launch_gemm(const GemmParams& prm, cudaStream_t s) {
+static int launch_gemm(GemmParams prm, cudaStream_t s) {
   auto kern = mink_gemm_kernel<VK, MODE>;
-  const size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0);
+  prm.stages = GSTAGES;
+  size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages);
+  if (smem > 227 * 1024) {     // long lists: give up one ring stage before giving up the fused path
+    prm.stages = GSTAGES - 1;
+    smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages);
+  }
   if (smem > 227 * 1024) { set_error("minkowski GEMM: k or row width too large for shared memory (%zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const unsigned grid = static_cast<unsigned>(ceil_div(prm.M, GM));
