@@ -215,7 +215,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const long long row0 = static_cast<long long>(blockIdx.x) * GM;
-  const int n_tiles = static_cast<int>((prm.N + GN - 1) / GN);
+  // blockIdx.y splits the dataset (tile mode with few query rows): this CTA sweeps tiles
+  // [t_begin, t_begin + n_tiles); `t` below counts tiles within that range
+  const int all_tiles = static_cast<int>((prm.N + GN - 1) / GN);
+  const int tiles_per_split = (all_tiles + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
+  const int t_begin = static_cast<int>(blockIdx.y) * tiles_per_split;
+  const int n_tiles = max(0, min(tiles_per_split, all_tiles - t_begin));
   const bool sim = prm.similarity != 0;
 
   if (tid == 0) {
@@ -248,12 +253,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         mbar_arrive_expect_tx(&full[stage], tile_bytes + GN * 4);
         // the norms of tile t live in slot t % GNORM_SLOTS until the epilogue of tile t is done;
         // slot reuse (tile t + 8) is ordered behind MMA t+4, i.e. behind the epilogue of tile t+2
-        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t) * GN, GN * 4, &full[stage]);
+        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + t) * GN, GN * 4, &full[stage]);
       }
       __syncwarp();
       if (lane < GPROD_LANES) {
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
-                 prm.B + static_cast<size_t>(t) * GN * K + lane * slice, slice, &full[stage]);
+                 prm.B + static_cast<size_t>(t_begin + t) * GN * K + lane * slice, slice, &full[stage]);
       }
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
     }
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       const int acc = t & (GACC - 1);       // group g drains accumulators g and g+2 in turn
       mbar_wait(&acc_full[acc], (t / GACC) & 1);
       tc_fence_after();
-      const long long col_tile = static_cast<long long>(t) * GN;
+      const long long col_tile = static_cast<long long>(t_begin + t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
       uint32_t dotbuf[2][32];
       tmem_ld32_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
@@ -494,8 +499,16 @@ static int launch_gemm(GemmParams prm, cudaStream_t s) {
   }
   if (smem > 227 * 1024) { set_error("minkowski GEMM: k or row width too large for shared memory (%zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const unsigned grid = static_cast<unsigned>(ceil_div(prm.M, GM));
-  kern<<<grid, GTHREADS, smem, s>>>(prm);
+  const unsigned gx = static_cast<unsigned>(ceil_div(prm.M, GM));
+  unsigned gy = 1;
+  if (MODE == GM_TILE) {   // few query rows: split the dataset so that every SM gets a CTA or two
+    const long long tiles = ceil_div(prm.N, GN);
+    long long want = ceil_div(2 * static_cast<long long>(num_sms()), gx);
+    if (want > tiles / 8) want = tiles / 8;
+    if (want > 65535) want = 65535;
+    gy = static_cast<unsigned>(want < 1 ? 1 : want);
+  }
+  kern<<<dim3(gx, gy), GTHREADS, smem, s>>>(prm);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
