@@ -43,7 +43,7 @@ struct Geometry {
   int n_rowblocks, n_splits, tiles_per_split, n_tiles, tile_cols;
 };
 
-static int tile_cols_for(int words) { return 512 / words; }
+static int tile_cols_for(int words) { return words > 16 ? 32 : 512 / words; }   // long rows: pg_sweep_long.cu
 
 // Splits of the stream shorten the persistent grid's last wave, but every split restarts its
 // kNN lists from empty.  Pick the split count that minimises a small cost model (in units of
@@ -86,7 +86,12 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
   return g;
 }
 
+int sweep_long_p5(const SweepParams& prm, const SweepLaunch& l, int words);   // pg_sweep_long.cu
+
+static bool long_rows(int planes, int words) { return planes == 5 && words > 16 && words <= 56 && words % 8 == 0; }
+
 static int dispatch(int planes, int words, const SweepParams& prm, const SweepLaunch& l) {
+  if (long_rows(planes, words)) return sweep_long_p5(prm, l, words);
 #define PG_CASE(P, W) \
   if (planes == P && words == W) return sweep_p##P##_w##W(prm, l);
   PG_CASE(5, 1) PG_CASE(5, 2) PG_CASE(5, 4) PG_CASE(5, 8) PG_CASE(5, 16)
@@ -106,9 +111,9 @@ static int check_common(const void* own, long long own_rows, long long row0, lon
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(str) & 15) == 0, "stream table must be 16-byte aligned");
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(own) & 15) == 0, "own table must be 16-byte aligned");
   if (!(((planes == 5 || planes == 8) && (words == 1 || words == 2 || words == 4 || words == 8)) ||
-        (planes == 5 && words == 16))) {
-    set_error("fused sweep supports planes in {5,8} x words in {1,2,4,8} and planes=5, words=16; got planes=%d words=%d",
-              planes, words);
+        (planes == 5 && words == 16) || long_rows(planes, words))) {
+    set_error("fused sweep supports planes in {5,8} x words in {1,2,4,8} and planes=5 with words 16,24,..,56; got "
+              "planes=%d words=%d", planes, words);
     return PG_ERR_UNSUPPORTED;
   }
   return PG_OK;
@@ -242,7 +247,6 @@ extern "C" {
 
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
-  if (words > 16) words = 16;
   // the largest split count any sweep of this shape may choose (kNN with k1 entries, the
   // count / fill passes, the two-rows-per-thread kNN variants)
   int n_splits = 1;
@@ -258,7 +262,7 @@ size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words
 
 size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
-  const Geometry g = make_geometry(own_rows, stream_rows, words > 16 ? 16 : words, kConsumers, 0);
+  const Geometry g = make_geometry(own_rows, stream_rows, words, kConsumers, 0);
   size_t bytes = eps_counts_bytes(g, own_rows) + 256;
   if (eps_capture_bytes(g, own_rows) <= kEpsCaptureLimit && own_rows < (1ll << 31))
     bytes += eps_flag_bytes(own_rows) + eps_list_bytes(own_rows) + eps_capture_bytes(g, own_rows);

@@ -323,7 +323,7 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     if kind == "hamming":
         try:
             packed = pack_table(eng, X, rank, world, group)
-            if packed.words > 16 or (packed.words > 8 and packed.planes != 5):
+            if packed.words > 56 or (packed.words > 8 and packed.planes != 5):
                 packed = None
         except OverflowError:
             packed = None

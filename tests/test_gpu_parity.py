@@ -94,7 +94,7 @@ def test_hamming_tokens_golden(pgb, g_distance):
     np.testing.assert_array_equal(np_(out), g["i_ham"])
 
 
-@pytest.mark.parametrize("L", [1, 20, 32, 33, 56, 64, 100, 128, 200, 256, 300, 512, 513, 700])
+@pytest.mark.parametrize("L", [1, 20, 32, 33, 56, 64, 100, 128, 200, 256, 300, 512, 513, 700, 1500, 2000])
 @pytest.mark.parametrize("alphabet", [20, 200])
 def test_hamming_matrix_vs_oracle(pgb, L, alphabet):
     rng = np.random.default_rng(L * 1000 + alphabet)
@@ -143,7 +143,7 @@ def test_minkowski_golden(pgb, g_distance):
 
 
 # ------------------------------------------------------------------ fused kNN / eps (engine level)
-@pytest.mark.parametrize("L,k", [(3, 3), (20, 16), (56, 16), (100, 5), (256, 16), (256, 40), (400, 16), (512, 7)])
+@pytest.mark.parametrize("L,k", [(3, 3), (20, 16), (56, 16), (100, 5), (256, 16), (256, 40), (400, 16), (512, 7), (700, 16), (1000, 5), (1792, 3)])
 def test_fused_knn_uniform_ties(eng, L, k):
     """iid-uniform tokens: the k-th place of almost every row is a tie."""
     rng = np.random.default_rng(L + k)
@@ -203,7 +203,7 @@ def test_fused_knn_queries_vs_dataset(eng):
     np.testing.assert_array_equal(np_(d)[:, 0], D.min(axis=1))
 
 
-@pytest.mark.parametrize("L", [3, 56, 256, 300])
+@pytest.mark.parametrize("L", [3, 56, 256, 300, 900])
 def test_fused_eps_vs_oracle(eng, L):
     from prograph_b200.graph import distance_lut
     rng = np.random.default_rng(L)
