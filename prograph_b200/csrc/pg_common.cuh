@@ -88,30 +88,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
-// Producer-side wait: try_wait with a suspend-time hint parks the lone producer lane in
-// hardware until the phase completes (or ~20 us pass) instead of polling -- the bare spin was
-// 14 % of all executed instructions and stole issue slots from the consumer warps on its
-// scheduler (profiles/r1_ncu_notes.md).
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    __nanosleep(1000);
-    if (++spins > (1u << 22)) __trap();
-  }
-}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
