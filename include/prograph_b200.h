@@ -170,6 +170,20 @@ int pg_minkowski2_gemm_knn(const uint8_t* A, const int32_t* normA, int64_t M,
                            int value_kind, int similarity, int k, int drop,
                            int64_t* out_idx, void* out_val, void* stream);
 
+/* fused epsilon graph (prograph.py:731-753 with distance=minkowski): the edge test
+ * comp(d, eps) & (d > 0) is monotone in S, so the caller passes it as the integer range
+ * [s_lo, s_hi].  Pass 1: group_counts [2][M] (hits in the first / second half of the dataset,
+ * a workspace the fill pass reads back) and counts [M]; pass 2 writes ascending column indices
+ * and values (fp16 / float32) at indptr[r].. */
+int pg_minkowski2_gemm_eps_count(const uint8_t* A, const int32_t* normA, int64_t M,
+                                 const uint8_t* B, const int32_t* normB, int64_t N, int K,
+                                 int s_lo, int s_hi, int64_t* group_counts, int64_t* counts, void* stream);
+int pg_minkowski2_gemm_eps_fill(const uint8_t* A, const int32_t* normA, int64_t M,
+                                const uint8_t* B, const int32_t* normB, int64_t N, int K,
+                                int value_kind, int similarity, int s_lo, int s_hi,
+                                const int64_t* group_counts, const int64_t* indptr,
+                                int64_t* out_idx, void* out_val, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Consumers of a materialised (rows x N) tile: used for Minkowski, for user supplied
  * distance callables (README.md:48) and for single-row queries.

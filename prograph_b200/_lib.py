@@ -51,6 +51,8 @@ SIGNATURES = {
     "pg_gemm_pack": (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _i, _i, _vp, _vp]),
     "pg_minkowski2_gemm_tile": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp]),
     "pg_minkowski2_gemm_knn": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pg_minkowski2_gemm_eps_count": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "pg_minkowski2_gemm_eps_fill": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pg_tile_topk": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "pg_tile_threshold_count": (_i, [_vp, _i, _i64, _i64, _i64, _i, _dbl, _i, _i, _vp, _vp]),
     "pg_tile_threshold_fill": (_i, [_vp, _i, _i64, _i64, _i64, _i, _dbl, _i, _i, _vp, _vp, _vp, _vp]),

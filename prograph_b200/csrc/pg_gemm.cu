@@ -39,7 +39,7 @@ constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
 constexpr int PAD_NORM = 0x3fffffff;
 
 enum GemmValue { GV_F16 = 0, GV_F32 = 1 };     // which rounding chain turns S into the distance
-enum GemmMode { GM_TILE = 0, GM_KNN = 1 };
+enum GemmMode { GM_TILE = 0, GM_KNN = 1, GM_COUNT = 2, GM_FILL = 3 };
 
 // ---- tcgen05 / TMEM PTX -----------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
@@ -123,6 +123,10 @@ struct GemmParams {
   // kNN
   int k1, k, drop;
   long long* out_idx; void* out_val;
+  // epsilon graph: keep iff s_lo <= S <= s_lo + s_span (the reference's edge test is monotone in S)
+  int s_lo; unsigned s_span;
+  long long* group_counts;      // [2][M] hits of every row in the first / second half of the dataset
+  const long long* indptr;      // [M+1] (fill)
 };
 
 // Warp-cooperative sorted insertion of (key, S) into one row's list (see knn_insert_coop in
@@ -192,6 +196,18 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Epsilon modes walk the tiles as 0, h, 1, h+1, ... (h = half the tiles) so that each epilogue group
+// (even / odd positions) owns one contiguous half of the dataset: its hits of a row are then a
+// contiguous, ascending part of that row's edge list.
+template <int MODE>
+__device__ __forceinline__ int tile_at(int pos, int n_tiles) {
+  if (MODE == GM_COUNT || MODE == GM_FILL) {
+    const int half = (n_tiles + 1) >> 1;
+    return (pos & 1) ? half + (pos >> 1) : (pos >> 1);
+  }
+  return pos;
+}
+
 template <int VK, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -253,12 +269,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         mbar_arrive_expect_tx(&full[stage], tile_bytes + GN * 4);
         // the norms of tile t live in slot t % GNORM_SLOTS until the epilogue of tile t is done;
         // slot reuse (tile t + 8) is ordered behind MMA t+4, i.e. behind the epilogue of tile t+2
-        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + t) * GN, GN * 4, &full[stage]);
+        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN,
+                 GN * 4, &full[stage]);
       }
       __syncwarp();
       if (lane < GPROD_LANES) {
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
-                 prm.B + static_cast<size_t>(t_begin + t) * GN * K + lane * slice, slice, &full[stage]);
+                 prm.B + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN * K + lane * slice, slice,
+                 &full[stage]);
       }
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
     }
@@ -302,12 +320,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       for (int j = 0; j < prm.k1; ++j) { my_list[j] = ~0ull; my_slist[j] = 0x7fffffff; }
       __syncwarp();
     }
+    long long ecur = 0;    // epsilon modes: hits counted / next edge slot of this (row, group)
+    if (MODE == GM_FILL && valid)
+      ecur = prm.indptr[row] + (group ? prm.group_counts[row] : 0);
+    const int eoff = nq - prm.s_lo;    // in range iff (unsigned)(v + eoff) <= s_span
     const uint32_t lane_base = static_cast<uint32_t>(qwarp * 32) << 16;
     for (int t = group; t < n_tiles; t += 2) {
       const int acc = t & (GACC - 1);       // group g drains accumulators g and g+2 in turn
       mbar_wait(&acc_full[acc], (t / GACC) & 1);
       tc_fence_after();
-      const long long col_tile = static_cast<long long>(t_begin + t) * GN;
+      const long long col_tile = static_cast<long long>(t_begin + tile_at<MODE>(t, n_tiles)) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
       uint32_t dotbuf[2][32];
       tmem_ld32_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
@@ -361,6 +383,24 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
               }
             }
           }
+        } else if (MODE == GM_COUNT) {
+          int c32 = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c32 += (static_cast<unsigned>(v[j] + eoff) <= prm.s_span) ? 1 : 0;
+          ecur += valid ? c32 : 0;
+        } else if (MODE == GM_FILL) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (static_cast<unsigned>(v[j] + eoff) <= prm.s_span) {
+                prm.out_idx[ecur] = col0 + j;
+                const uint32_t bits = value_bits<VK>(nq + v[j], sim);
+                if (VK == GV_F16) static_cast<unsigned short*>(prm.out_val)[ecur] = static_cast<unsigned short>(bits);
+                else static_cast<uint32_t*>(prm.out_val)[ecur] = bits;
+                ++ecur;
+              }
+            }
+          }
         } else {
           // tree minimum of the 32 values (a linear chain would serialise 31 dependent mins)
           int m8[8];
@@ -384,6 +424,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
+    if (MODE == GM_COUNT && valid) prm.group_counts[static_cast<size_t>(group) * prm.M + row] = ecur;
     if (MODE == GM_KNN) {
       // merge the two groups' lists of every row (both ascending, keys unique) and write out
       named_barrier_sync(1, 8 * 32);
@@ -597,6 +638,56 @@ int pg_minkowski2_gemm_knn(const uint8_t* A, const int32_t* normA, int64_t M, co
   prm.out_val = out_val;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return value_kind == GV_F16 ? launch_gemm<GV_F16, GM_KNN>(prm, s) : launch_gemm<GV_F32, GM_KNN>(prm, s);
+}
+
+static int gemm_eps_common(GemmParams& prm, int s_lo, int s_hi, int64_t* group_counts) {
+  PG_CHECK_ARG(group_counts, "null group counts");
+  PG_CHECK_ARG(s_lo >= 0 && s_hi >= s_lo && s_hi < PAD_NORM / 2, "bad S range [%d, %d]", s_lo, s_hi);
+  prm.s_lo = s_lo;
+  prm.s_span = static_cast<unsigned>(s_hi - s_lo);
+  prm.group_counts = reinterpret_cast<long long*>(group_counts);
+  return PG_OK;
+}
+
+__global__ void gemm_sum_groups_kernel(const long long* __restrict__ gc, long long M, long long* __restrict__ counts) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r < M) counts[r] = gc[r] + gc[M + r];
+}
+
+int pg_minkowski2_gemm_eps_count(const uint8_t* A, const int32_t* normA, int64_t M, const uint8_t* B,
+                                 const int32_t* normB, int64_t N, int K, int s_lo, int s_hi, int64_t* group_counts,
+                                 int64_t* counts, void* stream) {
+  GemmParams prm;
+  int rc = gemm_common(prm, A, normA, M, B, normB, N, K, GV_F32, 0);
+  if (rc != PG_OK) return rc;
+  rc = gemm_eps_common(prm, s_lo, s_hi, group_counts);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(counts, "null counts");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_CUDA(cudaMemsetAsync(group_counts, 0, sizeof(int64_t) * 2 * M, s));
+  rc = launch_gemm<GV_F32, GM_COUNT>(prm, s);
+  if (rc != PG_OK) return rc;
+  gemm_sum_groups_kernel<<<static_cast<unsigned>(ceil_div(M, 256)), 256, 0, s>>>(prm.group_counts, M,
+                                                                                 reinterpret_cast<long long*>(counts));
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_minkowski2_gemm_eps_fill(const uint8_t* A, const int32_t* normA, int64_t M, const uint8_t* B,
+                                const int32_t* normB, int64_t N, int K, int value_kind, int similarity, int s_lo,
+                                int s_hi, const int64_t* group_counts, const int64_t* indptr, int64_t* out_idx,
+                                void* out_val, void* stream) {
+  GemmParams prm;
+  int rc = gemm_common(prm, A, normA, M, B, normB, N, K, value_kind, similarity);
+  if (rc != PG_OK) return rc;
+  rc = gemm_eps_common(prm, s_lo, s_hi, const_cast<int64_t*>(group_counts));
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(indptr && out_idx && out_val, "null indptr / output");
+  prm.indptr = reinterpret_cast<const long long*>(indptr);
+  prm.out_idx = reinterpret_cast<long long*>(out_idx);
+  prm.out_val = out_val;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return value_kind == GV_F16 ? launch_gemm<GV_F16, GM_FILL>(prm, s) : launch_gemm<GV_F32, GM_FILL>(prm, s);
 }
 
 }  // extern "C"

@@ -249,6 +249,28 @@ class CudaEngine:
                                                 self._stream()))
         return idx, val
 
+    def minkowski2_gemm_eps(self, data, queries, s_lo, s_hi, value_kind, similarity=False):
+        """Fused Minkowski p=2 epsilon graph: CSR (indptr, idx, val) of the dataset rows whose exact
+        integer sum S lies in [s_lo, s_hi] (the caller derives the range from comp / eps)."""
+        assert data.K == queries.K
+        M = queries.rows
+        gc = self.empty((2 * M,), torch.int64)
+        counts = self.empty((M,), torch.int64)
+        L.check(self.lib.pg_minkowski2_gemm_eps_count(_ptr(queries.data), _ptr(queries.norms), M, _ptr(data.data),
+                                                      _ptr(data.norms), data.rows, data.K, int(s_lo), int(s_hi), _ptr(gc),
+                                                      _ptr(counts), self._stream()))
+        indptr = self.exclusive_scan(counts)
+        nnz = int(indptr[-1].item())
+        self._check_edge_budget(nnz)
+        idx = self.empty((nnz,), torch.int64)
+        val = self.empty((nnz,), torch.float16 if value_kind == 0 else torch.float32)
+        if nnz:
+            L.check(self.lib.pg_minkowski2_gemm_eps_fill(_ptr(queries.data), _ptr(queries.norms), M, _ptr(data.data),
+                                                         _ptr(data.norms), data.rows, data.K, int(value_kind),
+                                                         1 if similarity else 0, int(s_lo), int(s_hi), _ptr(gc),
+                                                         _ptr(indptr), _ptr(idx), _ptr(val), self._stream()))
+        return indptr, idx, val
+
     # ---- tile consumers ----------------------------------------------------------------------
     def tile_topk(self, tile, k, drop=1, descending=False):
         rows, N = tile.shape

@@ -229,6 +229,34 @@ def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows):
 
 
 # ---------------------------------------------------------------------------------
+# Minkowski p=2 on integer tokens: the edge test as a range of the exact integer sum S
+# ---------------------------------------------------------------------------------
+def minkowski_s_range(s_max, comp, eps, similarity):
+    """The fp16 rounding chain of minkowski.py:36-40 maps the exact integer
+    S = sum (x - y)^2 to d = fp16(sqrt(fp16(S))) (and to 1/(1+d) for similarity), monotonically.
+    Evaluate the reference's edge test (prograph.py:734-736) for every S in [0, s_max] and return
+    it as an inclusive range (lo, hi), (1, 0) when nothing passes, or None when the passing set is
+    not one interval (operator.ne)."""
+    S = np.arange(s_max + 1, dtype=np.int64)
+    with np.errstate(over="ignore"):
+        s16 = S.astype(np.float32).astype(np.float16)
+        d = np.sqrt(s16.astype(np.float32)).astype(np.float16)
+        if similarity:
+            one_plus = (np.float32(1.0) + d.astype(np.float32)).astype(np.float16)
+            d = (np.float32(1.0) / one_plus.astype(np.float32)).astype(np.float16)
+    t = torch.from_numpy(d)
+    keep = (comp(eps, t) & (t < 1)) if similarity else (comp(t, eps) & (t > 0))
+    keep = torch.as_tensor(keep).numpy().astype(bool)
+    hits = np.nonzero(keep)[0]
+    if len(hits) == 0:
+        return 1, 0
+    lo, hi = int(hits[0]), int(hits[-1])
+    if hi - lo + 1 != len(hits):
+        return None
+    return lo, hi
+
+
+# ---------------------------------------------------------------------------------
 # tile path (minkowski, hamming on values, user callables)
 # ---------------------------------------------------------------------------------
 def _tile_rows(n_cols, itemsize, batch_size):
@@ -354,6 +382,16 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
                     part = eng.minkowski2_gemm_knn(gemm, q, kk, 1, 0, similarity=similarity)
                 except L.Unsupported:
                     part = None
+        if gemm is not None and eps and rows and comp in _CMP_CODES:
+            rng = minkowski_s_range(gemm.K * gemm.max_token * gemm.max_token, comp, eps, similarity)
+            if rng is not None:
+                lo, hi = rng
+                if lo > hi:
+                    part = (torch.zeros(rows + 1, dtype=torch.int64, device=eng.device),
+                            eng.empty((0,), torch.int64), eng.empty((0,), torch.float16))
+                else:
+                    q = gemm if (row0 == 0 and rows == n) else eng.gemm_pack(Xh[row0:row0 + rows], max_token=31, K=gemm.K)
+                    part = eng.minkowski2_gemm_eps(gemm, q, lo, hi, 0, similarity=similarity)
         if part is None:
             tiles = _tiles(eng, Xh, kind, p, distance, similarity, batch_size, row0, rows, gemm=gemm)
             if eps:

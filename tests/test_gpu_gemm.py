@@ -78,3 +78,36 @@ def test_gemm_knn_uniform_and_queries(eng):
     D = O.minkowski(X.astype(np.int64), Q.astype(np.int64))
     np.testing.assert_array_equal(np_(idx)[:, 0], np.argmin(D, axis=1))
     np.testing.assert_array_equal(np_(val)[:, 0], D.min(axis=1))
+
+
+@pytest.mark.parametrize("sim", [False, True])
+def test_gemm_eps_graph_matches_tile_threshold(eng, sim):
+    """Fused epsilon epilogue (S-range test) against the threshold consumer on the materialised
+    fp16 tile, for every ordering comparison."""
+    import operator
+    from prograph_b200 import _lib as L
+    from prograph_b200.graph import minkowski_s_range
+    rng = np.random.default_rng(21)
+    n, Lw = 2500, 100
+    wt = rng.integers(1, 21, size=Lw)
+    X = np.tile(wt, (n, 1))
+    for i in range(1, n):
+        pos = rng.choice(Lw, size=rng.integers(1, 5), replace=False)
+        X[i, pos] = rng.integers(1, 21, size=len(pos))
+    X[40] = X[39]
+    tab = eng.gemm_pack(X, max_token=31)
+    tile = eng.minkowski2_gemm_tile(tab, tab, 0, similarity=sim)
+    for comp, code, eps in ((operator.le, L.LE, 12.0), (operator.lt, L.LT, 9.5), (operator.ge, L.GE, 30.0),
+                            (operator.gt, L.GT, 25.0), (operator.eq, L.EQ, 10.0), (operator.le, L.LE, 0.01)):
+        e = 1 / (1 + eps) if sim else eps
+        r = minkowski_s_range(tab.K * 31 * 31, comp, e, sim)
+        assert r is not None
+        ref = eng.tile_threshold(tile, code, e, swap=sim, guard=2 if sim else 1)
+        if r[0] > r[1]:
+            assert int(ref[0][-1]) == 0
+            continue
+        got = eng.minkowski2_gemm_eps(tab, tab, r[0], r[1], 0, similarity=sim)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(np_(a).view(np.uint16) if a.dtype == torch.float16 else np_(a),
+                                          np_(b).view(np.uint16) if b.dtype == torch.float16 else np_(b))
+    assert minkowski_s_range(1000, operator.ne, 3.0, False) is None
