@@ -75,6 +75,12 @@ size_t  pg_packed_bytes(int64_t N, int L, int planes);
 int pg_pack_tokens(const void* tokens, int dtype, int64_t N, int L, int64_t ld,
                    uint32_t* packed, int planes, int words, int* flag, void* stream);
 
+/* fused tokeniser + pack (prograph.py:454-474 then :726): chars is the (N, L) matrix of residue
+ * letters (numpy 'S1' view, zero bytes pad shorter strings), lut256_host maps a byte to its token
+ * (letter i of the alphabet -> i+1, everything else -> 0) */
+int pg_pack_chars(const uint8_t* chars, int64_t N, int L, int64_t ld, const uint8_t* lut256_host,
+                  uint32_t* packed, int planes, int words, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Fused Hamming sweeps: "own" rows live in registers, the "stream" table is swept
  * through shared memory; the (own x stream) distance matrix never reaches HBM.

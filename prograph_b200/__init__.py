@@ -14,7 +14,8 @@ from .distance import hamming, minkowski, clean_input  # noqa: E402
 from .protein import Protein  # noqa: E402
 from .prograph import Prograph  # noqa: E402
 from .graph import build_neighbours, NeighbourTable, KnnTable  # noqa: E402
+from .io import save  # noqa: E402
 
 __all__ = ["Prograph", "Protein", "hamming", "minkowski", "clean_input", "build_neighbours",
-           "NeighbourTable", "KnnTable"]
+           "NeighbourTable", "KnnTable", "save"]
 __version__ = "0.1.0"

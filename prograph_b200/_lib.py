@@ -37,6 +37,7 @@ SIGNATURES = {
     "pg_packed_rows": (_i64, [_i64]),
     "pg_packed_bytes": (_sz, [_i64, _i, _i]),
     "pg_pack_tokens": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i, _i, _vp, _vp]),
+    "pg_pack_chars": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp]),
     "pg_sweep_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),
     "pg_eps_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "pg_hamming_knn": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

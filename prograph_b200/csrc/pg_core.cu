@@ -95,6 +95,34 @@ __global__ void pack_kernel(const T* __restrict__ tokens, long long N, int L, lo
   }
 }
 
+// ---- fused tokeniser + pack: raw residue letters -> bit planes ------------------------------
+// Replaces tokenize (prograph.py:454-474: twenty np.where passes producing an (N, L) int64
+// array) followed by the fp16 staging: one pass over the sequence bytes through a 256-entry
+// letter -> token table, ballots build the plane words.  Byte 0 (numpy's pad of shorter
+// strings) and letters outside the alphabet map to token 0, as in the reference.
+struct CharLut { uint8_t t[256]; };
+
+__global__ void pack_chars_kernel(const uint8_t* __restrict__ chars, long long N, int L, long long ld, CharLut lut,
+                                  uint32_t* __restrict__ packed, long long rows_padded, int planes, int words) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long row = warp0; row < rows_padded; row += nwarps) {
+    uint32_t* dst = packed + static_cast<size_t>(row) * planes * words;
+    for (int w = 0; w < words; ++w) {
+      const int l = w * 32 + lane;
+      unsigned tok = 0;
+      if (row < N && l < L) tok = lut.t[chars[static_cast<size_t>(row) * ld + l]];
+      uint32_t mine = 0;
+      for (int p = 0; p < planes; ++p) {
+        const uint32_t word = __ballot_sync(0xffffffffu, (tok >> p) & 1u);
+        if (lane == p) mine = word;
+      }
+      if (lane < planes) dst[lane * words + w] = mine;
+    }
+  }
+}
+
 // ---- integer pipe peak probe ------------------------------------------------------------
 // Register-only loops with the instruction mix of the Hamming inner loop; the achieved
 // lane-op rate is the "speed of light" the sweep kernel's roofline fraction is quoted on.
@@ -215,6 +243,27 @@ int pg_pack_tokens(const void* tokens, int dtype, int64_t N, int L, int64_t ld, 
     default: set_error("unsupported token dtype %d", dtype); return PG_ERR_INVALID;
   }
 #undef PG_PACK
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_pack_chars(const uint8_t* chars, int64_t N, int L, int64_t ld, const uint8_t* lut256_host, uint32_t* packed,
+                  int planes, int words, void* stream) {
+  PG_CHECK_ARG(chars && lut256_host && packed, "null pointer");
+  PG_CHECK_ARG(N > 0 && L > 0 && ld >= L, "bad shape N=%lld L=%d ld=%lld", (long long)N, L, (long long)ld);
+  PG_CHECK_ARG(planes >= 1 && planes <= 8 && words * 32 >= L, "bad planes / words");
+  CharLut lut;
+  for (int i = 0; i < 256; ++i) {
+    PG_CHECK_ARG(lut256_host[i] < (1u << planes), "token %d of letter %d does not fit %d planes", lut256_host[i], i, planes);
+    lut.t[i] = lut256_host[i];
+  }
+  const long long rows_padded = pg_packed_rows(N);
+  const int threads = 256;
+  long long blocks = ceil_div(rows_padded * 32, threads);
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  pack_chars_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      chars, N, L, ld, lut, packed, rows_padded, planes, words);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -109,6 +109,21 @@ class CudaEngine:
                 return PackedTable(out, N, L_, pl, words)
         raise OverflowError("values are not integer tokens in [0, 256): the bit-plane path does not apply")
 
+    def pack_chars(self, chars, lut256, planes=5):
+        """Residue letters straight to bit planes: `chars` is the (N, L) uint8 matrix of sequence
+        bytes (zero padded), `lut256` the byte -> token table (tokenize + pack in one pass)."""
+        c = self.to_device(chars)
+        if c.dtype != torch.uint8 or c.dim() != 2 or c.shape[0] == 0 or c.shape[1] == 0:
+            raise ValueError("pack_chars expects a non-empty (N, L) uint8 matrix")
+        lut = np.ascontiguousarray(lut256, dtype=np.uint8)
+        assert lut.shape == (256,)
+        N, L_ = int(c.shape[0]), int(c.shape[1])
+        words = self.packed_words(L_)
+        out = self.empty((int(self.lib.pg_packed_rows(N)), planes, words), torch.int32)
+        L.check(self.lib.pg_pack_chars(_ptr(c), N, L_, int(c.stride(0)), lut.ctypes.data_as(C.c_void_p), _ptr(out),
+                                       int(planes), words, self._stream()))
+        return PackedTable(out, N, L_, planes, words)
+
     # ---- fused Hamming sweeps -----------------------------------------------------------
     def _workspace(self, rows, stream_rows, words, k1):
         nbytes = int(self.lib.pg_sweep_workspace_bytes(int(rows), int(stream_rows), int(words), int(k1)))

@@ -330,7 +330,7 @@ def _tile_eps(eng, tiles, eps, comp, similarity):
 # public entry
 # ---------------------------------------------------------------------------------
 def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, comp=operator.le,
-                     batch_size=8, idxs=None, engine=None, group=None):
+                     batch_size=8, idxs=None, engine=None, group=None, packed=None):
     """Device implementation of ``Prograph.build_graph`` (prograph.py:656-765) on a
     representation matrix.  Returns a NeighbourTable (epsilon) or KnnTable (k)."""
     validate(eps, k)
@@ -347,14 +347,15 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     rank, world = _shard.rank_world(group)
     row0, rows = _shard.row_range(n, rank, world)
 
-    packed = None
-    if kind == "hamming":
+    if packed is not None and (kind != "hamming" or idxs is not None or packed.rows != n):
+        packed = None
+    if kind == "hamming" and packed is None:
         try:
             packed = pack_table(eng, X, rank, world, group)
-            if packed.words > 56 or (packed.words > 8 and packed.planes != 5):
-                packed = None
         except OverflowError:
             packed = None
+    if packed is not None and (packed.words > 56 or (packed.words > 8 and packed.planes != 5)):
+        packed = None          # wider than the fused sweeps: element-wise tiles below
 
     if packed is not None:
         if eps:

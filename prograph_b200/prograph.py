@@ -88,6 +88,10 @@ class Prograph:
         if "Neighbours" not in self.graph:
             self.graph["Neighbours"] = self.build_graph(eps=1)             # prograph.py:140-141
 
+        if file.split(".")[-1] == "pkl":
+            from .io import attach_sidecar
+            attach_sidecar(self, file)
+
         self.learners = {}
         print(self)
 
@@ -172,23 +176,33 @@ class Prograph:
             return np.array([self.tokens[aa.encode("utf-8")] for aa in seq])
         return "This feature is not ready yet"
 
+    def _letter_table(self):
+        table = np.zeros(256, dtype=np.uint8)
+        for ch, tok in self.tokens.items():
+            table[ch[0]] = tok
+        return table
+
+    @staticmethod
+    def _letter_codes(sequences):
+        """(N, L) uint8 matrix of the sequences' bytes, zero padded to the longest one."""
+        chars = np.array(sequences, dtype="bytes").reshape(-1, 1).view("S1")
+        return chars.view(np.uint8).reshape(chars.shape) if chars.size else np.zeros(chars.shape, np.uint8)
+
     def tokenize(self, sequences):
         """Letters -> 1..len(alphabet) through a 256-entry byte table; shorter sequences are
         right-padded with 0 (prograph.py:454-474 semantics, one pass instead of 20)."""
-        chars = np.array(sequences, dtype="bytes").reshape(-1, 1).view("S1")
-        table = np.zeros(256, dtype=np.int64)
-        for ch, tok in self.tokens.items():
-            table[ch[0]] = tok
-        codes = chars.view(np.uint8).reshape(chars.shape) if chars.size else np.zeros(chars.shape, np.uint8)
-        return table[codes]
+        return self._letter_table().astype(np.int64)[self._letter_codes(sequences)]
 
     def embedding(self, embedded, name):
         self.graph[f"{name}_embedded"] = embedded
 
     def _device_tokens(self):
+        """Bit planes of the dataset on the device, packed straight from the sequence letters
+        (tokenise + pack fused, pg_pack_chars) -- one byte per residue crosses PCIe."""
         if self._packed is None or self._packed.rows != len(self.tokenized):
-            self._packed = get_engine().pack(self.tokenized.astype(np.uint8)
-                                             if self.tokenized.max(initial=0) < 256 else self.tokenized)
+            planes = 5 if len(self.amino_acids) < 32 else 8
+            self._packed = get_engine().pack_chars(self._letter_codes(self.graph[self.seqs_col]),
+                                                   self._letter_table(), planes=planes)
         return self._packed
 
     def _mutant_bits(self, row):
@@ -384,8 +398,11 @@ class Prograph:
             rep = self.tokenized
         else:
             rep = self(representation)
+        packed = None
+        if representation == "Tokenized" and idxs is None and distance is hamming and rep is self.tokenized:
+            packed = self._device_tokens()       # already on the device, packed from the letters
         table = _graph.build_neighbours(rep, eps=eps, k=k, similarity=similarity, distance=distance, comp=comp,
-                                        batch_size=batch_size, idxs=idxs)
+                                        batch_size=batch_size, idxs=idxs, packed=packed)
         lists = table.as_list()
         self._remember(table if isinstance(table, _graph.NeighbourTable) else table.to_csr(), lists)
         return lists

@@ -505,3 +505,37 @@ def test_large_knn_sampled_rows(eng):
     assert np.all(np.diff(w, axis=1) >= 0)                       # weights ascending per row
     pick = rng.choice(n, size=5000, replace=False)
     assert np.all((X[pick] != X[idx[pick, 0]]).sum(1) == w[pick, 0])
+
+
+# ------------------------------------------------------------------ next rows: fused tokeniser, sidecar
+def test_pack_chars_matches_tokenise_then_pack(eng, pg_lib, g_library):
+    seqs = list(g_library["sequences"])                       # ragged lengths: zero padded
+    codes = pg_lib._letter_codes(seqs)
+    a = eng.pack_chars(codes, pg_lib._letter_table(), planes=5)
+    b = eng.pack(g_library["tokenized"], planes=5)
+    assert (a.rows, a.L, a.words) == (b.rows, b.L, b.words)
+    assert torch.equal(a.data, b.data)
+    # letters outside the alphabet and pad bytes are token 0, like the reference tokeniser
+    odd = pg_lib._letter_codes(["AXZ", "C"])
+    t = eng.pack_chars(odd, pg_lib._letter_table(), planes=5)
+    ref = eng.pack(np.array([[1, 0, 0], [2, 0, 0]]), planes=5)
+    assert torch.equal(t.data, ref.data)
+
+
+def test_save_reload_with_csr_sidecar(pgb, pg_synth, tmp_path):
+    assert pgb.save(pg_synth, name="synth", directory=str(tmp_path) + "/")
+    assert (tmp_path / "synth.pkl").exists() and (tmp_path / "synth.graph.npz").exists()
+    again = pgb.Prograph(file=str(tmp_path / "synth.pkl"))
+    assert again[0]["Sequence"] == "AAA"                                          # tests.py:121
+    t = again._table_for("Neighbours")
+    z = np.load(tmp_path / "synth.graph.npz")
+    np.testing.assert_array_equal(t.idx, z["idx"])
+    np.testing.assert_array_equal(again.degree(), pg_synth.degree())
+    A, B = again.adjacency(), pg_synth.adjacency()
+    np.testing.assert_array_equal(A.row, B.row)
+    np.testing.assert_array_equal(A.col, B.col)
+    np.testing.assert_array_equal(A.data, B.data)
+    # a pickle without a sidecar still loads (lists are flattened on demand)
+    (tmp_path / "synth.graph.npz").unlink()
+    plain = pgb.Prograph(file=str(tmp_path / "synth.pkl"))
+    np.testing.assert_array_equal(plain.degree(), pg_synth.degree())
