@@ -539,3 +539,29 @@ def test_save_reload_with_csr_sidecar(pgb, pg_synth, tmp_path):
     (tmp_path / "synth.graph.npz").unlink()
     plain = pgb.Prograph(file=str(tmp_path / "synth.pkl"))
     np.testing.assert_array_equal(plain.degree(), pg_synth.degree())
+
+
+def test_headline_config_one_million_uniform(eng):
+    """The bench workload itself (C4-U: 1 M x 256 iid-uniform tokens, k=16, all 10^12 pairs):
+    sampled rows bit for bit against the oracle, plus size-independent properties."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import make_tokens
+    n, L, k = 1_000_000, 256, 16
+    X = make_tokens(n, L, "uniform")
+    tab = eng.pack(X)
+    idx, w = eng.hamming_knn(tab, 0, n, tab, k, drop=1)
+    idx, w = np_(idx), np_(w)
+    rng = np.random.default_rng(123)
+    sample = np.concatenate([[0, n - 1], rng.choice(n, size=22, replace=False)])
+    D = O.hamming(X, X[sample], chunk=8)
+    ri, rw = O.knn_from_distances(D, k)
+    np.testing.assert_array_equal(idx[sample], ri)
+    np.testing.assert_array_equal(w[sample], rw)
+    assert idx.min() >= 0 and idx.max() < n
+    assert np.all(np.diff(w, axis=1) >= 0)
+    ties = np.diff(w, axis=1) == 0
+    assert np.all(np.diff(idx, axis=1)[ties] > 0)                 # equal distances: ascending index
+    pick = rng.choice(n, size=4000, replace=False)
+    for j in (0, k - 1):
+        assert np.all((X[pick] != X[idx[pick, j]]).sum(1) == w[pick, j])

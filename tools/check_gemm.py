@@ -14,18 +14,20 @@ def main():
     from bench import make_tokens
     eng = get_engine()
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+    k = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    drop = 1 if k > 1 else 0
     X = make_tokens(n, 256, "uniform")
     tab = eng.gemm_pack(X, max_token=31)
     for kind in (0, 1):
-        eng.minkowski2_gemm_knn(tab, tab, 16, 1, kind)
+        eng.minkowski2_gemm_knn(tab, tab, k, drop, kind)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.minkowski2_gemm_knn(tab, tab, 16, 1, kind)
+        eng.minkowski2_gemm_knn(tab, tab, k, drop, kind)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
-        print(f"minkowski2 gemm kNN k=16 kind={kind} N={n}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  "
+        print(f"minkowski2 gemm kNN k={k} kind={kind} N={n}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  "
               f"{2.0 * 256 * n * n / ms / 1e9:.1f} int8 TOPS", flush=True)
     q = eng.gemm_pack(X[:4096], max_token=31)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
