@@ -107,6 +107,34 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
                    int64_t* out_idx, void* out_w,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Symmetric kNN of a table against itself (the case build_graph runs, prograph.py:755-765):
+ * d(i,j) == d(j,i), so every unordered pair is evaluated once and offered to the lists of both
+ * rows -- half of the reference's N x N evaluations.  This rank handles row blocks (256 rows)
+ * rb_first, rb_first + rb_stride, ... (rb_first = rank, rb_stride = world size; 0, 1 for one
+ * GPU) and leaves in lists[r*k1 .. r*k1+k1) the k1 smallest keys  distance<<32 | index  it saw
+ * for row r, ascending, ~0 = empty.  With several ranks the per-rank lists are all-gathered and
+ * merged by pg_knn_lists_finalize.  k1 <= 32; wider lists take pg_hamming_knn.
+ *
+ * Bootstrap (boot_rows > 0, a multiple of 512): the caller first runs pg_hamming_knn_boot, which
+ * sweeps rows [row0,row0+rows) one-sided against table rows [0,boot_rows) and writes their
+ * lists; `lists` of ALL rows (all-gathered when the bootstrap was sharded) then enter
+ * pg_hamming_knn_sym as the starting lists.  Every row's filter is tight from the first tile on,
+ * which keeps the locked list updates rare.  */
+size_t pg_knn_sym_workspace_bytes(int64_t rows, int words);
+int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0, int64_t rows,
+                        int64_t boot_rows, int planes, int words, int k1, uint64_t* lists,
+                        void* workspace /* pg_sweep_workspace_bytes(rows, boot_rows, words, k1) */,
+                        size_t workspace_bytes, void* stream);
+int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1,
+                       int rb_first, int rb_stride, int64_t boot_rows, uint64_t* lists,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* merge n_lists key lists per row (list s of row r at lists[s*list_stride + r*k1]), drop the first
+ * `drop` merged positions and write the next k as out_idx[(r-row0)*k + j] / out_w per `weight`
+ * for rows [row0, row0+rows); missing entries get idx = -1 (as pg_hamming_knn).  */
+int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride,
+                          int64_t row0, int64_t rows, int k1, int k, int drop, int weight,
+                          int64_t* out_idx, void* out_w, void* stream);
+
 /* epsilon graph, pass 1 (prograph.py:731-736): per own row, the number of stream rows
  * whose distance d has bit d set in `lut` (a host array of (L+32)/32 words: the
  * truth table of  comp(d, eps) & (d > 0)  -- or any other predicate of d -- evaluated

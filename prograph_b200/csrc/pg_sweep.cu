@@ -11,7 +11,10 @@
 #include <cstdlib>
 #include <cmath>
 
+#include <algorithm>
+
 #include "pg_sweep.cuh"
+#include "pg_sweep_sym.cuh"
 
 namespace pg {
 
@@ -239,6 +242,166 @@ constexpr size_t kEpsCaptureLimit = 8ull << 30;   // do not spend more than 8 Gi
 static size_t eps_flag_bytes(long long rows) { return static_cast<size_t>(round_up(rows, 256)); }
 static size_t eps_list_bytes(long long rows) { return static_cast<size_t>(rows) * 8; }
 
+
+// ---- symmetric kNN sweep (pg_sweep_sym.cuh): host side ---------------------------------
+static int dispatch_sym(int planes, int words, const SymParams& prm, const SymLaunch& l, int* resident) {
+#define PG_CASE(P, W) \
+  if (planes == P && words == W) return sweep_sym_p##P##_w##W(prm, l, resident);
+  PG_CASE(5, 1) PG_CASE(5, 2) PG_CASE(5, 4) PG_CASE(5, 8) PG_CASE(5, 16)
+  PG_CASE(8, 1) PG_CASE(8, 2) PG_CASE(8, 4) PG_CASE(8, 8)
+#undef PG_CASE
+  set_error("symmetric sweep supports planes in {5,8} x words in {1,2,4,8} and planes=5, words=16; got planes=%d "
+            "words=%d", planes, words);
+  return PG_ERR_UNSUPPORTED;
+}
+
+static bool sym_shape_ok(int planes, int words) {
+  return ((planes == 5 || planes == 8) && (words == 1 || words == 2 || words == 4 || words == 8)) ||
+         (planes == 5 && words == 16);
+}
+
+// workspace: [filter words: tiles*tile_cols u64][locks: rows u32][stats][items]
+struct SymLayout {
+  int tile_cols, n_tiles, n_blocks;
+  size_t gnt_bytes, lock_bytes, stats_off, item_off, item_bytes_max, total;
+};
+
+static SymLayout sym_layout(long long rows, int words) {
+  SymLayout s;
+  s.tile_cols = tile_cols_for(words);
+  s.n_tiles = static_cast<int>(ceil_div(rows, s.tile_cols));
+  s.n_blocks = static_cast<int>(ceil_div(rows, kConsumers));
+  s.gnt_bytes = static_cast<size_t>(round_up(static_cast<int64_t>(s.n_tiles) * s.tile_cols * 8, 256));
+  s.lock_bytes = static_cast<size_t>(round_up(rows * 4, 256));
+  s.stats_off = s.gnt_bytes + s.lock_bytes;
+  s.item_off = s.stats_off + 256;
+  // every row block contributes at most ceil(len / chunk) <= len / chunk + 1 items and the planner
+  // keeps sum(len) / chunk below 64 items per resident CTA (<= 4 CTAs per SM)
+  s.item_bytes_max = (2 * static_cast<size_t>(s.n_blocks) + 64ull * 4 * 160 + 1024) * sizeof(SymItem);
+  s.total = s.item_off + s.item_bytes_max;
+  return s;
+}
+
+// Chunks of (row block, tile range), longest first, dealt to the persistent grid in snake
+// order so that every CTA gets the same number of tiles to within one short chunk.  Chunk
+// boundaries are shifted from row block to row block so that CTAs that start together do not
+// walk the same stream rows in lockstep (they would fight for the same row locks).
+static std::vector<SymItem> sym_plan(const SymLayout& s, int rb_first, int rb_stride, int grid, long long boot_rows) {
+  const int boot_blocks = static_cast<int>(boot_rows / kConsumers);
+  auto first_tile = [&](int rb) {
+    const long long row = rb < boot_blocks ? boot_rows : static_cast<long long>(rb) * kConsumers;
+    return static_cast<int>(row / s.tile_cols);
+  };
+  long long total = 0;
+  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride) total += std::max(0, s.n_tiles - first_tile(rb));
+  long long chunk = ceil_div(total, static_cast<long long>(grid) * 24);
+  if (const char* ev = std::getenv("PG_SYM_CHUNK")) chunk = std::atoll(ev);
+  if (chunk < 32) chunk = 32;
+  std::vector<SymItem> items;
+  unsigned n_seen = 0;
+  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride, ++n_seen) {
+    const int tb = first_tile(rb);
+    const int len = s.n_tiles - tb;
+    if (len <= 0) continue;
+    const int boot = rb < boot_blocks ? 1 : 0;
+    // golden-ratio phase of the first boundary, in (chunk/4, 5*chunk/4]
+    const double frac = (n_seen * 0.6180339887498949) - static_cast<long long>(n_seen * 0.6180339887498949);
+    int t = tb;
+    int first = static_cast<int>(chunk / 4 + static_cast<long long>(frac * static_cast<double>(chunk))) + 1;
+    while (t < s.n_tiles) {
+      int t1 = t + (t == tb ? first : static_cast<int>(chunk));
+      if (s.n_tiles - t1 < chunk / 4) t1 = s.n_tiles;     // no crumbs at the end
+      if (t1 > s.n_tiles) t1 = s.n_tiles;
+      items.push_back(SymItem{rb, t, t1, boot});
+      t = t1;
+    }
+  }
+  std::stable_sort(items.begin(), items.end(),
+                   [](const SymItem& a, const SymItem& b) { return a.t1 - a.t0 > b.t1 - b.t0; });
+  const size_t n = items.size();
+  std::vector<SymItem> dealt(n);
+  for (size_t base = 0, round = 0; base < n; base += grid, ++round) {
+    const size_t in_round = std::min<size_t>(grid, n - base);
+    for (size_t b = 0; b < in_round; ++b) dealt[base + b] = items[base + ((round & 1) ? in_round - 1 - b : b)];
+  }
+  return dealt;
+}
+
+__global__ void sym_init_kernel(unsigned long long* glist, long long n_keys, unsigned long long* glast, long long n_gnt, unsigned* glock,
+                                long long rows, unsigned long long* stats, int k1, int seeded) {
+  if (blockIdx.x == 0 && threadIdx.x < 8) stats[threadIdx.x] = 0ull;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (!seeded)
+    for (long long j = i; j < n_keys; j += stride) glist[j] = ~0ull;
+  for (long long j = i; j < n_gnt; j += stride) {
+    unsigned long long last = ~0ull;
+    if (seeded && j < rows) last = glist[j * k1 + (k1 - 1)];
+    glast[j] = sym_filter_word(last);
+  }
+  for (long long j = i; j < rows; j += stride) glock[j] = 0u;
+}
+
+// bootstrap: merged split lists [n_splits][k1][rows] -> row-major key lists [rows][k1]
+__global__ void knn_part_to_lists_kernel(const unsigned long long* __restrict__ part, int n_splits, int k1,
+                                         long long rows, unsigned long long* __restrict__ lists) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  unsigned long long last = 0;
+  for (int j = 0; j < k1; ++j) {
+    unsigned long long best = ~0ull;
+    for (int s = 0; s < n_splits; ++s) {
+      const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
+      for (int i = 0; i < k1; ++i) {
+        const unsigned long long v = lst[static_cast<size_t>(i) * rows];
+        if (j > 0 && v <= last) continue;
+        if (v < best) best = v;
+        break;
+      }
+    }
+    last = best;
+    lists[r * k1 + j] = best;
+    if (best == ~0ull) {
+      for (int jj = j + 1; jj < k1; ++jj) lists[r * k1 + jj] = ~0ull;
+      break;
+    }
+  }
+}
+
+// Final lists: merge n_lists sorted key lists per row (one per rank), drop, widen.
+__global__ void knn_lists_finalize_kernel(const unsigned long long* __restrict__ lists, int n_lists,
+                                          long long list_stride, long long row0, long long rows, int k1, int k,
+                                          int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  unsigned long long last = 0;
+  bool have_last = false;
+  for (int j = 0; j < drop + k; ++j) {
+    unsigned long long best = ~0ull;
+    for (int s = 0; s < n_lists; ++s) {
+      const unsigned long long* lst = lists + static_cast<size_t>(s) * list_stride + static_cast<size_t>(row0 + r) * k1;
+      for (int i = 0; i < k1; ++i) {
+        const unsigned long long v = lst[i];
+        if (have_last && v <= last) continue;
+        if (v < best) best = v;
+        break;
+      }
+    }
+    last = best;
+    have_last = true;
+    if (j >= drop) {
+      const long long at = r * k + (j - drop);
+      if (best == ~0ull) {
+        out_idx[at] = -1;
+        write_weight(out_w, at, 0, weight);
+      } else {
+        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
+        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
+      }
+    }
+  }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -424,6 +587,118 @@ int pg_hamming_tile(const uint32_t* data, int64_t data_rows, const uint32_t* que
   SweepTimer t(l.stream);
   return dispatch(planes, words, prm, l);
 }
+
+size_t pg_knn_sym_workspace_bytes(int64_t rows, int words) {
+  if (rows <= 0 || words <= 0) return 0;
+  return sym_layout(rows, words).total;
+}
+
+int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0, int64_t rows, int64_t boot_rows,
+                        int planes, int words, int k1, uint64_t* lists, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int rc = check_common(table, table_rows, row0, rows, table, boot_rows, planes, words);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(boot_rows <= table_rows, "bootstrap rows exceed the table");
+  PG_CHECK_ARG(lists && workspace, "null output/workspace pointer");
+  if (!sym_shape_ok(planes, words) || k1 < 1 || k1 > 32) {
+    set_error("symmetric sweep: planes/words %d/%d or list length %d not covered", planes, words, k1);
+    return PG_ERR_UNSUPPORTED;
+  }
+  const Geometry g = make_geometry(rows, boot_rows, words, kConsumers, k1);
+  const size_t need = static_cast<size_t>(g.n_splits) * k1 * rows * 8;
+  PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  SweepParams prm;
+  fill_common(prm, g, table, row0, rows, table, boot_rows);
+  prm.part = static_cast<unsigned long long*>(workspace);
+  prm.k1 = k1;
+  SweepLaunch l{MODE_KNN, 0, PG_W_I64, 0, static_cast<size_t>(k1) * kConsumers * 8, static_cast<cudaStream_t>(stream)};
+  {
+    SweepTimer t(l.stream);
+    rc = dispatch(planes, words, prm, l);
+  }
+  if (rc != PG_OK) return rc;
+  const int threads = 128;
+  knn_part_to_lists_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
+      prm.part, g.n_splits, k1, rows, reinterpret_cast<unsigned long long*>(lists));
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1, int rb_first,
+                       int rb_stride, int64_t boot_rows, uint64_t* lists, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  PG_CHECK_ARG(table && lists && workspace, "null pointer");
+  PG_CHECK_ARG(rows > 0 && rows < (1ll << 31), "row count out of range");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "table must be 16-byte aligned");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  PG_CHECK_ARG(rb_stride >= 1 && rb_first >= 0 && rb_first < rb_stride, "bad row-block interleave %d/%d", rb_first,
+               rb_stride);
+  PG_CHECK_ARG(boot_rows >= 0 && boot_rows % kStreamRowPad == 0 && boot_rows <= rows,
+               "bootstrap rows must be a multiple of %d within the table", kStreamRowPad);
+  if (!sym_shape_ok(planes, words) || k1 < 1 || k1 > 32) {
+    set_error("symmetric sweep: planes/words %d/%d or list length %d not covered", planes, words, k1);
+    return PG_ERR_UNSUPPORTED;
+  }
+  const SymLayout lay = sym_layout(rows, words);
+  PG_CHECK_ARG(workspace_bytes >= lay.total, "workspace too small: %zu < %zu", workspace_bytes, lay.total);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  SymParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.tab = table;
+  prm.rows = rows;
+  prm.one = 1u;
+  prm.k1 = k1;
+  prm.boot_rows = boot_rows;
+  prm.glist = reinterpret_cast<unsigned long long*>(lists);
+  prm.glast = reinterpret_cast<unsigned long long*>(wsb);
+  prm.glock = reinterpret_cast<unsigned*>(wsb + lay.gnt_bytes);
+  prm.items = reinterpret_cast<const SymItem*>(wsb + lay.item_off);
+  prm.stats = reinterpret_cast<unsigned long long*>(wsb + lay.stats_off);
+  if (const char* ev = std::getenv("PG_SYM_NOCOL")) prm.no_col = std::atoi(ev);
+  SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs};
+  int resident = 0;
+  int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
+  if (rc != PG_OK) return rc;
+  const std::vector<SymItem> items = sym_plan(lay, rb_first, rb_stride, resident, boot_rows);
+  sym_init_kernel<<<num_sms() * 4, 256, 0, cs>>>(prm.glist, static_cast<long long>(rows) * k1, prm.glast,
+                                                 static_cast<long long>(lay.n_tiles) * lay.tile_cols, prm.glock, rows,
+                                                 prm.stats, k1, boot_rows > 0 ? 1 : 0);
+  PG_LAUNCH_CHECK();
+  if (items.empty()) return PG_OK;
+  PG_CHECK_ARG(items.size() * sizeof(SymItem) <= lay.item_bytes_max, "item table overflow (%zu items)", items.size());
+  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off, items.data(), items.size() * sizeof(SymItem), cudaMemcpyHostToDevice, cs));
+  prm.n_items = static_cast<int>(items.size());
+  l.grid = static_cast<int>(std::min<size_t>(items.size(), static_cast<size_t>(resident)));
+  {
+    SweepTimer t(cs);
+    rc = dispatch_sym(planes, words, prm, l, nullptr);
+  }
+  if (rc == PG_OK && std::getenv("PG_SYM_STATS")) {
+    unsigned long long st[8];
+    PG_CUDA(cudaMemcpyAsync(st, prm.stats, sizeof(st), cudaMemcpyDeviceToHost, cs));
+    PG_CUDA(cudaStreamSynchronize(cs));
+    fprintf(stderr, "[pg sym] rows=%lld boot=%lld items=%zu grid=%d | column calls %llu, locks %llu, lock spins %llu, "
+            "list writes %llu | row inserts %llu\n", static_cast<long long>(rows), static_cast<long long>(boot_rows),
+            items.size(), l.grid, st[0], st[1], st[2], st[3], st[4]);
+  }
+  return rc;
+}
+
+int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1,
+                          int k, int drop, int weight, int64_t* out_idx, void* out_w, void* stream) {
+  PG_CHECK_ARG(lists && out_idx && out_w, "null pointer");
+  PG_CHECK_ARG(n_lists >= 1 && rows > 0 && row0 >= 0 && k >= 1 && drop >= 0 && k1 >= 1, "bad list geometry");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
+  const int threads = 128;
+  knn_lists_finalize_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0,
+                              static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(lists), n_lists, list_stride, row0, rows, k1, k, drop, weight,
+      reinterpret_cast<long long*>(out_idx), out_w);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
 
 int pg_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream) {
   PG_CHECK_ARG(in && out && n >= 0, "bad scan arguments");

@@ -1,0 +1,359 @@
+// Symmetric fused Hamming kNN sweep for sm_100a: every unordered pair {i, j} of one table is
+// evaluated once and feeds the neighbour lists of BOTH rows.
+//
+// Replaces the same reference code as pg_sweep.cuh (hamming.py:34 + sort/slice of
+// prograph.py:757-762) for the case build_graph actually runs -- a table against itself --
+// where d(i,j) == d(j,i) makes half of the reference's N x N evaluations redundant.
+//
+// Mapping.  Row block rb (256 rows, one per thread, plane words in registers) sweeps the
+// stream tiles from its own diagonal to the end of the table:
+//   * stream rows of blocks  < rb : skipped (block pair handled by the lower block);
+//   * stream rows of block  == rb : "row side" only -- both (i,j) and (j,i) are seen here;
+//   * stream rows of blocks  > rb : row side for i (key (d,j) into the thread's list in shared
+//     memory) AND column side for j (key (d,i) into row j's list in global memory).
+// Every row has ONE global list of k1 sorted keys d<<32|index behind a per-row spin lock, plus a
+// 64-bit filter word glast[j] = (~distance)<<32 | index of its k1-th key that travels to shared
+// memory with the stream tile (a second bulk copy on the same mbarrier).  The hot loop tests four stream
+// rows at a time against both thresholds with eight IMADs (FMA pipe) and four LOP3s, one vote;
+// everything behind the vote is rare and out of line.  A stale filter word is only ever larger
+// than the current one, so no candidate is lost; the locked insertion compares full keys, so the
+// result is the k1 smallest (distance, index) keys whatever the arrival order.
+// Work items are (row block, tile range) chunks from a host-built table; a chunk starts its
+// shared-memory lists empty but seeds its filter from the row's global list, and merges its lists
+// into the global ones when it ends, so chunks can be short (good load balance) without the
+// cold-start insertion storm of the split lists in pg_sweep.cuh.
+#pragma once
+#include "pg_sweep.cuh"
+
+namespace pg {
+
+constexpr int kTauInf = 0x3fffffff;   // filter value of a list that is not full yet
+
+struct SymItem { int rb, t0, t1, boot; };   // row block, stream tiles [t0, t1); boot: block of the bootstrap rows
+
+struct SymParams {
+  const uint32_t* tab;        // packed table, own == stream
+  long long rows;             // valid rows
+  const SymItem* items;
+  int n_items;
+  unsigned one;               // opaque 1 (see SweepParams::one)
+  int k1;                     // list length, <= 32
+  unsigned long long* glist;  // [rows][k1] ascending keys, ~0 = empty
+  unsigned long long* glast;  // [n_tiles * tile_cols] filter word per row: (~tau)<<32 | index of the last key
+  unsigned* glock;            // [rows]
+  unsigned long long* stats;  // [8] slow-path counters: column calls, locks, lock spins, list writes, row calls
+  int no_col;                 // experiments: skip the column side (results are then incomplete)
+  long long boot_rows;        // rows [0, boot_rows) were swept one-sided against every row beforehand
+};
+
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_cg_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// filter word of a list whose last key is `last` (~0 = list not full)
+__host__ __device__ __forceinline__ unsigned long long sym_filter_word(unsigned long long last) {
+  const unsigned tau = (last == ~0ull) ? static_cast<unsigned>(kTauInf) : static_cast<unsigned>(last >> 32);
+  return (static_cast<unsigned long long>(~tau) << 32) | (last & 0xffffffffull);
+}
+__device__ __forceinline__ int mad_s32(int a, unsigned b, int c) {
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// Warp-cooperative merge of up to 32 candidate keys (one per lane, `is_cand`) into the global
+// list of row j.  All lanes call it with the same j.  Lock-free early out against the list's
+// current last key; otherwise the list is edited in registers under the row's lock.
+static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long long j, unsigned long long key, bool is_cand,
+                                           int lane) {
+  const int k1 = prm.k1;
+  unsigned long long* lst = prm.glist + static_cast<size_t>(j) * k1;
+  const unsigned long long last0 = ld_cg_u64(lst + (k1 - 1));
+  unsigned cand = __ballot_sync(0xffffffffu, is_cand && key < last0);
+  if (lane == 0) atomicAdd(prm.stats + 0, 1ull);
+  if (cand == 0u) return;
+  unsigned* lock = prm.glock + j;
+  if (lane == 0) {
+    unsigned spins = 0;
+    while (atomicCAS(lock, 0u, 1u) != 0u) {
+      __nanosleep(100);
+      if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
+    }
+    __threadfence();
+    atomicAdd(prm.stats + 1, 1ull);
+    if (spins) atomicAdd(prm.stats + 2, static_cast<unsigned long long>(spins));
+  }
+  __syncwarp();
+  unsigned long long e = lane < k1 ? ld_cg_u64(lst + lane) : ~0ull;
+  bool changed = false;
+  while (cand) {
+    const int src = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const unsigned long long kk = __shfl_sync(0xffffffffu, key, src);
+    const int pos = __popc(__ballot_sync(0xffffffffu, lane < k1 && e < kk));
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, e, 1);
+    if (pos < k1) {
+      if (lane == pos) e = kk;
+      else if (lane > pos) e = up;
+      changed = true;
+    }
+  }
+  if (changed) {
+    if (lane < k1) st_cg_u64(lst + lane, e);
+    const unsigned long long last = __shfl_sync(0xffffffffu, e, k1 - 1);
+    if (lane == 0) {
+      st_cg_u64(prm.glast + j, sym_filter_word(last));
+      atomicAdd(prm.stats + 3, 1ull);
+    }
+    __threadfence();
+  }
+  __syncwarp();
+  if (lane == 0) atomicExch(lock, 0u);
+}
+
+// Row side: the warp inserts the candidates of one stream row (column `col`) into the
+// shared-memory lists of its own rows; returns the lane's updated filter.
+static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists, int k1, unsigned cand, unsigned dv,
+                                          unsigned col, int lane, int tau_seed, int tau,
+                                          unsigned long long* stats) {
+  if (lane == 0) atomicAdd(stats + 4, static_cast<unsigned long long>(__popc(cand)));
+  while (cand) {
+    const int src = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const unsigned dd = __shfl_sync(0xffffffffu, dv, src);
+    const unsigned long long key = (static_cast<unsigned long long>(dd) << 32) | col;
+    const unsigned t_new = knn_insert_coop(warp_lists + static_cast<size_t>(src) * k1, k1, key, lane);
+    if (lane == src) tau = min(tau_seed, t_new == 0xffffffffu ? kTauInf : static_cast<int>(t_new));
+  }
+  return tau;
+}
+
+struct SymCursor {
+  int idx, t, t1;
+  __device__ __forceinline__ void start(int i, const SymParams& prm) {
+    idx = i;
+    if (idx < prm.n_items) {
+      const int4 it = __ldg(reinterpret_cast<const int4*>(prm.items) + idx);
+      t = it.y;
+      t1 = it.z;
+    } else {
+      t = t1 = 0;
+    }
+  }
+  __device__ __forceinline__ bool valid(const SymParams& prm) const { return idx < prm.n_items; }
+  __device__ __forceinline__ void advance(const SymParams& prm, int stride) {
+    if (++t == t1) start(idx + stride, prm);
+  }
+};
+
+template <int P, int W>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __grid_constant__ SymParams prm) {
+  constexpr int BN = TileCols<W>::value;
+  constexpr int COLW = P * W;
+  constexpr uint32_t STAGE_BYTES = BN * COLW * 4;
+  constexpr uint32_t TAU_BYTES = BN * 8;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* stage_mem = reinterpret_cast<uint32_t*>(smem_raw);
+  unsigned long long* taus = reinterpret_cast<unsigned long long*>(smem_raw + kStages * STAGE_BYTES);   // [kStages][BN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * (STAGE_BYTES + TAU_BYTES));
+  unsigned* done = reinterpret_cast<unsigned*>(full + kStages);
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(full + 2 * kStages);   // [256][k1]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int k1 = prm.k1;
+  unsigned long long* warp_lists = lists + static_cast<size_t>(warp << 5) * k1;
+
+  SymCursor la;
+  la.start(blockIdx.x, prm);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      done[s] = 0;
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int s = 0; s < kStages; ++s) {
+    if (tid == 0 && la.valid(prm)) {
+      mbar_arrive_expect_tx(&full[s], STAGE_BYTES + TAU_BYTES);
+      bulk_g2s(stage_mem + s * (BN * COLW), prm.tab + static_cast<size_t>(la.t) * BN * COLW, STAGE_BYTES, &full[s]);
+      bulk_g2s(taus + s * BN, prm.glast + static_cast<size_t>(la.t) * BN, TAU_BYTES, &full[s]);
+    }
+    if (la.valid(prm)) la.advance(prm, gridDim.x);
+  }
+
+  int stage = 0;
+  uint32_t phase = 0;
+  const unsigned one = prm.one;
+
+  for (int ii = blockIdx.x; ii < prm.n_items; ii += gridDim.x) {
+    const int4 it = __ldg(reinterpret_cast<const int4*>(prm.items) + ii);
+    const int rb = it.x, t0 = it.y, t1 = it.z;
+    const bool boot = it.w != 0;
+    const long long r = static_cast<long long>(rb) * kConsumers + tid;
+    const bool valid = r < prm.rows;
+    uint32_t q[COLW];
+    {
+      const uint32_t* src = prm.tab + static_cast<size_t>(valid ? r : 0) * COLW;
+#pragma unroll
+      for (int j = 0; j < COLW; ++j) q[j] = valid ? __ldg(src + j) : 0u;
+    }
+    // the row's global list already bounds what can still matter: ties at its last distance
+    // stay admissible (the index decides), hence the +1
+    int tau_seed = 0;
+    if (valid) {
+      const int g = ~static_cast<int>(ld_cg_u64(prm.glast + r) >> 32);
+      tau_seed = g >= kTauInf ? kTauInf : g + 1;
+    }
+    int tau = tau_seed;
+    {
+      unsigned long long* mine = lists + static_cast<size_t>(tid) * k1;
+      for (int j = 0; j < k1; ++j) mine[j] = ~0ull;
+    }
+    // invalid own rows never feed a column list; blocks of the bootstrap rows have no column side
+    // (every list already holds its candidates among the bootstrap rows) and start behind them
+    const unsigned vmask = (valid && !boot && !prm.no_col) ? 0xffffffffu : 0u;
+    const long long diag_begin = boot ? prm.boot_rows : static_cast<long long>(rb) * kConsumers;
+    const long long diag_end = boot ? (1ll << 40) : diag_begin + kConsumers;
+    __syncwarp();
+
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait(&full[stage], phase);
+      const uint32_t* tile = stage_mem + stage * (BN * COLW);
+      const unsigned long long* tnt = taus + stage * BN;
+      const long long col0 = static_cast<long long>(t) * BN;
+      const int ncols = static_cast<int>(min(static_cast<long long>(BN), prm.rows - col0));
+      int c = static_cast<int>(min(static_cast<long long>(ncols), max(0ll, diag_begin - col0)));
+      const int c_mid = static_cast<int>(min(static_cast<long long>(ncols), max(static_cast<long long>(c), diag_end - col0)));
+
+#pragma unroll 1
+      for (; c + 4 <= ncols; c += 4) {
+        int d0[1], d1[1], d2[1], d3[1];
+        const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
+        ham_rows<P, W, 1>(qq, tile + (c + 0) * COLW, d0, one);
+        ham_rows<P, W, 1>(qq, tile + (c + 1) * COLW, d1, one);
+        ham_rows<P, W, 1>(qq, tile + (c + 2) * COLW, d2, one);
+        ham_rows<P, W, 1>(qq, tile + (c + 3) * COLW, d3, one);
+        // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
+        const int4 na = *reinterpret_cast<const int4*>(tnt + c);
+        const int4 nb = *reinterpret_cast<const int4*>(tnt + c + 2);
+        const unsigned cm = c >= c_mid ? vmask : 0u;
+        // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
+        const int s0 = mad_s32(d0[0], one, -tau), s1 = mad_s32(d1[0], one, -tau);
+        const int s2 = mad_s32(d2[0], one, -tau), s3 = mad_s32(d3[0], one, -tau);
+        const int u0 = mad_s32(d0[0], one, na.y), u1 = mad_s32(d1[0], one, na.w);
+        const int u2 = mad_s32(d2[0], one, nb.y), u3 = mad_s32(d3[0], one, nb.w);
+        const int any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
+        if (__any_sync(0xffffffffu, any < 0)) {
+          const bool col_on = c >= c_mid;
+          auto rare = [&](int dv, int e) {
+            const unsigned col = static_cast<unsigned>(col0 + c + e);
+            const unsigned rc = __ballot_sync(0xffffffffu, dv < tau);
+            if (rc) tau = sym_serve_row(warp_lists, k1, rc, static_cast<unsigned>(dv), col, lane, tau_seed, tau, prm.stats);
+            if (col_on) {
+              // exact test against the snapshot of row col's last key: ties are decided by the index
+              const unsigned long long fw = tnt[c + e];
+              const unsigned long long lastk = (static_cast<unsigned long long>(~static_cast<unsigned>(fw >> 32)) << 32) |
+                                               (fw & 0xffffffffull);
+              const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(dv)) << 32) |
+                                              static_cast<unsigned>(r);
+              const bool cc = vmask != 0u && mine < lastk;
+              if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
+            }
+          };
+          rare(d0[0], 0);
+          rare(d1[0], 1);
+          rare(d2[0], 2);
+          rare(d3[0], 3);
+        }
+      }
+#pragma unroll 1
+      for (; c < ncols; ++c) {   // ragged end of the table (last tile only)
+        int d[1];
+        const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
+        ham_rows<P, W, 1>(qq, tile + c * COLW, d, one);
+        const unsigned col = static_cast<unsigned>(col0 + c);
+        const unsigned rc = __ballot_sync(0xffffffffu, d[0] < tau);
+        if (rc) tau = sym_serve_row(warp_lists, k1, rc, static_cast<unsigned>(d[0]), col, lane, tau_seed, tau, prm.stats);
+        const unsigned long long fw = tnt[c];
+        const unsigned long long lastk = (static_cast<unsigned long long>(~static_cast<unsigned>(fw >> 32)) << 32) |
+                                         (fw & 0xffffffffull);
+        const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(d[0])) << 32) |
+                                        static_cast<unsigned>(r);
+        const bool cc = vmask != 0u && c >= c_mid && mine < lastk;
+        if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
+      }
+
+      __syncwarp();
+      if (lane == 0) {
+        if (atom_add_acq_rel_cta(&done[stage], 1u) == kConsumerWarps - 1) {
+          done[stage] = 0;
+          if (la.valid(prm)) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES + TAU_BYTES);
+            bulk_g2s(stage_mem + stage * (BN * COLW), prm.tab + static_cast<size_t>(la.t) * BN * COLW, STAGE_BYTES,
+                     &full[stage]);
+            bulk_g2s(taus + stage * BN, prm.glast + static_cast<size_t>(la.t) * BN, TAU_BYTES, &full[stage]);
+          }
+        }
+      }
+      if (la.valid(prm)) la.advance(prm, gridDim.x);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+
+    // merge the chunk's lists into the rows' global lists (ascending keys, one row at a time)
+    __syncwarp();
+    const long long wrow0 = static_cast<long long>(rb) * kConsumers + (warp << 5);
+#pragma unroll 1
+    for (int src = 0; src < 32; ++src) {
+      if (wrow0 + src >= prm.rows) break;
+      const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
+      sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
+    }
+    __syncwarp();
+  }
+}
+
+struct SymLaunch {
+  int grid;
+  size_t list_bytes;
+  cudaStream_t stream;
+};
+
+template <int P, int W>
+inline size_t sweep_sym_smem_bytes(size_t list_bytes) {
+  return static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 + TileCols<W>::value * 8) +
+         2 * kStages * sizeof(uint64_t) + list_bytes;
+}
+
+// grid == 0: only report the resident grid (CTAs) through *resident
+template <int P, int W>
+int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
+  auto kern = sweep_sym_kernel<P, W>;
+  const size_t smem = sweep_sym_smem_bytes<P, W>(l.list_bytes);
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int occ = 0;
+  PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSweepThreads, smem));
+  if (occ < 1) { set_error("symmetric sweep does not fit on an SM (smem %zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
+  if (resident) *resident = num_sms() * occ;
+  if (l.grid <= 0) return PG_OK;
+  kern<<<static_cast<unsigned>(l.grid), kSweepThreads, smem, l.stream>>>(prm);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+#define PG_DECL_SWEEP_SYM(P, W) int sweep_sym_p##P##_w##W(const SymParams& prm, const SymLaunch& l, int* resident);
+PG_DECL_SWEEP_SYM(5, 1) PG_DECL_SWEEP_SYM(5, 2) PG_DECL_SWEEP_SYM(5, 4) PG_DECL_SWEEP_SYM(5, 8) PG_DECL_SWEEP_SYM(5, 16)
+PG_DECL_SWEEP_SYM(8, 1) PG_DECL_SWEEP_SYM(8, 2) PG_DECL_SWEEP_SYM(8, 4) PG_DECL_SWEEP_SYM(8, 8)
+#undef PG_DECL_SWEEP_SYM
+
+}  // namespace pg

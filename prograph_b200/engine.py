@@ -147,6 +147,53 @@ class CudaEngine:
                                         nbytes, self._stream()))
         return idx, w
 
+    SYM_MAX_LIST = 32      # list length (k + drop) the symmetric sweep keeps per row
+
+    def _sym_check(self, table, k1):
+        if k1 > self.SYM_MAX_LIST or table.words > 16 or (table.words > 8 and table.planes != 5):
+            raise L.Unsupported("shape not covered by the symmetric sweep")
+
+    def hamming_knn_boot(self, table, row0, rows, boot_rows, k1):
+        """Bootstrap lists (pg_hamming_knn_boot): rows [row0,row0+rows) one-sided against table rows
+        [0, boot_rows); (rows, k1) int64 keys distance<<32 | index, -1 = empty."""
+        self._sym_check(table, k1)
+        lists = self.empty((rows, k1), torch.int64)
+        ws, nbytes = self._workspace(rows, boot_rows, table.words, k1)
+        L.check(self.lib.pg_hamming_knn_boot(_ptr(table.data), table.rows, int(row0), int(rows), int(boot_rows),
+                                             table.planes, table.words, int(k1), _ptr(lists), _ptr(ws), nbytes,
+                                             self._stream()))
+        return lists
+
+    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0):
+        """Symmetric sweep of `table` against itself (pg_hamming_knn_sym): this rank's row blocks
+        rank, rank+world, ...; returns the (rows, k1) int64 tensor of sorted keys
+        distance<<32 | index (-1 = empty) this rank found for EVERY row of the table.  `lists`:
+        the bootstrap lists of all rows when boot_rows > 0 (updated in place)."""
+        self._sym_check(table, k1)
+        if boot_rows:
+            assert lists is not None and tuple(lists.shape) == (table.rows, k1) and lists.is_contiguous()
+        else:
+            lists = self.empty((table.rows, k1), torch.int64)
+        nbytes = int(self.lib.pg_knn_sym_workspace_bytes(table.rows, table.words))
+        ws = self.empty((nbytes,), torch.uint8)
+        L.check(self.lib.pg_hamming_knn_sym(_ptr(table.data), table.rows, table.planes, table.words, int(k1),
+                                            int(rank), int(world), int(boot_rows), _ptr(lists), _ptr(ws), nbytes,
+                                            self._stream()))
+        return lists
+
+    def knn_lists_finalize(self, lists, row0, rows, k, drop=1, similarity=False):
+        """lists: (n_lists, N, k1) or (N, k1) key lists -> (idx, w) of rows [row0,row0+rows)."""
+        if lists.dim() == 2:
+            lists = lists.unsqueeze(0)
+        lists = lists.contiguous()
+        n_lists, n, k1 = lists.shape
+        weight = L.W_SIM_F32 if similarity else L.W_I64
+        idx = self.empty((rows, k), torch.int64)
+        w = self.empty((rows, k), torch.float32 if similarity else torch.int64)
+        L.check(self.lib.pg_knn_lists_finalize(_ptr(lists), n_lists, n * k1, int(row0), int(rows), k1, int(k),
+                                               int(drop), weight, _ptr(idx), _ptr(w), self._stream()))
+        return idx, w
+
     def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
         """prograph.py:731-753 for own rows [row0,row0+rows): CSR (indptr, idx, w) of the
         stream rows whose distance d has bit d set in `lut` (uint32 words, host)."""

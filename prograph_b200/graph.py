@@ -21,6 +21,7 @@ ends up with the whole graph (all-gather of the result shards).
 """
 import functools
 import operator
+import os
 
 import numpy as np
 import torch
@@ -218,6 +219,65 @@ def hamming_knn_device(eng, own, stream, k, similarity, row0, rows):
         return hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows)
 
 
+# ---------------------------------------------------------------------------------
+# symmetric kNN build: every unordered pair once (pg_sweep_sym.cuh)
+# ---------------------------------------------------------------------------------
+SYM_MIN_ROWS = 65536      # below this the one-sided sweep is as fast (bootstrap + merge overheads)
+SYM_BOOT_ROWS = 8192      # bootstrap columns: tight filters from the first tile on
+SYM_BOOT_DIV = 8          # ... but at most 1/8 of the table
+
+
+def _sym_enabled(eng, packed, k1, world):
+    if not hasattr(eng, "hamming_knn_sym"):
+        return False
+    force = os.environ.get("PG_KNN_SYM")
+    if force is not None:
+        return force not in ("0", "")
+    return packed.rows >= SYM_MIN_ROWS and k1 <= getattr(eng, "SYM_MAX_LIST", 0)
+
+
+def sym_boot_rows(n):
+    """Bootstrap columns for a table of n rows: a multiple of the 512-row packed tile."""
+    return max(0, min(SYM_BOOT_ROWS, n // SYM_BOOT_DIV // _shard.ROW_ALIGN * _shard.ROW_ALIGN))
+
+
+def hamming_knn_graph(eng, packed, k, similarity, rank, world, group):
+    """kNN lists of EVERY row of `packed` against itself (prograph.py:755-765), on every rank.
+
+    Large tables take the symmetric sweep: d(i,j) == d(j,i), so each unordered pair is evaluated
+    once and offered to both rows' lists.  Ranks own interleaved 256-row blocks of the triangle;
+    the per-rank candidate lists of all rows are all-gathered (NCCL) and merged -- the exchange
+    step of this path.  Small tables and long lists take the one-sided sweep on this rank's row
+    block followed by the all-gather of the result rows."""
+    n = packed.rows
+    kk = min(k, n - 1)
+    if kk > 0 and _sym_enabled(eng, packed, kk + 1, world):
+        try:
+            return _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group)
+        except L.Unsupported:
+            pass
+    row0, rows = _shard.row_range(n, rank, world)
+    part = hamming_knn_device(eng, packed, packed, k, similarity, row0, rows) if rows else None
+    return _shard.gather_rows(part, n, rank, world, group, eng)
+
+
+def _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group):
+    n, k1 = packed.rows, kk + 1
+    sharded = world > 1 and n >= world
+    if not sharded:
+        rank, world = 0, 1
+    boot = sym_boot_rows(n)
+    seed = None
+    if boot:
+        row0, rows = _shard.row_range(n, rank, world)
+        seed = eng.hamming_knn_boot(packed, row0, rows, boot, k1)
+        seed = _shard.gather_rows((seed,), n, rank, world, group, eng)[0].contiguous()
+    lists = eng.hamming_knn_sym(packed, k1, rank, world, lists=seed, boot_rows=boot)
+    if sharded:
+        lists = _shard.all_gather_stack(lists, world, group)          # (world, n, k1)
+    return eng.knn_lists_finalize(lists, 0, n, kk, 1, similarity)
+
+
 def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
     """Same result through materialised int64 tiles + the tile top-k: used when k is too large
     for the in-shared-memory lists of the fused sweep.  Ascending distance with index ties is
@@ -374,7 +434,8 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
             lut = distance_lut(packed.words * 32, comp, eps, similarity)
             part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
         else:
-            part = hamming_knn_device(eng, packed, packed, k, similarity, row0, rows) if rows else None
+            idx, w = hamming_knn_graph(eng, packed, k, similarity, rank, world, group)
+            return KnnTable(_to_host(idx), _to_host(w))
     else:
         # prograph.py:726: every representation is rounded to fp16 before the metric sees it
         Xh = eng.to_device(X).to(torch.float16)

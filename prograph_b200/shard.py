@@ -5,6 +5,9 @@ the whole table only, so rank g owns query rows [g*ceil(N/G), (g+1)*ceil(N/G)) a
 N columns: no cross-rank merge, tie semantics untouched.  The only
 collectives are all-gathers of the result shards over torch.distributed (NCCL over NVLink
 on the GPU box, gloo in the CPU tests); there is no collective inside the distance sweep.
+The symmetric kNN build (graph.hamming_knn_graph) shards the triangle of unordered pairs by
+interleaved 256-row blocks instead; there every rank holds candidate lists for all rows and
+the all-gather of those lists is followed by a merge (pg_knn_lists_finalize).
 """
 import torch
 import torch.distributed as dist
@@ -75,6 +78,13 @@ def gather_rows(part, n, rank, world, group, eng=None):
     if not _sharded(n, world):
         return part
     return tuple(_gather_blocks(t, n, world, group) for t in part)
+
+
+def all_gather_stack(t, world, group):
+    """Same-shaped tensor from every rank -> (world, *t.shape)."""
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out.reshape((world,) + tuple(t.shape))
 
 
 def gather_csr(part, n, rank, world, group, eng=None):

@@ -37,6 +37,70 @@ class CheckerEngine:
         order = np.argsort(-key if similarity else key, axis=1, kind="stable")[:, drop:drop + k]
         return torch.from_numpy(order.astype(np.int64)), torch.from_numpy(np.take_along_axis(D, order, axis=1))
 
+    # ---- symmetric kNN build: the same contract as CudaEngine, answered with the oracle ----
+    SYM_MAX_LIST = 32
+    EMPTY = np.int64(-1)
+
+    @staticmethod
+    def _keys(D, cols):
+        return (D.astype(np.int64) << 32) | cols.astype(np.int64)
+
+    @classmethod
+    def _smallest(cls, keys, k1):
+        """k1 smallest keys per row (rows may hold EMPTY = all ones, which sorts last as uint64)."""
+        u = np.sort(keys.view(np.uint64), axis=1)[:, :k1]
+        if u.shape[1] < k1:
+            u = np.concatenate([u, np.full((u.shape[0], k1 - u.shape[1]), np.uint64(2**64 - 1))], axis=1)
+        return u.view(np.int64)
+
+    def hamming_knn_boot(self, table, row0, rows, boot_rows, k1):
+        D = O.hamming(table.tokens[:boot_rows], table.tokens[row0:row0 + rows])
+        keys = self._keys(D, np.broadcast_to(np.arange(boot_rows), D.shape))
+        return torch.from_numpy(np.ascontiguousarray(self._smallest(keys, k1)))
+
+    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0):
+        """Candidates this rank sees: row blocks rank, rank+world, ... of 256 rows, each against
+        the stream rows from its own block on (row side) and feeding the later blocks' rows
+        (column side); blocks of the bootstrap rows start behind them and have no column side."""
+        n = table.rows
+        self.sym_calls = getattr(self, "sym_calls", 0) + 1
+        cand = [[] for _ in range(n)]
+        if boot_rows:
+            for r in range(n):
+                cand[r].extend(int(v) for v in lists[r].numpy() if v != -1)
+        T = table.tokens
+        for rb in range(rank, -(-n // 256), world):
+            a, b = rb * 256, min(n, rb * 256 + 256)
+            start = boot_rows if a < boot_rows else a
+            if start >= n:
+                continue
+            D = O.hamming(T[start:], T[a:b])                      # (b-a, n-start)
+            for i in range(a, b):
+                for j in range(start, n):
+                    d = int(D[i - a, j - start])
+                    cand[i].append((d << 32) | j)
+                    if a >= boot_rows and j >= b:
+                        cand[j].append((d << 32) | i)
+        out = np.full((n, k1), -1, dtype=np.int64)
+        for r in range(n):
+            u = sorted(set(cand[r]))[:k1]
+            out[r, :len(u)] = u
+        return torch.from_numpy(out)
+
+    def knn_lists_finalize(self, lists, row0, rows, k, drop=1, similarity=False):
+        lists = lists.numpy()
+        if lists.ndim == 2:
+            lists = lists[None]
+        idx = np.full((rows, k), -1, dtype=np.int64)
+        w = np.zeros((rows, k), dtype=np.float32 if similarity else np.int64)
+        for r in range(rows):
+            keys = sorted(set(int(v) for v in lists[:, row0 + r].reshape(-1) if v != -1))[drop:drop + k]
+            for j, key in enumerate(keys):
+                idx[r, j] = key & 0xffffffff
+                d = key >> 32
+                w[r, j] = np.float32(1.0) / np.float32(1 + d) if similarity else d
+        return torch.from_numpy(idx), torch.from_numpy(w)
+
     def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
         self.rows_seen = (row0, rows)
         D = O.hamming(stream.tokens, own.tokens[row0:row0 + rows])

@@ -171,3 +171,45 @@ def test_sharded_build_over_gloo(tmp_path, n):
         seen.append(tuple(z["rows"]))
     # the two ranks worked on disjoint row blocks that tile [0, n)
     assert seen[0][0] == 0 and seen[0][0] + seen[0][1] == seen[1][0] and seen[1][0] + seen[1][1] == n
+
+
+def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _cpu_engine import CheckerEngine
+    from prograph_b200 import graph
+    graph.SYM_MIN_ROWS, graph.SYM_BOOT_DIV = 0, boot_div      # route this small table through the symmetric build
+    rng = np.random.default_rng(5)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    eng = CheckerEngine()
+    knn = graph.build_neighbours(X, k=k, engine=eng)
+    sim = graph.build_neighbours(X, k=k, similarity=True, engine=eng)
+    np.savez(os.path.join(tmpdir, f"r{rank}.npz"), idx=knn.idx, w=knn.w, sidx=sim.idx, sw=sim.w,
+             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,boot_div", [(700, 8), (1301, 2)])
+def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
+    """world_size 2 on CPU, symmetric kNN build: ranks take interleaved row blocks of the triangle,
+    exchange their candidate lists (all-gather) and merge; with and without the bootstrap pass."""
+    import torch.multiprocessing as mp
+    from oracle import prograph_oracle as O
+    k, world = 5, 2
+    port = 29950 + (os.getpid() + n) % 40
+    mp.spawn(_gloo_sym_worker, args=(world, port, n, k, boot_div, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(5)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    ri, rw = O.knn_from_distances(O.hamming(X, X), k)
+    si, sw = O.knn_from_distances(O.hamming(X, X, similarity=True), k, descending=True)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(z["idx"], ri)
+        np.testing.assert_array_equal(z["w"], rw)
+        np.testing.assert_array_equal(z["sidx"], si)
+        np.testing.assert_array_equal(z["sw"], sw)
+        assert z["calls"][0] == 2                       # both builds went through the symmetric sweep
+        assert z["calls"][1] == (512 if boot_div == 2 else 0)
