@@ -7,13 +7,18 @@ synthetic library of N=1M sequences, L=256 (BASELINE.json configs[3]), at 1/2/4/
         --master-port 29500 bench.py --gpus 8 --steps 3 --warmup 3
     python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port)
 
-A step = one full graph build: pack the token table into bit planes, sweep all N x N
-ordered pairs with the fused Hamming+top-k kernel on this rank's row block, finalise, and
-all-gather the result shards.  `value` times that with the uint8 token table resident in
-HBM; `e2e` times the public API call (prograph_b200.build_neighbours) on a pinned HOST
-token table, i.e. H2D + the same work + D2H of the neighbour lists.  Rows are sharded
-across ranks (total work fixed -> "strong" scaling); times are CUDA-event times, max over
-ranks.  One JSON line is printed by rank 0.
+A step = one full graph build: pack the token table into bit planes, build the kNN lists of
+all N rows with the fused Hamming+top-k sweeps, finalise, and all-gather.  The build is the
+symmetric one (prograph_b200/csrc/pg_sweep_sym.cuh): d(i,j) == d(j,i), so after a one-sided
+bootstrap pass over the first 8192 columns every unordered pair is evaluated ONCE and offered
+to both rows' lists.  The metric still counts all N^2 ordered pairs -- what the reference
+evaluates and what `--one-sided` (the previous kernel) evaluates -- while the roofline is
+computed on the pair evaluations actually issued (`pairs_evaluated`).  `value` times the
+build with the uint8 token table resident in HBM; `e2e` times the public API call
+(prograph_b200.build_neighbours) on a pinned HOST token table, i.e. H2D + the same work +
+D2H of the neighbour lists.  Ranks own interleaved row blocks of the triangle (total work
+fixed -> "strong" scaling) and all-gather their candidate lists; times are CUDA-event times,
+max over ranks.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -45,6 +50,8 @@ def parse_args():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "mutational"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--one-sided", action="store_true",
+                    help="evaluate all N^2 ordered pairs with the one-sided sweep (no symmetry)")
     return ap.parse_args()
 
 
@@ -66,7 +73,9 @@ def make_tokens(n, L, kind):
 def config_of(args, world):
     return {
         "workload": f"C4-{'U' if args.dist == 'uniform' else 'M'}: synthetic {args.n} sequences, L={args.length}, "
-                    f"Hamming kNN k={args.k}, all N^2 ordered pairs, rows sharded over {world} GPU(s)",
+                    f"Hamming kNN k={args.k}, N^2 ordered pairs counted, "
+                    + ("one-sided sweep, rows" if args.one_sided else "symmetric sweep (each unordered pair evaluated "
+                       "once), interleaved row blocks") + f" sharded over {world} GPU(s)",
         "n_sequences": args.n, "seq_len": args.length, "k": args.k, "distribution": args.dist,
         "parallelism": f"row-block x{world}",
         "l2": "inputs exceed L2: 160 MB packed table + split partial lists (>400 MB) are re-read every step",
@@ -174,12 +183,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def ncu_traffic_bytes(n, world):
+def ncu_traffic_bytes(n, world, capture):
     """dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, per launch, from the
     committed `ncu --set full` capture of this exact configuration (profiles/); None otherwise."""
     if n != 1_000_000 or world != 1:
         return None
-    path = os.path.join(ROOT, "profiles", "r1_ncu_sweep_r1d.csv")
+    path = os.path.join(ROOT, "profiles", capture)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total = 0.0
     try:
@@ -204,8 +213,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.one_sided:
+        os.environ["PG_KNN_SYM"] = "0"
     from prograph_b200 import build_neighbours
-    from prograph_b200 import shard
+    from prograph_b200 import graph, shard
     from prograph_b200.engine import get_engine
     eng = get_engine()
     n, L, k = args.n, args.length, args.k
@@ -222,8 +233,7 @@ def run_b200(args):
 
     def step_resident():
         tab = eng.pack(dev)
-        part = eng.hamming_knn(tab, row0, rows, tab, k, drop=1)
-        return shard.gather_rows(part, n, rank, world, None, eng)
+        return graph.hamming_knn_graph(eng, tab, k, False, rank, world, None)
 
     def timed(fn, steps):
         barrier()
@@ -247,7 +257,7 @@ def run_b200(args):
     eng.time_sweeps(True)
     eng.sweep_time(reset=True)
     ms_total = timed(step_resident, args.steps)
-    sweep_ms, sweep_launches = eng.sweep_time(reset=True)
+    sweep_list = eng.sweep_times(reset=True)
     eng.time_sweeps(False)
     launches = eng.launch_count(reset=True)
     clocks = sampler.stop() if rank == 0 else None
@@ -273,35 +283,54 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the fused sweep) ---------------------------------
+    # ---- roofline of the dominant kernel, on the pair evaluations it actually issued ---------
     words = eng.packed_words(L)
     lane_ops_per_pair = 7 * words                       # 5 LOP3 + 1 POPC + 1 IADD per 32 residues
-    pairs_per_launch = float(rows) * float(n)           # rank 0's row block
+    symmetric = (not args.one_sided) and len(sweep_list) == 2 * args.steps
+    boot = graph.sym_boot_rows(n) if symmetric else 0
+    if symmetric:
+        # rank 0's share: bootstrap rectangle + its interleaved row blocks of the triangle
+        boot_pairs = float(shard.row_range(n, 0, world)[1]) * boot
+        tri_pairs = 0.0
+        for rb in range(0, -(-n // 256), world):
+            a, b = rb * 256, min(n, rb * 256 + 256)
+            tri_pairs += float(b - a) * (n - (boot if a < boot else a))
+        kernel_ms = sum(sweep_list[1::2]) / args.steps
+        boot_ms = sum(sweep_list[0::2]) / args.steps
+        pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8>"
+        capture = "r1_ncu_sym.csv"
+    else:
+        boot_pairs, boot_ms = 0.0, 0.0
+        kernel_ms = sum(sweep_list) / max(1, len(sweep_list))
+        pairs_per_launch, kernel_name = float(rows) * float(n), "pg::sweep_kernel<5,8,KNN>"
+        capture = "r1_ncu_sweep_r1d.csv"
     peak_ops, _ = eng.int_peak(mix=0, iters=2048)
     lop_ops, _ = eng.int_peak(mix=1, iters=2048)
     popc_ops, _ = eng.int_peak(mix=2, iters=2048)
     roofline = None
-    if sweep_launches:
-        avg_ms = sweep_ms / sweep_launches
-        achieved = lane_ops_per_pair * pairs_per_launch / (avg_ms * 1e-3)
+    if sweep_list:
+        achieved = lane_ops_per_pair * pairs_per_launch / (kernel_ms * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         packed_bytes = float(n) * 5 * words * 4
-        hbm_algo = packed_bytes + float(rows) * (k + 1) * 8     # table read once + lists written once
+        hbm_algo = packed_bytes + float(n) * (k + 1) * 8     # table read once + lists written once
         roofline = {
-            "bound": "int-alu", "kernel": "pg::sweep_kernel<5,8,KNN>", "achieved": achieved / 1e12,
+            "bound": "int-alu", "kernel": kernel_name, "achieved": achieved / 1e12,
             "peak": peak_ops / 1e12, "unit": "Tlane-op/s", "frac": achieved / peak_ops,
             "peak_source": "measured live: pg_measure_int_peak (register-only kernel, 5 LOP3 : 1 POPC : 1 IMAD like the sweep)",
-            "lane_ops_per_pair": lane_ops_per_pair, "pairs_per_launch": pairs_per_launch,
-            "kernel_ms": avg_ms, "kernel_launches": sweep_launches,
-            "kernel_share_of_step": sweep_ms / ms_total,
-            "gpairs_per_s_kernel": pairs_per_launch / (avg_ms * 1e-3) / 1e9,
+            "lane_ops_per_pair": lane_ops_per_pair, "pairs_evaluated_per_launch": pairs_per_launch,
+            "ordered_pairs_counted_per_step": float(n) * float(n),
+            "kernel_ms": kernel_ms, "kernel_launches": args.steps,
+            "kernel_share_of_step": kernel_ms * args.steps / ms_total,
+            "gpairs_evaluated_per_s_kernel": pairs_per_launch / (kernel_ms * 1e-3) / 1e9,
+            "bootstrap": ({"rows": boot, "pairs_evaluated": boot_pairs, "kernel": "pg::sweep_kernel<5,8,KNN>",
+                           "kernel_ms": boot_ms} if symmetric else None),
             "lop3_peak_tlops": lop_ops / 1e12, "popc_peak_tlops": popc_ops / 1e12,
-            "traffic": ncu_traffic_bytes(n, world),
-            "hbm": {"algorithmic_bytes_per_launch": hbm_algo, "achieved_gbs": hbm_algo / (avg_ms * 1e-3) / 1e9,
+            "traffic": ncu_traffic_bytes(n, world, capture),
+            "hbm": {"algorithmic_bytes_per_launch": hbm_algo, "achieved_gbs": hbm_algo / (kernel_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                     "note": "compute-bound kernel: the HBM roofline is not the binding one"},

@@ -290,6 +290,8 @@ int64_t pg_launch_count(int reset);
  * the last reset: total ms and launches. Enable with pg_time_sweeps(1). */
 int pg_time_sweeps(int enable);
 int pg_sweep_time(double* total_ms, int64_t* launches, int reset);
+/* the same, one entry per timed launch in launch order (ms[0..min(cap,*n))) */
+int pg_sweep_times(double* ms, int64_t cap, int64_t* n, int reset);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pg_launch_count": (_i64, [_i]),
     "pg_time_sweeps": (_i, [_i]),
     "pg_sweep_time": (_i, [_pdbl, _pi64, _i]),
+    "pg_sweep_times": (_i, [_pdbl, _i64, _pi64, _i]),
 }
 
 _lib = None

@@ -745,4 +745,22 @@ int pg_sweep_time(double* total_ms, int64_t* launches, int reset) {
   return PG_OK;
 }
 
+int pg_sweep_times(double* ms, int64_t cap, int64_t* n, int reset) {
+  std::lock_guard<std::mutex> g(g_time_mu);
+  int64_t i = 0;
+  for (auto& ev : g_time_events) {
+    cudaEventSynchronize(ev.second);
+    float t = 0;
+    cudaEventElapsedTime(&t, ev.first, ev.second);
+    if (ms && i < cap) ms[i] = t;
+    ++i;
+  }
+  if (n) *n = i;
+  if (reset) {
+    for (auto& ev : g_time_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    g_time_events.clear();
+  }
+  return PG_OK;
+}
+
 }  // extern "C"

@@ -424,6 +424,13 @@ class CudaEngine:
         self.lib.pg_sweep_time(C.byref(ms), C.byref(n), 1 if reset else 0)
         return ms.value, n.value
 
+    def sweep_times(self, reset=True, cap=4096):
+        """Per-launch times (ms) of the timed sweeps, in launch order."""
+        buf = (C.c_double * cap)()
+        n = C.c_int64(0)
+        self.lib.pg_sweep_times(buf, cap, C.byref(n), 1 if reset else 0)
+        return [buf[i] for i in range(min(cap, n.value))]
+
 
 _ENGINE = None
 

@@ -542,18 +542,22 @@ def test_save_reload_with_csr_sidecar(pgb, pg_synth, tmp_path):
 
 
 def test_headline_config_one_million_uniform(eng):
-    """The bench workload itself (C4-U: 1 M x 256 iid-uniform tokens, k=16, all 10^12 pairs):
-    sampled rows bit for bit against the oracle, plus size-independent properties."""
+    """The bench workload itself (C4-U: 1 M x 256 iid-uniform tokens, k=16, all 10^12 ordered pairs
+    through the symmetric build): sampled rows bit for bit against the oracle, plus
+    size-independent properties."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import make_tokens
     n, L, k = 1_000_000, 256, 16
     X = make_tokens(n, L, "uniform")
     tab = eng.pack(X)
-    idx, w = eng.hamming_knn(tab, 0, n, tab, k, drop=1)
+    from prograph_b200 import graph
+    assert n >= graph.SYM_MIN_ROWS                                # i.e. the symmetric build, as in bench.py
+    idx, w = graph.hamming_knn_graph(eng, tab, k, False, 0, 1, None)
     idx, w = np_(idx), np_(w)
     rng = np.random.default_rng(123)
-    sample = np.concatenate([[0, n - 1], rng.choice(n, size=22, replace=False)])
+    # rows of the bootstrap block, of the first / last row blocks and random ones
+    sample = np.concatenate([[0, 5000, 8191, 8192, n - 1], rng.choice(n, size=19, replace=False)])
     D = O.hamming(X, X[sample], chunk=8)
     ri, rw = O.knn_from_distances(D, k)
     np.testing.assert_array_equal(idx[sample], ri)
@@ -565,3 +569,10 @@ def test_headline_config_one_million_uniform(eng):
     pick = rng.choice(n, size=4000, replace=False)
     for j in (0, k - 1):
         assert np.all((X[pick] != X[idx[pick, j]]).sum(1) == w[pick, j])
+    # mutuality (what the symmetric build must get right on both sides of every pair): if j is
+    # i's nearest neighbour and strictly closer than j's own k-th neighbour, j lists i
+    pick = rng.choice(n, size=200_000, replace=False)
+    j, d = idx[pick, 0], w[pick, 0]
+    must = d < w[j, k - 1]
+    assert must.sum() > 1000
+    assert np.all((idx[j[must]] == pick[must][:, None]).any(axis=1))

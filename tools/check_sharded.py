@@ -30,9 +30,17 @@ def main():
     import operator
     eng = get_engine()
     ok = True
-    for n, L in ((20000, 256), (3001, 56), (700, 20)):
+    from prograph_b200 import graph
+    for n, L, sym_min in ((20000, 256, None), (3001, 56, None), (700, 20, None), (70000, 256, None), (20000, 256, 0),
+                          (3001, 56, 0)):
+        # sym_min = 0 routes small tables through the symmetric build too (interleaved row blocks,
+        # all-gather + merge of the candidate lists); 70000 rows take it by default
+        default_min = graph.SYM_MIN_ROWS
+        if sym_min is not None:
+            graph.SYM_MIN_ROWS = sym_min
         X = make_tokens(n, L, "mutational")
         knn = build_neighbours(X, k=16)
+        graph.SYM_MIN_ROWS = default_min
         eps = build_neighbours(X, eps=2)
         tab = eng.pack(X)
         ri, rw = eng.hamming_knn(tab, 0, n, tab, 16, drop=1)
