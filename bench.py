@@ -75,11 +75,14 @@ def config_of(args, world):
         "workload": f"C4-{'U' if args.dist == 'uniform' else 'M'}: synthetic {args.n} sequences, L={args.length}, "
                     f"Hamming kNN k={args.k}, N^2 ordered pairs counted, "
                     + ("one-sided sweep, rows" if args.one_sided else "symmetric sweep (each unordered pair evaluated "
-                       "once), interleaved row blocks") + f" sharded over {world} GPU(s)",
+                       "once), bands of the triangle") + f" sharded over {world} GPU(s)",
         "n_sequences": args.n, "seq_len": args.length, "k": args.k, "distribution": args.dist,
         "parallelism": f"row-block x{world}",
         "l2": "inputs exceed L2: 160 MB packed table + split partial lists (>400 MB) are re-read every step",
     }
+
+
+emit = None      # set by main(): writes the one JSON line to the real stdout
 
 
 # ----------------------------------------------------------------------------------------
@@ -132,7 +135,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -289,12 +292,15 @@ def run_b200(args):
     symmetric = (not args.one_sided) and len(sweep_list) == 2 * args.steps
     boot = graph.sym_boot_rows(n) if symmetric else 0
     if symmetric:
-        # rank 0's share: bootstrap rectangle + its interleaved row blocks of the triangle
+        # rank 0's share: bootstrap rectangle + its piece of the triangle (one GPU: everything;
+        # several: the band of stream rows the library's planner gives rank 0)
         boot_pairs = float(shard.row_range(n, 0, world)[1]) * boot
+        band = (0, n) if world == 1 else eng.sym_band(n, words, boot, 0, world)
         tri_pairs = 0.0
-        for rb in range(0, -(-n // 256), world):
+        for rb in range(0, -(-n // 256)):
             a, b = rb * 256, min(n, rb * 256 + 256)
-            tri_pairs += float(b - a) * (n - (boot if a < boot else a))
+            lo = max(boot if a < boot else a, band[0])
+            tri_pairs += float(b - a) * max(0, band[1] - lo)
         kernel_ms = sum(sweep_list[1::2]) / args.steps
         boot_ms = sum(sweep_list[0::2]) / args.steps
         pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8>"
@@ -354,13 +360,22 @@ def run_b200(args):
         "config": config_of(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout must carry exactly one JSON line: park the real stdout, let everything libraries
+    # write to fd 1 (NCCL prints its version banner there) go to stderr, and hand the JSON line
+    # to the parked descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -109,10 +109,12 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
 
 /* Symmetric kNN of a table against itself (the case build_graph runs, prograph.py:755-765):
  * d(i,j) == d(j,i), so every unordered pair is evaluated once and offered to the lists of both
- * rows -- half of the reference's N x N evaluations.  This rank handles row blocks (256 rows)
- * rb_first, rb_first + rb_stride, ... (rb_first = rank, rb_stride = world size; 0, 1 for one
- * GPU) and leaves in lists[r*k1 .. r*k1+k1) the k1 smallest keys  distance<<32 | index  it saw
- * for row r, ascending, ~0 = empty.  With several ranks the per-rank lists are all-gathered and
+ * rows -- half of the reference's N x N evaluations.  The triangle is cut into `parts` pieces
+ * (part = rank, parts = world size; 0, 1 for one GPU): mode 0 gives this rank the row blocks
+ * (256 rows) part, part + parts, ...; mode 1 gives it every row block restricted to a band of
+ * stream rows (pg_knn_sym_band; bands hold equal numbers of pair evaluations), so that a row's
+ * column-side candidates all meet on one rank.  The call leaves in lists[r*k1 .. r*k1+k1) the k1
+ * smallest keys  distance<<32 | index  this rank saw for row r, ascending, ~0 = empty.  With several ranks the per-rank lists are all-gathered and
  * merged by pg_knn_lists_finalize.  k1 <= 32; wider lists take pg_hamming_knn.
  *
  * Bootstrap (boot_rows > 0, a multiple of 512): the caller first runs pg_hamming_knn_boot, which
@@ -126,8 +128,11 @@ int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0,
                         void* workspace /* pg_sweep_workspace_bytes(rows, boot_rows, words, k1) */,
                         size_t workspace_bytes, void* stream);
 int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1,
-                       int rb_first, int rb_stride, int64_t boot_rows, uint64_t* lists,
+                       int part, int parts, int mode, int64_t boot_rows, uint64_t* lists,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* host only: the stream rows [row_begin, row_end) of band `part` of `parts` (mode 1) */
+int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int parts,
+                    int64_t* row_begin, int64_t* row_end);
 /* merge n_lists key lists per row (list s of row r at lists[s*list_stride + r*k1]), drop the first
  * `drop` merged positions and write the next k as out_idx[(r-row0)*k + j] / out_w per `weight`
  * for rows [row0, row0+rows); missing entries get idx = -1 (as pg_hamming_knn).  */

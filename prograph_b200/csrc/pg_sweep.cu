@@ -282,36 +282,79 @@ static SymLayout sym_layout(long long rows, int words) {
   return s;
 }
 
+static int sym_first_tile(const SymLayout& s, int rb, long long boot_rows) {
+  const long long row = static_cast<long long>(rb) * kConsumers < boot_rows ? boot_rows
+                                                                            : static_cast<long long>(rb) * kConsumers;
+  return static_cast<int>(row / s.tile_cols);
+}
+
+// Column band of partition `part` of `parts`: tile range [t0, t1) such that every band holds the
+// same number of (own row, stream tile) visits of the triangle.
+static void sym_band(const SymLayout& s, long long rows, long long boot_rows, int part, int parts, int* t0, int* t1) {
+  std::vector<long long> visits(static_cast<size_t>(s.n_tiles) + 1, 0);
+  for (int rb = 0; rb < s.n_blocks; ++rb) {
+    const int tb = sym_first_tile(s, rb, boot_rows);
+    if (tb >= s.n_tiles) continue;
+    const long long in_block = std::min<long long>(kConsumers, rows - static_cast<long long>(rb) * kConsumers);
+    visits[tb] += in_block;          // rows that sweep every tile from tb on
+  }
+  long long total = 0, run = 0;
+  for (int t = 0; t < s.n_tiles; ++t) { run += visits[t]; visits[t] = run; total += run; }
+  auto bound = [&](int g) {
+    if (g <= 0) return 0;
+    if (g >= parts) return s.n_tiles;
+    const long long want = static_cast<long long>(static_cast<double>(total) * g / parts);
+    long long acc = 0;
+    for (int t = 0; t < s.n_tiles; ++t) {
+      acc += visits[t];
+      if (acc >= want) return t + 1;
+    }
+    return s.n_tiles;
+  };
+  *t0 = bound(part);
+  *t1 = bound(part + 1);
+}
+
 // Chunks of (row block, tile range), longest first, dealt to the persistent grid in snake
 // order so that every CTA gets the same number of tiles to within one short chunk.  Chunk
 // boundaries are shifted from row block to row block so that CTAs that start together do not
 // walk the same stream rows in lockstep (they would fight for the same row locks).
-static std::vector<SymItem> sym_plan(const SymLayout& s, int rb_first, int rb_stride, int grid, long long boot_rows) {
+// mode 0: this rank takes row blocks part, part+parts, ... over their whole tile range;
+// mode 1: every row block, restricted to this rank's column band (sym_band).
+static std::vector<SymItem> sym_plan(const SymLayout& s, long long rows, int part, int parts, int mode, int grid,
+                                     long long boot_rows) {
   const int boot_blocks = static_cast<int>(boot_rows / kConsumers);
-  auto first_tile = [&](int rb) {
-    const long long row = rb < boot_blocks ? boot_rows : static_cast<long long>(rb) * kConsumers;
-    return static_cast<int>(row / s.tile_cols);
+  int band0 = 0, band1 = s.n_tiles;
+  if (mode == 1) sym_band(s, rows, boot_rows, part, parts, &band0, &band1);
+  const int rb_first = mode == 1 ? 0 : part, rb_stride = mode == 1 ? 1 : parts;
+  auto range = [&](int rb, int* a, int* b) {
+    *a = std::max(sym_first_tile(s, rb, boot_rows), band0);
+    *b = band1;
   };
   long long total = 0;
-  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride) total += std::max(0, s.n_tiles - first_tile(rb));
+  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride) {
+    int a, b;
+    range(rb, &a, &b);
+    total += std::max(0, b - a);
+  }
   long long chunk = ceil_div(total, static_cast<long long>(grid) * 24);
   if (const char* ev = std::getenv("PG_SYM_CHUNK")) chunk = std::atoll(ev);
   if (chunk < 32) chunk = 32;
   std::vector<SymItem> items;
   unsigned n_seen = 0;
   for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride, ++n_seen) {
-    const int tb = first_tile(rb);
-    const int len = s.n_tiles - tb;
-    if (len <= 0) continue;
+    int tb, te;
+    range(rb, &tb, &te);
+    if (te <= tb) continue;
     const int boot = rb < boot_blocks ? 1 : 0;
     // golden-ratio phase of the first boundary, in (chunk/4, 5*chunk/4]
     const double frac = (n_seen * 0.6180339887498949) - static_cast<long long>(n_seen * 0.6180339887498949);
     int t = tb;
-    int first = static_cast<int>(chunk / 4 + static_cast<long long>(frac * static_cast<double>(chunk))) + 1;
-    while (t < s.n_tiles) {
+    const int first = static_cast<int>(chunk / 4 + static_cast<long long>(frac * static_cast<double>(chunk))) + 1;
+    while (t < te) {
       int t1 = t + (t == tb ? first : static_cast<int>(chunk));
-      if (s.n_tiles - t1 < chunk / 4) t1 = s.n_tiles;     // no crumbs at the end
-      if (t1 > s.n_tiles) t1 = s.n_tiles;
+      if (te - t1 < chunk / 4) t1 = te;     // no crumbs at the end
+      if (t1 > te) t1 = te;
       items.push_back(SymItem{rb, t, t1, boot});
       t = t1;
     }
@@ -624,9 +667,23 @@ int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0,
   return PG_OK;
 }
 
-int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1, int rb_first,
-                       int rb_stride, int64_t boot_rows, uint64_t* lists, void* workspace, size_t workspace_bytes,
+int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int parts, int64_t* row_begin,
+                    int64_t* row_end) {
+  PG_CHECK_ARG(rows > 0 && words > 0 && parts >= 1 && part >= 0 && part < parts && row_begin && row_end,
+               "bad band arguments");
+  const SymLayout lay = sym_layout(rows, words);
+  int t0 = 0, t1 = 0;
+  sym_band(lay, rows, boot_rows, part, parts, &t0, &t1);
+  *row_begin = static_cast<int64_t>(t0) * lay.tile_cols;
+  *row_end = std::min<int64_t>(rows, static_cast<int64_t>(t1) * lay.tile_cols);
+  return PG_OK;
+}
+
+int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1, int part, int parts,
+                       int mode, int64_t boot_rows, uint64_t* lists, void* workspace, size_t workspace_bytes,
                        void* stream) {
+  const int rb_first = part, rb_stride = parts;
+  PG_CHECK_ARG(mode == 0 || mode == 1, "bad partition mode %d", mode);
   PG_CHECK_ARG(table && lists && workspace, "null pointer");
   PG_CHECK_ARG(rows > 0 && rows < (1ll << 31), "row count out of range");
   PG_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "table must be 16-byte aligned");
@@ -654,16 +711,18 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   prm.glast = reinterpret_cast<unsigned long long*>(wsb);
   prm.glock = reinterpret_cast<unsigned*>(wsb + lay.gnt_bytes);
   prm.items = reinterpret_cast<const SymItem*>(wsb + lay.item_off);
-  prm.stats = reinterpret_cast<unsigned long long*>(wsb + lay.stats_off);
+  unsigned long long* stats_dev = reinterpret_cast<unsigned long long*>(wsb + lay.stats_off);
+  const bool want_stats = std::getenv("PG_SYM_STATS") != nullptr;
+  prm.stats = want_stats ? stats_dev : nullptr;
   if (const char* ev = std::getenv("PG_SYM_NOCOL")) prm.no_col = std::atoi(ev);
   SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs};
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;
-  const std::vector<SymItem> items = sym_plan(lay, rb_first, rb_stride, resident, boot_rows);
+  const std::vector<SymItem> items = sym_plan(lay, rows, part, parts, mode, resident, boot_rows);
   sym_init_kernel<<<num_sms() * 4, 256, 0, cs>>>(prm.glist, static_cast<long long>(rows) * k1, prm.glast,
                                                  static_cast<long long>(lay.n_tiles) * lay.tile_cols, prm.glock, rows,
-                                                 prm.stats, k1, boot_rows > 0 ? 1 : 0);
+                                                 stats_dev, k1, boot_rows > 0 ? 1 : 0);
   PG_LAUNCH_CHECK();
   if (items.empty()) return PG_OK;
   PG_CHECK_ARG(items.size() * sizeof(SymItem) <= lay.item_bytes_max, "item table overflow (%zu items)", items.size());
@@ -674,13 +733,13 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
     SweepTimer t(cs);
     rc = dispatch_sym(planes, words, prm, l, nullptr);
   }
-  if (rc == PG_OK && std::getenv("PG_SYM_STATS")) {
+  if (rc == PG_OK && want_stats) {
     unsigned long long st[8];
-    PG_CUDA(cudaMemcpyAsync(st, prm.stats, sizeof(st), cudaMemcpyDeviceToHost, cs));
+    PG_CUDA(cudaMemcpyAsync(st, stats_dev, sizeof(st), cudaMemcpyDeviceToHost, cs));
     PG_CUDA(cudaStreamSynchronize(cs));
-    fprintf(stderr, "[pg sym] rows=%lld boot=%lld items=%zu grid=%d | column calls %llu, locks %llu, lock spins %llu, "
-            "list writes %llu | row inserts %llu\n", static_cast<long long>(rows), static_cast<long long>(boot_rows),
-            items.size(), l.grid, st[0], st[1], st[2], st[3], st[4]);
+    fprintf(stderr, "[pg sym] rows=%lld boot=%lld items=%zu grid=%d | locks %llu, lock spins %llu, list writes %llu | row "
+            "inserts %llu\n", static_cast<long long>(rows), static_cast<long long>(boot_rows), items.size(), l.grid,
+            st[1], st[2], st[3], st[4]);
   }
   return rc;
 }

@@ -41,7 +41,7 @@ struct SymParams {
   unsigned long long* glist;  // [rows][k1] ascending keys, ~0 = empty
   unsigned long long* glast;  // [n_tiles * tile_cols] filter word per row: (~tau)<<32 | index of the last key
   unsigned* glock;            // [rows]
-  unsigned long long* stats;  // [8] slow-path counters: column calls, locks, lock spins, list writes, row calls
+  unsigned long long* stats;  // null, or [8] slow-path counters: -, locks, lock spins, list writes, row inserts
   int no_col;                 // experiments: skip the column side (results are then incomplete)
   long long boot_rows;        // rows [0, boot_rows) were swept one-sided against every row beforehand
 };
@@ -66,15 +66,15 @@ __device__ __forceinline__ int mad_s32(int a, unsigned b, int c) {
 }
 
 // Warp-cooperative merge of up to 32 candidate keys (one per lane, `is_cand`) into the global
-// list of row j.  All lanes call it with the same j.  Lock-free early out against the list's
-// current last key; otherwise the list is edited in registers under the row's lock.
+// list of row j.  All lanes call it with the same j.  The list is edited in registers under the
+// row's lock; keys that no longer beat the current last key simply do not get in.
 static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long long j, unsigned long long key, bool is_cand,
                                            int lane) {
   const int k1 = prm.k1;
   unsigned long long* lst = prm.glist + static_cast<size_t>(j) * k1;
-  const unsigned long long last0 = ld_cg_u64(lst + (k1 - 1));
-  unsigned cand = __ballot_sync(0xffffffffu, is_cand && key < last0);
-  if (lane == 0) atomicAdd(prm.stats + 0, 1ull);
+  // the caller's filter (a snapshot at most a few tiles old) already passed: take the lock
+  // right away, the merge below re-checks every key against the current list
+  unsigned cand = __ballot_sync(0xffffffffu, is_cand);
   if (cand == 0u) return;
   unsigned* lock = prm.glock + j;
   if (lane == 0) {
@@ -84,8 +84,10 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
       if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
     }
     __threadfence();
-    atomicAdd(prm.stats + 1, 1ull);
-    if (spins) atomicAdd(prm.stats + 2, static_cast<unsigned long long>(spins));
+    if (prm.stats != nullptr) {
+      atomicAdd(prm.stats + 1, 1ull);
+      if (spins) atomicAdd(prm.stats + 2, static_cast<unsigned long long>(spins));
+    }
   }
   __syncwarp();
   unsigned long long e = lane < k1 ? ld_cg_u64(lst + lane) : ~0ull;
@@ -107,7 +109,7 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
     const unsigned long long last = __shfl_sync(0xffffffffu, e, k1 - 1);
     if (lane == 0) {
       st_cg_u64(prm.glast + j, sym_filter_word(last));
-      atomicAdd(prm.stats + 3, 1ull);
+      if (prm.stats != nullptr) atomicAdd(prm.stats + 3, 1ull);
     }
     __threadfence();
   }
@@ -120,7 +122,7 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
 static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists, int k1, unsigned cand, unsigned dv,
                                           unsigned col, int lane, int tau_seed, int tau,
                                           unsigned long long* stats) {
-  if (lane == 0) atomicAdd(stats + 4, static_cast<unsigned long long>(__popc(cand)));
+  if (stats != nullptr && lane == 0) atomicAdd(stats + 4, static_cast<unsigned long long>(__popc(cand)));
   while (cand) {
     const int src = __ffs(cand) - 1;
     cand &= cand - 1;

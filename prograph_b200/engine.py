@@ -164,9 +164,10 @@ class CudaEngine:
                                              self._stream()))
         return lists
 
-    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0):
-        """Symmetric sweep of `table` against itself (pg_hamming_knn_sym): this rank's row blocks
-        rank, rank+world, ...; returns the (rows, k1) int64 tensor of sorted keys
+    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0, mode=0):
+        """Symmetric sweep of `table` against itself (pg_hamming_knn_sym): this rank's piece of the
+        triangle (mode 0: row blocks rank, rank+world, ...; mode 1: a band of stream rows);
+        returns the (rows, k1) int64 tensor of sorted keys
         distance<<32 | index (-1 = empty) this rank found for EVERY row of the table.  `lists`:
         the bootstrap lists of all rows when boot_rows > 0 (updated in place)."""
         self._sym_check(table, k1)
@@ -177,9 +178,16 @@ class CudaEngine:
         nbytes = int(self.lib.pg_knn_sym_workspace_bytes(table.rows, table.words))
         ws = self.empty((nbytes,), torch.uint8)
         L.check(self.lib.pg_hamming_knn_sym(_ptr(table.data), table.rows, table.planes, table.words, int(k1),
-                                            int(rank), int(world), int(boot_rows), _ptr(lists), _ptr(ws), nbytes,
-                                            self._stream()))
+                                            int(rank), int(world), int(mode), int(boot_rows), _ptr(lists), _ptr(ws),
+                                            nbytes, self._stream()))
         return lists
+
+    def sym_band(self, rows, words, boot_rows, rank, world):
+        """Stream rows [begin, end) of this rank's band (mode 1 of hamming_knn_sym)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        L.check(self.lib.pg_knn_sym_band(int(rows), int(words), int(boot_rows), int(rank), int(world), C.byref(a),
+                                         C.byref(b)))
+        return a.value, b.value
 
     def knn_lists_finalize(self, lists, row0, rows, k, drop=1, similarity=False):
         """lists: (n_lists, N, k1) or (N, k1) key lists -> (idx, w) of rows [row0,row0+rows)."""

@@ -245,9 +245,9 @@ def hamming_knn_graph(eng, packed, k, similarity, rank, world, group):
     """kNN lists of EVERY row of `packed` against itself (prograph.py:755-765), on every rank.
 
     Large tables take the symmetric sweep: d(i,j) == d(j,i), so each unordered pair is evaluated
-    once and offered to both rows' lists.  Ranks own interleaved 256-row blocks of the triangle;
-    the per-rank candidate lists of all rows are all-gathered (NCCL) and merged -- the exchange
-    step of this path.  Small tables and long lists take the one-sided sweep on this rank's row
+    once and offered to both rows' lists.  Ranks own bands of stream rows of the triangle (equal
+    numbers of pair evaluations); the per-rank candidate lists of all rows are all-gathered
+    (NCCL) and merged -- the exchange step of this path.  Small tables and long lists take the one-sided sweep on this rank's row
     block followed by the all-gather of the result rows."""
     n = packed.rows
     kk = min(k, n - 1)
@@ -272,7 +272,9 @@ def _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group):
         row0, rows = _shard.row_range(n, rank, world)
         seed = eng.hamming_knn_boot(packed, row0, rows, boot, k1)
         seed = _shard.gather_rows((seed,), n, rank, world, group, eng)[0].contiguous()
-    lists = eng.hamming_knn_sym(packed, k1, rank, world, lists=seed, boot_rows=boot)
+    # several ranks: column bands (mode 1) -- all column-side candidates of a row meet on one rank,
+    # so its filter tightens as fast as on a single GPU
+    lists = eng.hamming_knn_sym(packed, k1, rank, world, lists=seed, boot_rows=boot, mode=1 if sharded else 0)
     if sharded:
         lists = _shard.all_gather_stack(lists, world, group)          # (world, n, k1)
     return eng.knn_lists_finalize(lists, 0, n, kk, 1, similarity)

@@ -58,25 +58,37 @@ class CheckerEngine:
         keys = self._keys(D, np.broadcast_to(np.arange(boot_rows), D.shape))
         return torch.from_numpy(np.ascontiguousarray(self._smallest(keys, k1)))
 
-    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0):
-        """Candidates this rank sees: row blocks rank, rank+world, ... of 256 rows, each against
-        the stream rows from its own block on (row side) and feeding the later blocks' rows
-        (column side); blocks of the bootstrap rows start behind them and have no column side."""
+    def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0, mode=0):
+        """Candidates this rank sees.  Every 256-row block sweeps the stream rows from its own
+        block on (row side) and feeds the rows of later blocks (column side); blocks of the
+        bootstrap rows start behind them and have no column side.  mode 0: this rank takes blocks
+        rank, rank+world, ...; mode 1: all blocks, restricted to the rank's band of stream rows
+        (the band limits come from the library's host-side planner, pg_knn_sym_band)."""
         n = table.rows
         self.sym_calls = getattr(self, "sym_calls", 0) + 1
+        self.sym_modes = getattr(self, "sym_modes", []) + [mode]
         cand = [[] for _ in range(n)]
         if boot_rows:
             for r in range(n):
                 cand[r].extend(int(v) for v in lists[r].numpy() if v != -1)
+        band = (0, n)
+        if mode == 1:
+            import ctypes as C
+            from prograph_b200 import _lib
+            a, b = C.c_int64(0), C.c_int64(0)
+            _lib.check(_lib.load().pg_knn_sym_band(n, table.words, int(boot_rows), rank, world, C.byref(a), C.byref(b)))
+            band = (a.value, b.value)
         T = table.tokens
-        for rb in range(rank, -(-n // 256), world):
+        blocks = range(-(-n // 256)) if mode == 1 else range(rank, -(-n // 256), world)
+        for rb in blocks:
             a, b = rb * 256, min(n, rb * 256 + 256)
-            start = boot_rows if a < boot_rows else a
-            if start >= n:
+            start = max(boot_rows if a < boot_rows else a, band[0])
+            end = band[1]
+            if start >= end:
                 continue
-            D = O.hamming(T[start:], T[a:b])                      # (b-a, n-start)
+            D = O.hamming(T[start:end], T[a:b])                      # (b-a, end-start)
             for i in range(a, b):
-                for j in range(start, n):
+                for j in range(start, end):
                     d = int(D[i - a, j - start])
                     cand[i].append((d << 32) | j)
                     if a >= boot_rows and j >= b:

@@ -35,19 +35,20 @@ def mutational(rng, n, L, alphabet=20, max_mut=8):
     return X.astype(np.int64)
 
 
-def sym_knn(eng, tab, k, drop=1, world=1, boot=0, similarity=False):
-    """All ranks of a `world`-GPU build emulated on one device, merged like graph._hamming_knn_sym."""
+def sym_knn(eng, tab, k, drop=1, world=1, boot=0, similarity=False, mode=0):
+    """All ranks of a `world`-GPU build emulated on one device, merged like graph._hamming_knn_sym
+    (mode 0: interleaved row blocks per rank, mode 1: bands of stream rows per rank)."""
     k1 = k + drop
     seed = eng.hamming_knn_boot(tab, 0, tab.rows, boot, k1) if boot else None
-    lists = [eng.hamming_knn_sym(tab, k1, r, world, lists=seed.clone() if boot else None, boot_rows=boot)
+    lists = [eng.hamming_knn_sym(tab, k1, r, world, lists=seed.clone() if boot else None, boot_rows=boot, mode=mode)
              for r in range(world)]
     return eng.knn_lists_finalize(torch.stack(lists), 0, tab.rows, k, drop, similarity)
 
 
 @pytest.mark.parametrize("L,k,alphabet", [(3, 3, 4), (20, 16, 2), (56, 16, 20), (100, 5, 20), (256, 16, 20),
                                           (256, 31, 20), (300, 16, 20), (512, 7, 20), (64, 16, 200)])
-@pytest.mark.parametrize("world,boot", [(1, 0), (1, 512), (2, 1024), (3, 0)])
-def test_symmetric_knn_uniform_ties(eng, L, k, alphabet, world, boot):
+@pytest.mark.parametrize("world,boot,mode", [(1, 0, 0), (1, 512, 0), (2, 1024, 0), (3, 0, 1), (4, 512, 1)])
+def test_symmetric_knn_uniform_ties(eng, L, k, alphabet, world, boot, mode):
     """iid-uniform tokens: the k-th place of almost every row is a tie, so the (distance, index)
     order of the merged row / column candidates is what is being tested."""
     rng = np.random.default_rng(L * 131 + k)
@@ -56,7 +57,7 @@ def test_symmetric_knn_uniform_ties(eng, L, k, alphabet, world, boot):
     tab = eng.pack(X)
     D = O.hamming(X, X)
     ri, rw = O.knn_from_distances(D, k)
-    idx, w = sym_knn(eng, tab, k, world=world, boot=boot)
+    idx, w = sym_knn(eng, tab, k, world=world, boot=boot, mode=mode)
     np.testing.assert_array_equal(np_(idx), ri)
     np.testing.assert_array_equal(np_(w), rw)
     if world == 1:
@@ -73,8 +74,9 @@ def test_symmetric_knn_ragged_sizes_and_duplicates(eng, n):
     tab = eng.pack(X.astype(np.uint8))
     k = min(16, n - 1)
     ri, rw = O.knn_from_distances(O.hamming(X, X), k)
-    for world, boot in ((1, 0), (2, 0), (1, 512 if n >= 512 else 0)):
-        idx, w = sym_knn(eng, tab, k, world=world, boot=boot)
+    for world, boot, mode in ((1, 0, 0), (2, 0, 0), (1, 512 if n >= 512 else 0, 0), (2, 0, 1),
+                              (8, 512 if n >= 512 else 0, 1)):
+        idx, w = sym_knn(eng, tab, k, world=world, boot=boot, mode=mode)
         np.testing.assert_array_equal(np_(idx), ri)
         np.testing.assert_array_equal(np_(w), rw)
     # nearest neighbour including the row itself (drop = 0): position 0 is the smallest (d, index)

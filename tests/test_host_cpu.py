@@ -188,14 +188,14 @@ def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
     knn = graph.build_neighbours(X, k=k, engine=eng)
     sim = graph.build_neighbours(X, k=k, similarity=True, engine=eng)
     np.savez(os.path.join(tmpdir, f"r{rank}.npz"), idx=knn.idx, w=knn.w, sidx=sim.idx, sw=sim.w,
-             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n)]))
+             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n), min(eng.sym_modes)]))
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("n,boot_div", [(700, 8), (1301, 2)])
 def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
-    """world_size 2 on CPU, symmetric kNN build: ranks take interleaved row blocks of the triangle,
-    exchange their candidate lists (all-gather) and merge; with and without the bootstrap pass."""
+    """world_size 2 on CPU, symmetric kNN build: ranks take column bands of the triangle, exchange
+    their candidate lists (all-gather) and merge; with and without the bootstrap pass."""
     import torch.multiprocessing as mp
     from oracle import prograph_oracle as O
     k, world = 5, 2
@@ -213,3 +213,4 @@ def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
         np.testing.assert_array_equal(z["sw"], sw)
         assert z["calls"][0] == 2                       # both builds went through the symmetric sweep
         assert z["calls"][1] == (512 if boot_div == 2 else 0)
+        assert z["calls"][2] == 1                       # ranks took column bands of the triangle

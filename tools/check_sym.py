@@ -30,7 +30,7 @@ def mutational(rng, n, L, alphabet=20, max_mut=8, dup=True):
     return X.astype(np.uint8)
 
 
-def run_sym(eng, tab, k, drop, world=1, similarity=False, boot=None):
+def run_sym(eng, tab, k, drop, world=1, similarity=False, boot=None, mode=0):
     k1 = k + drop
     if boot is None:
         boot = int(os.environ.get("PG_BOOT", "-1"))
@@ -38,7 +38,7 @@ def run_sym(eng, tab, k, drop, world=1, similarity=False, boot=None):
         boot = min(8192, tab.rows // 32 // 512 * 512)
     boot = min(boot, tab.rows // 512 * 512)
     seed = eng.hamming_knn_boot(tab, 0, tab.rows, boot, k1) if boot else None
-    lists = [eng.hamming_knn_sym(tab, k1, r, world, lists=seed.clone() if boot else None, boot_rows=boot)
+    lists = [eng.hamming_knn_sym(tab, k1, r, world, lists=seed.clone() if boot else None, boot_rows=boot, mode=mode)
              for r in range(world)]
     return eng.knn_lists_finalize(torch.stack(lists), 0, tab.rows, k, drop, similarity)
 
@@ -90,8 +90,9 @@ def main():
             for boot in (0, 512, 2048):
                 if boot > X.shape[0]:
                     continue
-                si, sw = run_sym(eng, tab, kk, drop, world, boot=boot)
-                good &= bool(torch.equal(ri, si)) and bool(torch.equal(rw, sw))
+                for mode in (0, 1):
+                    si, sw = run_sym(eng, tab, kk, drop, world, boot=boot, mode=mode)
+                    good &= bool(torch.equal(ri, si)) and bool(torch.equal(rw, sw))
             ok &= good
             print(f"{name:28s} n={X.shape[0]:6d} planes={tab.planes} words={tab.words:2d} k={kk} world={world}: "
                   f"{'ok' if good else 'MISMATCH'}", flush=True)
