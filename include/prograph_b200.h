@@ -133,6 +133,26 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
 /* host only: the stream rows [row_begin, row_end) of band `part` of `parts` (mode 1) */
 int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int parts,
                     int64_t* row_begin, int64_t* row_end);
+/* Symmetric epsilon graph of a table against itself (prograph.py:731-753): one sweep over the
+ * triangle of unordered pairs appends BOTH directed edges of every pair whose distance passes the
+ * truth table `lut_host` (which must be one contiguous range of distances, else
+ * PG_ERR_UNSUPPORTED) to `keys` as  row << (idxbits+dbits) | column << dbits | distance.  Slots are
+ * handed out in chunks of 512; unused slots hold the sentinel ~0.  counters[0] (device) = slots
+ * reserved, counters[1] = edges; if counters[0] > capacity the buffer was too small (nothing is
+ * written past it) and the call is repeated with counters[0] slots.  part / parts / mode as in
+ * pg_hamming_knn_sym; workspace: pg_knn_sym_workspace_bytes.  */
+int pg_hamming_eps_sym(const uint32_t* table, int64_t rows, int planes, int words,
+                       const uint32_t* lut_host, int lut_words, int part, int parts, int mode,
+                       uint64_t* keys, int64_t capacity, uint64_t* counters,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* sort n_keys edge keys (sentinels included; keys_alt: scratch of the same size) by (row, column)
+ * and write the CSR arrays of the first nnz: indptr[rows+1], out_idx int64, out_w per `weight`
+ * (int64 distance or float32 similarity).  Replaces prod_neighbours + merge/fill, prograph.py:626-654,
+ * 743-753.  */
+int pg_edge_keys_to_csr(uint64_t* keys, int64_t n_keys, uint64_t* keys_alt, int64_t rows, int words,
+                        int64_t nnz, int weight, int64_t* indptr, int64_t* out_idx, void* out_w,
+                        void* stream);
+
 /* merge n_lists key lists per row (list s of row r at lists[s*list_stride + r*k1]), drop the first
  * `drop` merged positions and write the next k as out_idx[(r-row0)*k + j] / out_w per `weight`
  * for rows [row0, row0+rows); missing entries get idx = -1 (as pg_hamming_knn).  */

@@ -44,6 +44,8 @@ SIGNATURES = {
     "pg_knn_sym_workspace_bytes": (_sz, [_i64, _i]),
     "pg_hamming_knn_boot": (_i, [_vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pg_hamming_knn_sym": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _i, _i64, _vp, _vp, _sz, _vp]),
+    "pg_hamming_eps_sym": (_i, [_vp, _i64, _i, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "pg_edge_keys_to_csr": (_i, [_vp, _i64, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "pg_knn_sym_band": (_i, [_i64, _i, _i64, _i, _i, _pi64, _pi64]),
     "pg_knn_lists_finalize": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pg_hamming_eps_count": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -6,6 +6,7 @@
 
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 #include <cstdlib>
@@ -445,6 +446,41 @@ __global__ void knn_lists_finalize_kernel(const unsigned long long* __restrict__
   }
 }
 
+
+// ---- symmetric epsilon graph: edge keys -> CSR -----------------------------------------------
+struct EdgeKeyBits { int dbits, idxbits; };
+static EdgeKeyBits edge_key_bits(long long rows, int words) {
+  EdgeKeyBits b;
+  b.dbits = 1;
+  while ((1 << b.dbits) <= words * 32) ++b.dbits;          // distances 0 .. 32*words
+  b.idxbits = 1;
+  while ((1ll << b.idxbits) <= rows) ++b.idxbits;          // rows < 2^idxbits - 1: the all-ones row is the sentinel
+  return b;
+}
+
+__global__ void edge_decode_kernel(const unsigned long long* __restrict__ keys, long long nnz, long long rows, int dbits,
+                                   int idxbits, int weight, long long* __restrict__ indptr,
+                                   long long* __restrict__ out_idx, void* out_w) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (nnz == 0) {
+    for (long long x = e; x <= rows; x += static_cast<long long>(gridDim.x) * blockDim.x) indptr[x] = 0;
+    return;
+  }
+  if (e >= nnz) return;
+  const unsigned long long key = keys[e];
+  const unsigned long long imask = (1ull << idxbits) - 1ull;
+  const long long row = static_cast<long long>(key >> (dbits + idxbits));
+  const long long col = static_cast<long long>((key >> dbits) & imask);
+  const int d = static_cast<int>(key & ((1ull << dbits) - 1ull));
+  out_idx[e] = col;
+  write_weight(out_w, e, d, weight);
+  // row boundaries: indptr[x] = e for every row x in (row of edge e-1, row of edge e]
+  const long long prev = e > 0 ? static_cast<long long>(keys[e - 1] >> (dbits + idxbits)) : -1;
+  for (long long x = prev + 1; x <= row; ++x) indptr[x] = e;
+  if (e == nnz - 1)
+    for (long long x = row + 1; x <= rows; ++x) indptr[x] = nnz;
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -715,7 +751,7 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   const bool want_stats = std::getenv("PG_SYM_STATS") != nullptr;
   prm.stats = want_stats ? stats_dev : nullptr;
   if (const char* ev = std::getenv("PG_SYM_NOCOL")) prm.no_col = std::atoi(ev);
-  SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs};
+  SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs, SYM_KNN};
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;
@@ -743,6 +779,100 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   }
   return rc;
 }
+
+int pg_hamming_eps_sym(const uint32_t* table, int64_t rows, int planes, int words, const uint32_t* lut_host,
+                       int lut_words, int part, int parts, int mode, uint64_t* keys, int64_t capacity,
+                       uint64_t* counters, void* workspace, size_t workspace_bytes, void* stream) {
+  PG_CHECK_ARG(table && keys && counters && workspace && lut_host, "null pointer");
+  PG_CHECK_ARG(rows > 0 && rows < (1ll << 27), "row count out of range for packed edge keys");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "table must be 16-byte aligned");
+  PG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  PG_CHECK_ARG(parts >= 1 && part >= 0 && part < parts && (mode == 0 || mode == 1), "bad partition %d/%d mode %d", part,
+               parts, mode);
+  PG_CHECK_ARG(lut_words >= 1 && lut_words <= kMaxLutWords && lut_words * 32 > words * 32, "lut must cover distances 0..%d",
+               words * 32);
+  PG_CHECK_ARG(capacity >= 0, "negative capacity");
+  if (!sym_shape_ok(planes, words)) {
+    set_error("symmetric sweep: planes/words %d/%d not covered", planes, words);
+    return PG_ERR_UNSUPPORTED;
+  }
+  SymParams prm;
+  memset(&prm, 0, sizeof(prm));
+  unsigned span = 0;
+  if (!lut_as_range(lut_host, lut_words, &prm.lo, &span)) {
+    set_error("symmetric epsilon sweep needs a contiguous distance range");
+    return PG_ERR_UNSUPPORTED;
+  }
+  prm.hi = prm.lo == 0x7fffffff ? -1 : prm.lo + static_cast<int>(span);
+  if (prm.lo == 0x7fffffff) prm.lo = 1 << 20;            // empty predicate: nothing passes
+  const SymLayout lay = sym_layout(rows, words);
+  PG_CHECK_ARG(workspace_bytes >= lay.total, "workspace too small: %zu < %zu", workspace_bytes, lay.total);
+  const EdgeKeyBits kb = edge_key_bits(rows, words);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  prm.tab = table;
+  prm.rows = rows;
+  prm.one = 1u;
+  prm.k1 = 1;
+  prm.items = reinterpret_cast<const SymItem*>(wsb + lay.item_off);
+  prm.sh_col = kb.dbits;
+  prm.sh_row = kb.dbits + kb.idxbits;
+  prm.keys = reinterpret_cast<unsigned long long*>(keys);
+  prm.capacity = capacity;
+  prm.counters = reinterpret_cast<unsigned long long*>(counters);
+  SymLaunch l{0, 0, cs, SYM_EPS};
+  int resident = 0;
+  int rc = dispatch_sym(planes, words, prm, l, &resident);
+  if (rc != PG_OK) return rc;
+  const std::vector<SymItem> items = sym_plan(lay, rows, part, parts, mode, resident, 0);
+  PG_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(uint64_t), cs));
+  if (items.empty()) return PG_OK;
+  PG_CHECK_ARG(items.size() * sizeof(SymItem) <= lay.item_bytes_max, "item table overflow (%zu items)", items.size());
+  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off, items.data(), items.size() * sizeof(SymItem), cudaMemcpyHostToDevice, cs));
+  prm.n_items = static_cast<int>(items.size());
+  l.grid = static_cast<int>(std::min<size_t>(items.size(), static_cast<size_t>(resident)));
+  {
+    SweepTimer t(cs);
+    rc = dispatch_sym(planes, words, prm, l, nullptr);
+  }
+  return rc;
+}
+
+int pg_edge_keys_to_csr(uint64_t* keys, int64_t n_keys, uint64_t* keys_alt, int64_t rows, int words, int64_t nnz,
+                        int weight, int64_t* indptr, int64_t* out_idx, void* out_w, void* stream) {
+  PG_CHECK_ARG(indptr && rows > 0 && n_keys >= 0 && nnz >= 0 && nnz <= n_keys, "bad edge list geometry");
+  PG_CHECK_ARG(n_keys < (1ll << 31), "too many edge slots for one sort");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32, "edges carry int64 distances or float32 similarities");
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  const EdgeKeyBits kb = edge_key_bits(rows, words);
+  const unsigned long long* sorted = reinterpret_cast<const unsigned long long*>(keys);
+  if (n_keys > 0) {
+    PG_CHECK_ARG(keys && keys_alt && (nnz == 0 || (out_idx && out_w)), "null key / output buffers");
+    // (row, column) order = the ascending-index rows of prograph.py:736-753; the distance rides in
+    // the low bits and the sentinels (all ones) end up behind the last edge
+    cub::DoubleBuffer<unsigned long long> buf(reinterpret_cast<unsigned long long*>(keys),
+                                              reinterpret_cast<unsigned long long*>(keys_alt));
+    size_t tmp_bytes = 0;
+    PG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, buf, static_cast<int>(n_keys), kb.dbits,
+                                           kb.dbits + 2 * kb.idxbits, cs));
+    void* tmp = nullptr;
+    PG_CUDA(temp_alloc(&tmp, tmp_bytes, cs));
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, buf, static_cast<int>(n_keys), kb.dbits,
+                                                   kb.dbits + 2 * kb.idxbits, cs);
+    count_launch();
+    cudaFreeAsync(tmp, cs);
+    if (e != cudaSuccess) { set_error("cub radix sort failed: %s", cudaGetErrorString(e)); return PG_ERR_CUDA; }
+    sorted = buf.Current();
+  }
+  const int threads = 256;
+  const long long work = nnz > 0 ? nnz : rows + 1;
+  edge_decode_kernel<<<static_cast<unsigned>(std::min<long long>(ceil_div(work, threads), 1 << 30)), threads, 0, cs>>>(
+      sorted, nnz, rows, kb.dbits, kb.idxbits, weight, reinterpret_cast<long long*>(indptr),
+      reinterpret_cast<long long*>(out_idx), out_w);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
 
 int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1,
                           int k, int drop, int weight, int64_t* out_idx, void* out_w, void* stream) {

@@ -44,6 +44,13 @@ struct SymParams {
   unsigned long long* stats;  // null, or [8] slow-path counters: -, locks, lock spins, list writes, row inserts
   int no_col;                 // experiments: skip the column side (results are then incomplete)
   long long boot_rows;        // rows [0, boot_rows) were swept one-sided against every row beforehand
+  // epsilon mode (SYM_EPS): edge <=> lo <= d <= hi; edges are appended to `keys` as
+  // row << sh_row | column << sh_col | d, both directions of every unordered pair
+  int lo, hi;
+  int sh_row, sh_col;
+  unsigned long long* keys;
+  long long capacity;            // slots in `keys`
+  unsigned long long* counters;  // [0] slots reserved (multiples of kEdgeChunk), [1] edges written or dropped
 };
 
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
@@ -152,12 +159,47 @@ struct SymCursor {
   }
 };
 
-template <int P, int W>
+enum SymMode { SYM_KNN = 0, SYM_EPS = 1 };
+
+constexpr int kEdgeChunk = 512;   // edge slots a warp reserves at a time (one global atomic per chunk)
+
+// Epsilon mode: the warp appends the edges of one stream row.  `hit` lanes emit key_fwd (own row ->
+// stream row) and, outside the diagonal block, key_rev (stream row -> own row).  Slots come from
+// warp-private chunks of the global key buffer; unused slots of a closed chunk hold the sentinel ~0.
+// Past the buffer's capacity nothing is written, but the reservations keep counting so that the
+// caller learns the size it needs.
+static __device__ __noinline__ void sym_emit(const SymParams& prm, bool hit, unsigned long long key_fwd,
+                                             unsigned long long key_rev, bool both, int lane, long long& ch_base,
+                                             int& ch_used, unsigned long long& n_real) {
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (m == 0u) return;
+  const int mult = both ? 2 : 1;
+  const int n = __popc(m) * mult;
+  if (ch_base == -1 || ch_used + n > kEdgeChunk) {
+    if (ch_base >= 0)
+      for (int sl = ch_used + lane; sl < kEdgeChunk; sl += 32) prm.keys[ch_base + sl] = ~0ull;
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(prm.counters, static_cast<unsigned long long>(kEdgeChunk));
+    b = __shfl_sync(0xffffffffu, b, 0);
+    ch_base = (static_cast<long long>(b) + kEdgeChunk <= prm.capacity) ? static_cast<long long>(b) : -2;
+    ch_used = 0;
+  }
+  if (ch_base >= 0 && hit) {
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    unsigned long long* at = prm.keys + ch_base + ch_used + rank * mult;
+    at[0] = key_fwd;
+    if (both) at[1] = key_rev;
+  }
+  ch_used += n;
+  n_real += static_cast<unsigned long long>(n);
+}
+
+template <int P, int W, int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __grid_constant__ SymParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
   constexpr uint32_t STAGE_BYTES = BN * COLW * 4;
-  constexpr uint32_t TAU_BYTES = BN * 8;
+  constexpr uint32_t TAU_BYTES = MODE == SYM_KNN ? BN * 8 : 0;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* stage_mem = reinterpret_cast<uint32_t*>(smem_raw);
@@ -172,6 +214,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   const int k1 = prm.k1;
   unsigned long long* warp_lists = lists + static_cast<size_t>(warp << 5) * k1;
 
+  auto fill_stage = [&](int s, int t) {   // one elected thread: tile t (and its filter words) into ring stage s
+    mbar_arrive_expect_tx(&full[s], STAGE_BYTES + TAU_BYTES);
+    bulk_g2s(stage_mem + s * (BN * COLW), prm.tab + static_cast<size_t>(t) * BN * COLW, STAGE_BYTES, &full[s]);
+    if constexpr (MODE == SYM_KNN) bulk_g2s(taus + s * BN, prm.glast + static_cast<size_t>(t) * BN, TAU_BYTES, &full[s]);
+  };
+
   SymCursor la;
   la.start(blockIdx.x, prm);
   if (tid == 0) {
@@ -185,17 +233,17 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   __syncthreads();
 #pragma unroll 1
   for (int s = 0; s < kStages; ++s) {
-    if (tid == 0 && la.valid(prm)) {
-      mbar_arrive_expect_tx(&full[s], STAGE_BYTES + TAU_BYTES);
-      bulk_g2s(stage_mem + s * (BN * COLW), prm.tab + static_cast<size_t>(la.t) * BN * COLW, STAGE_BYTES, &full[s]);
-      bulk_g2s(taus + s * BN, prm.glast + static_cast<size_t>(la.t) * BN, TAU_BYTES, &full[s]);
-    }
+    if (tid == 0 && la.valid(prm)) fill_stage(s, la.t);
     if (la.valid(prm)) la.advance(prm, gridDim.x);
   }
 
   int stage = 0;
   uint32_t phase = 0;
   const unsigned one = prm.one;
+  // epsilon mode: the warp's current chunk of the edge buffer
+  long long ch_base = -1;
+  int ch_used = 0;
+  unsigned long long n_real = 0;
 
   for (int ii = blockIdx.x; ii < prm.n_items; ii += gridDim.x) {
     const int4 it = __ldg(reinterpret_cast<const int4*>(prm.items) + ii);
@@ -209,15 +257,16 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
 #pragma unroll
       for (int j = 0; j < COLW; ++j) q[j] = valid ? __ldg(src + j) : 0u;
     }
-    // the row's global list already bounds what can still matter: ties at its last distance
+    const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
+    // kNN: the row's global list already bounds what can still matter: ties at its last distance
     // stay admissible (the index decides), hence the +1
-    int tau_seed = 0;
-    if (valid) {
-      const int g = ~static_cast<int>(ld_cg_u64(prm.glast + r) >> 32);
-      tau_seed = g >= kTauInf ? kTauInf : g + 1;
-    }
-    int tau = tau_seed;
-    {
+    int tau_seed = 0, tau = 0;
+    if constexpr (MODE == SYM_KNN) {
+      if (valid) {
+        const int g = ~static_cast<int>(ld_cg_u64(prm.glast + r) >> 32);
+        tau_seed = g >= kTauInf ? kTauInf : g + 1;
+      }
+      tau = tau_seed;
       unsigned long long* mine = lists + static_cast<size_t>(tid) * k1;
       for (int j = 0; j < k1; ++j) mine[j] = ~0ull;
     }
@@ -226,6 +275,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
     const unsigned vmask = (valid && !boot && !prm.no_col) ? 0xffffffffu : 0u;
     const long long diag_begin = boot ? prm.boot_rows : static_cast<long long>(rb) * kConsumers;
     const long long diag_end = boot ? (1ll << 40) : diag_begin + kConsumers;
+    // epsilon mode: edge  <=>  lo <= d <= hi; an invalid own row gets an unreachable lower bound
+    const int nlo = valid ? -prm.lo : -(1 << 28);
+    const int hi = prm.hi;
+    const unsigned mone = 0u - one;
     __syncwarp();
 
     for (int t = t0; t < t1; ++t) {
@@ -237,62 +290,71 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
       int c = static_cast<int>(min(static_cast<long long>(ncols), max(0ll, diag_begin - col0)));
       const int c_mid = static_cast<int>(min(static_cast<long long>(ncols), max(static_cast<long long>(c), diag_end - col0)));
 
+      // one stream row behind the vote (rare): kNN serves both lists, epsilon appends the edges
+      auto rare = [&](int dv, int cc_, bool col_on) {
+        const unsigned col = static_cast<unsigned>(col0 + cc_);
+        if constexpr (MODE == SYM_KNN) {
+          const unsigned rc = __ballot_sync(0xffffffffu, dv < tau);
+          if (rc) tau = sym_serve_row(warp_lists, k1, rc, static_cast<unsigned>(dv), col, lane, tau_seed, tau, prm.stats);
+          if (col_on) {
+            // exact test against the snapshot of row col's last key: ties are decided by the index
+            const unsigned long long fw = tnt[cc_];
+            const unsigned long long lastk = (static_cast<unsigned long long>(~static_cast<unsigned>(fw >> 32)) << 32) |
+                                             (fw & 0xffffffffull);
+            const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(dv)) << 32) |
+                                            static_cast<unsigned>(r);
+            const bool cc = vmask != 0u && mine < lastk;
+            if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
+          }
+        } else {
+          const bool hit = (dv + nlo) >= 0 && dv <= hi;
+          const unsigned long long own = static_cast<unsigned long long>(r), oth = col;
+          const unsigned long long dd = static_cast<unsigned long long>(static_cast<unsigned>(dv));
+          sym_emit(prm, hit, (own << prm.sh_row) | (oth << prm.sh_col) | dd, (oth << prm.sh_row) | (own << prm.sh_col) | dd,
+                   col_on, lane, ch_base, ch_used, n_real);
+        }
+      };
+
 #pragma unroll 1
       for (; c + 4 <= ncols; c += 4) {
         int d0[1], d1[1], d2[1], d3[1];
-        const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
         ham_rows<P, W, 1>(qq, tile + (c + 0) * COLW, d0, one);
         ham_rows<P, W, 1>(qq, tile + (c + 1) * COLW, d1, one);
         ham_rows<P, W, 1>(qq, tile + (c + 2) * COLW, d2, one);
         ham_rows<P, W, 1>(qq, tile + (c + 3) * COLW, d3, one);
-        // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
-        const int4 na = *reinterpret_cast<const int4*>(tnt + c);
-        const int4 nb = *reinterpret_cast<const int4*>(tnt + c + 2);
-        const unsigned cm = c >= c_mid ? vmask : 0u;
-        // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
-        const int s0 = mad_s32(d0[0], one, -tau), s1 = mad_s32(d1[0], one, -tau);
-        const int s2 = mad_s32(d2[0], one, -tau), s3 = mad_s32(d3[0], one, -tau);
-        const int u0 = mad_s32(d0[0], one, na.y), u1 = mad_s32(d1[0], one, na.w);
-        const int u2 = mad_s32(d2[0], one, nb.y), u3 = mad_s32(d3[0], one, nb.w);
-        const int any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
+        int any;
+        if constexpr (MODE == SYM_KNN) {
+          // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
+          const int4 na = *reinterpret_cast<const int4*>(tnt + c);
+          const int4 nb = *reinterpret_cast<const int4*>(tnt + c + 2);
+          const unsigned cm = c >= c_mid ? vmask : 0u;
+          // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
+          const int s0 = mad_s32(d0[0], one, -tau), s1 = mad_s32(d1[0], one, -tau);
+          const int s2 = mad_s32(d2[0], one, -tau), s3 = mad_s32(d3[0], one, -tau);
+          const int u0 = mad_s32(d0[0], one, na.y), u1 = mad_s32(d1[0], one, na.w);
+          const int u2 = mad_s32(d2[0], one, nb.y), u3 = mad_s32(d3[0], one, nb.w);
+          any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
+        } else {
+          // sign bit set <=> no edge: d - lo < 0 or hi - d < 0; all four miss <=> the AND keeps the sign
+          const int a0 = mad_s32(d0[0], one, nlo), a1 = mad_s32(d1[0], one, nlo);
+          const int a2 = mad_s32(d2[0], one, nlo), a3 = mad_s32(d3[0], one, nlo);
+          const int b0 = mad_s32(d0[0], mone, hi), b1 = mad_s32(d1[0], mone, hi);
+          const int b2 = mad_s32(d2[0], mone, hi), b3 = mad_s32(d3[0], mone, hi);
+          any = ~((a0 | b0) & (a1 | b1) & (a2 | b2) & (a3 | b3));
+        }
         if (__any_sync(0xffffffffu, any < 0)) {
           const bool col_on = c >= c_mid;
-          auto rare = [&](int dv, int e) {
-            const unsigned col = static_cast<unsigned>(col0 + c + e);
-            const unsigned rc = __ballot_sync(0xffffffffu, dv < tau);
-            if (rc) tau = sym_serve_row(warp_lists, k1, rc, static_cast<unsigned>(dv), col, lane, tau_seed, tau, prm.stats);
-            if (col_on) {
-              // exact test against the snapshot of row col's last key: ties are decided by the index
-              const unsigned long long fw = tnt[c + e];
-              const unsigned long long lastk = (static_cast<unsigned long long>(~static_cast<unsigned>(fw >> 32)) << 32) |
-                                               (fw & 0xffffffffull);
-              const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(dv)) << 32) |
-                                              static_cast<unsigned>(r);
-              const bool cc = vmask != 0u && mine < lastk;
-              if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
-            }
-          };
-          rare(d0[0], 0);
-          rare(d1[0], 1);
-          rare(d2[0], 2);
-          rare(d3[0], 3);
+          rare(d0[0], c + 0, col_on);
+          rare(d1[0], c + 1, col_on);
+          rare(d2[0], c + 2, col_on);
+          rare(d3[0], c + 3, col_on);
         }
       }
 #pragma unroll 1
       for (; c < ncols; ++c) {   // ragged end of the table (last tile only)
         int d[1];
-        const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
         ham_rows<P, W, 1>(qq, tile + c * COLW, d, one);
-        const unsigned col = static_cast<unsigned>(col0 + c);
-        const unsigned rc = __ballot_sync(0xffffffffu, d[0] < tau);
-        if (rc) tau = sym_serve_row(warp_lists, k1, rc, static_cast<unsigned>(d[0]), col, lane, tau_seed, tau, prm.stats);
-        const unsigned long long fw = tnt[c];
-        const unsigned long long lastk = (static_cast<unsigned long long>(~static_cast<unsigned>(fw >> 32)) << 32) |
-                                         (fw & 0xffffffffull);
-        const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(d[0])) << 32) |
-                                        static_cast<unsigned>(r);
-        const bool cc = vmask != 0u && c >= c_mid && mine < lastk;
-        if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
+        rare(d[0], c, c >= c_mid);
       }
 
       __syncwarp();
@@ -301,10 +363,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
           done[stage] = 0;
           if (la.valid(prm)) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES + TAU_BYTES);
-            bulk_g2s(stage_mem + stage * (BN * COLW), prm.tab + static_cast<size_t>(la.t) * BN * COLW, STAGE_BYTES,
-                     &full[stage]);
-            bulk_g2s(taus + stage * BN, prm.glast + static_cast<size_t>(la.t) * BN, TAU_BYTES, &full[stage]);
+            fill_stage(stage, la.t);
           }
         }
       }
@@ -312,16 +371,23 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 
-    // merge the chunk's lists into the rows' global lists (ascending keys, one row at a time)
-    __syncwarp();
-    const long long wrow0 = static_cast<long long>(rb) * kConsumers + (warp << 5);
+    if constexpr (MODE == SYM_KNN) {
+      // merge the chunk's lists into the rows' global lists (ascending keys, one row at a time)
+      __syncwarp();
+      const long long wrow0 = static_cast<long long>(rb) * kConsumers + (warp << 5);
 #pragma unroll 1
-    for (int src = 0; src < 32; ++src) {
-      if (wrow0 + src >= prm.rows) break;
-      const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
-      sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
+      for (int src = 0; src < 32; ++src) {
+        if (wrow0 + src >= prm.rows) break;
+        const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
+        sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
+      }
+      __syncwarp();
     }
-    __syncwarp();
+  }
+  if constexpr (MODE == SYM_EPS) {
+    if (ch_base >= 0)
+      for (int sl = ch_used + lane; sl < kEdgeChunk; sl += 32) prm.keys[ch_base + sl] = ~0ull;
+    if (lane == 0 && n_real) atomicAdd(prm.counters + 1, n_real);
   }
 }
 
@@ -329,19 +395,17 @@ struct SymLaunch {
   int grid;
   size_t list_bytes;
   cudaStream_t stream;
+  int mode = SYM_KNN;
 };
 
-template <int P, int W>
-inline size_t sweep_sym_smem_bytes(size_t list_bytes) {
-  return static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 + TileCols<W>::value * 8) +
-         2 * kStages * sizeof(uint64_t) + list_bytes;
-}
 
 // grid == 0: only report the resident grid (CTAs) through *resident
-template <int P, int W>
-int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
-  auto kern = sweep_sym_kernel<P, W>;
-  const size_t smem = sweep_sym_smem_bytes<P, W>(l.list_bytes);
+template <int P, int W, int MODE>
+int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* resident) {
+  auto kern = sweep_sym_kernel<P, W, MODE>;
+  const size_t smem = static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 +
+                                                      (MODE == SYM_KNN ? TileCols<W>::value * 8 : 0)) +
+                      2 * kStages * sizeof(uint64_t) + l.list_bytes;
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 0;
   PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSweepThreads, smem));
@@ -351,6 +415,12 @@ int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
   kern<<<static_cast<unsigned>(l.grid), kSweepThreads, smem, l.stream>>>(prm);
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+template <int P, int W>
+int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
+  if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS>(prm, l, resident);
+  return launch_sweep_sym_mode<P, W, SYM_KNN>(prm, l, resident);
 }
 
 #define PG_DECL_SWEEP_SYM(P, W) int sweep_sym_p##P##_w##W(const SymParams& prm, const SymLaunch& l, int* resident);

@@ -225,6 +225,57 @@ class CudaEngine:
                                                  weight, _ptr(idx), _ptr(w), _ptr(ws), nbytes, self._stream()))
         return indptr, idx, w
 
+    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
+        """Mean number of edges per row over own rows [row0,row0+rows) (pg_hamming_eps_count on a
+        row sample): sizes the edge buffer of the symmetric sweep and tells dense graphs apart."""
+        self._check_pair(own, stream)
+        lut, lut_p = _host_u32(lut)
+        counts = self.empty((rows,), torch.int64)
+        nbytes = int(self.lib.pg_eps_workspace_bytes(int(rows), int(stream.rows), int(own.words)))
+        ws = self.empty((nbytes,), torch.uint8)
+        L.check(self.lib.pg_hamming_eps_count(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
+                                              stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(counts),
+                                              _ptr(ws), nbytes, self._stream()))
+        return float(counts.sum().item()) / rows
+
+    def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):
+        """Symmetric epsilon sweep (pg_hamming_eps_sym): this rank's piece of the triangle of
+        unordered pairs; returns (keys, edges): the reserved slots of the edge-key buffer (both
+        directions of every passing pair, sentinels -1 in unused slots) and the number of edges
+        among them.  Raises Unsupported when `lut` is not one contiguous range of distances."""
+        if table.words > 16 or (table.words > 8 and table.planes != 5) or table.rows >= (1 << 27):
+            raise L.Unsupported("shape not covered by the symmetric sweep")
+        lut, lut_p = _host_u32(lut)
+        nbytes = int(self.lib.pg_knn_sym_workspace_bytes(table.rows, table.words))
+        ws = self.empty((nbytes,), torch.uint8)
+        cap = int(capacity) if capacity is not None else 96 * table.rows // max(1, world) + (4 << 20)
+        counters = self.empty((2,), torch.int64)
+        for attempt in range(2):
+            self._check_edge_budget(cap)
+            keys = self.empty((cap,), torch.int64)
+            L.check(self.lib.pg_hamming_eps_sym(_ptr(table.data), table.rows, table.planes, table.words, lut_p, len(lut),
+                                                int(rank), int(world), int(mode), _ptr(keys), cap, _ptr(counters), _ptr(ws),
+                                                nbytes, self._stream()))
+            reserved, edges = (int(v) for v in counters.tolist())
+            if reserved <= cap:
+                return keys[:reserved], edges
+            del keys
+            cap = reserved                 # the sweep counted what it needs: run it once more
+        raise RuntimeError("symmetric epsilon sweep: edge buffer overflow after resizing")
+
+    def edge_keys_to_csr(self, keys, rows, words, nnz, similarity=False):
+        """Edge keys (any order, sentinels -1) -> CSR (indptr, idx, w) with rows ascending and, within
+        a row, ascending neighbour index (pg_edge_keys_to_csr)."""
+        keys = keys.contiguous()
+        alt = self.empty((keys.numel(),), torch.int64)
+        indptr = self.empty((rows + 1,), torch.int64)
+        idx = self.empty((nnz,), torch.int64)
+        w = self.empty((nnz,), torch.float32 if similarity else torch.int64)
+        L.check(self.lib.pg_edge_keys_to_csr(_ptr(keys), keys.numel(), _ptr(alt), int(rows), int(words), int(nnz),
+                                             L.W_SIM_F32 if similarity else L.W_I64, _ptr(indptr), _ptr(idx), _ptr(w),
+                                             self._stream()))
+        return indptr, idx, w
+
     def hamming_tile(self, data, queries, q0=0, qrows=None, weight=L.W_I64):
         """hamming.py:34-38: (qrows, N) distances of query rows [q0,q0+qrows) vs all data rows."""
         self._check_pair(data, queries)

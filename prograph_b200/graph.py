@@ -302,6 +302,52 @@ def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows):
     return eng.hamming_eps(own, row0, rows, stream, lut, similarity=similarity)
 
 
+SYM_EPS_MIN_ROWS = 32768    # smaller epsilon graphs: count + capture with the one-sided sweep
+SYM_EPS_MAX_DEGREE = 384    # denser graphs are bound by writing their edges: one-sided count / fill
+
+
+def _eps_sample(n):
+    """(first row, rows) of the row sample that estimates the mean degree."""
+    rows = min(n, max(512, min(2048, n // 128 // _shard.ROW_ALIGN * _shard.ROW_ALIGN)))
+    row0 = (n // 2) // _shard.ROW_ALIGN * _shard.ROW_ALIGN
+    return (row0, rows) if row0 + rows <= n else (0, rows)
+
+
+def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
+    """Epsilon graph (CSR of every row) of `packed` against itself, on every rank
+    (prograph.py:731-753).  Large, sparse graphs whose edge test is one contiguous distance range
+    take the symmetric sweep: one pass over the triangle of unordered pairs appends both directed
+    edges of every passing pair as packed keys, a radix sort by (row, column) turns them into the
+    CSR.  A one-sided count over a small row sample estimates the mean degree first: it sizes the
+    key buffer and sends dense graphs (bound by writing their edges, not by distances) to the
+    count / fill passes.  Ranks sweep bands of the triangle and all-gather their key buffers.
+    Everything else: count / fill with the one-sided sweep on this rank's row block, then the CSR
+    all-gather."""
+    n = packed.rows
+    force = os.environ.get("PG_EPS_SYM")
+    use_sym = hasattr(eng, "hamming_eps_sym") and (n >= SYM_EPS_MIN_ROWS if force is None else force not in ("0", ""))
+    if use_sym:
+        try:
+            sharded = world > 1 and n >= world
+            parts = world if sharded else 1
+            degree = eng.hamming_eps_mean_degree(packed, *_eps_sample(n), packed, lut)
+            if degree > SYM_EPS_MAX_DEGREE and force is None:
+                raise L.Unsupported("dense graph")
+            capacity = int(1.5 * degree * n / parts) + (4 << 20)
+            keys, edges = eng.hamming_eps_sym(packed, lut, rank if sharded else 0, parts, mode=1 if sharded else 0,
+                                              capacity=capacity)
+            if sharded:
+                keys, edges = _shard.gather_edge_keys(keys, edges, world, group)
+            if hasattr(eng, "_check_edge_budget"):
+                eng._check_edge_budget(edges)
+            return eng.edge_keys_to_csr(keys, n, packed.words, edges, similarity)
+        except L.Unsupported:
+            pass
+    row0, rows = _shard.row_range(n, rank, world)
+    part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
+    return _shard.gather_csr(part, n, rank, world, group, eng)
+
+
 # ---------------------------------------------------------------------------------
 # Minkowski p=2 on integer tokens: the edge test as a range of the exact integer sum S
 # ---------------------------------------------------------------------------------
@@ -434,7 +480,8 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     if packed is not None:
         if eps:
             lut = distance_lut(packed.words * 32, comp, eps, similarity)
-            part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
+            indptr, idx, w = hamming_eps_graph(eng, packed, lut, similarity, rank, world, group)
+            return NeighbourTable(_to_host(indptr), _to_host(idx), _to_host(w))
         else:
             idx, w = hamming_knn_graph(eng, packed, k, similarity, rank, world, group)
             return KnnTable(_to_host(idx), _to_host(w))

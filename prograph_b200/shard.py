@@ -87,6 +87,21 @@ def all_gather_stack(t, world, group):
     return out.reshape((world,) + tuple(t.shape))
 
 
+def gather_edge_keys(keys, edges, world, group):
+    """Per-rank edge-key buffers of the symmetric epsilon sweep (ragged) -> one buffer holding all
+    of them (padding = the sentinel -1, which sorts behind every edge) and the total edge count."""
+    meta = torch.tensor([keys.numel(), edges], dtype=torch.int64, device=keys.device)
+    allmeta = torch.empty((world * 2,), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(allmeta, meta, group=group)
+    allmeta = allmeta.reshape(world, 2).cpu()
+    cap = max(int(allmeta[:, 0].max()), 1)
+    mine = torch.full((cap,), -1, dtype=keys.dtype, device=keys.device)
+    mine[: keys.numel()] = keys
+    out = torch.empty((world * cap,), dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out, int(allmeta[:, 1].sum())
+
+
 def gather_csr(part, n, rank, world, group, eng=None):
     """Ragged per-row results (epsilon graph): exchange the row counts, then the padded
     index / weight shards, and rebuild one global CSR on every rank."""

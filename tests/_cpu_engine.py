@@ -58,12 +58,34 @@ class CheckerEngine:
         keys = self._keys(D, np.broadcast_to(np.arange(boot_rows), D.shape))
         return torch.from_numpy(np.ascontiguousarray(self._smallest(keys, k1)))
 
+    def _band(self, table, boot_rows, rank, world, mode):
+        """Stream-row band of a rank (mode 1) from the library's host-side planner."""
+        if mode != 1:
+            return 0, table.rows
+        import ctypes as C
+        from prograph_b200 import _lib
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.load().pg_knn_sym_band(table.rows, table.words, int(boot_rows), rank, world, C.byref(a),
+                                               C.byref(b)))
+        return a.value, b.value
+
+    def _triangle(self, table, rank, world, mode, boot_rows=0):
+        """The (own rows a..b, stream rows start..end, distances) pieces of the triangle of unordered
+        pairs this rank sweeps.  Every 256-row block sweeps the stream rows from its own block on;
+        blocks of the bootstrap rows start behind them.  mode 0: blocks rank, rank+world, ...;
+        mode 1: all blocks, restricted to the rank's band of stream rows."""
+        n, T = table.rows, table.tokens
+        band = self._band(table, boot_rows, rank, world, mode)
+        blocks = range(-(-n // 256)) if mode == 1 else range(rank, -(-n // 256), world)
+        for rb in blocks:
+            a, b = rb * 256, min(n, rb * 256 + 256)
+            start, end = max(boot_rows if a < boot_rows else a, band[0]), band[1]
+            if start < end:
+                yield a, b, start, end, O.hamming(T[start:end], T[a:b])        # (b-a, end-start)
+
     def hamming_knn_sym(self, table, k1, rank=0, world=1, lists=None, boot_rows=0, mode=0):
-        """Candidates this rank sees.  Every 256-row block sweeps the stream rows from its own
-        block on (row side) and feeds the rows of later blocks (column side); blocks of the
-        bootstrap rows start behind them and have no column side.  mode 0: this rank takes blocks
-        rank, rank+world, ...; mode 1: all blocks, restricted to the rank's band of stream rows
-        (the band limits come from the library's host-side planner, pg_knn_sym_band)."""
+        """Candidates this rank sees: row side for the own row, column side for the rows of later
+        blocks; blocks of the bootstrap rows have no column side."""
         n = table.rows
         self.sym_calls = getattr(self, "sym_calls", 0) + 1
         self.sym_modes = getattr(self, "sym_modes", []) + [mode]
@@ -71,22 +93,7 @@ class CheckerEngine:
         if boot_rows:
             for r in range(n):
                 cand[r].extend(int(v) for v in lists[r].numpy() if v != -1)
-        band = (0, n)
-        if mode == 1:
-            import ctypes as C
-            from prograph_b200 import _lib
-            a, b = C.c_int64(0), C.c_int64(0)
-            _lib.check(_lib.load().pg_knn_sym_band(n, table.words, int(boot_rows), rank, world, C.byref(a), C.byref(b)))
-            band = (a.value, b.value)
-        T = table.tokens
-        blocks = range(-(-n // 256)) if mode == 1 else range(rank, -(-n // 256), world)
-        for rb in blocks:
-            a, b = rb * 256, min(n, rb * 256 + 256)
-            start = max(boot_rows if a < boot_rows else a, band[0])
-            end = band[1]
-            if start >= end:
-                continue
-            D = O.hamming(T[start:end], T[a:b])                      # (b-a, end-start)
+        for a, b, start, end, D in self._triangle(table, rank, world, mode, boot_rows):
             for i in range(a, b):
                 for j in range(start, end):
                     d = int(D[i - a, j - start])
@@ -98,6 +105,36 @@ class CheckerEngine:
             u = sorted(set(cand[r]))[:k1]
             out[r, :len(u)] = u
         return torch.from_numpy(out)
+
+    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
+        indptr, _, _ = self.hamming_eps(own, row0, rows, stream, lut)
+        return float(indptr[-1]) / rows
+
+    # symmetric epsilon sweep: edge keys row << 40 | column << 12 | distance (the checker's own packing)
+    def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):
+        self.eps_sym_calls = getattr(self, "eps_sym_calls", 0) + 1
+        lut = np.asarray(lut, dtype=np.uint32)
+        hits = np.nonzero([(lut[d >> 5] >> (d & 31)) & 1 for d in range(len(lut) * 32)])[0]
+        if len(hits) and hits[-1] - hits[0] + 1 != len(hits):
+            from prograph_b200._lib import Unsupported
+            raise Unsupported("not a contiguous range")
+        keys = []
+        for a, b, start, end, D in self._triangle(table, rank, world, mode):
+            keep = ((lut[D >> 5] >> (D & 31).astype(np.uint32)) & 1).astype(bool)
+            for i, j in zip(*np.nonzero(keep)):
+                gi, gj, d = a + int(i), start + int(j), int(D[i, j])
+                keys.append((gi << 40) | (gj << 12) | d)
+                if gj >= b:
+                    keys.append((gj << 40) | (gi << 12) | d)
+        keys = keys + [-1] * (7 + rank)                         # unused slots of the last chunk
+        return torch.tensor(keys, dtype=torch.int64), len(keys) - 7 - rank
+
+    def edge_keys_to_csr(self, keys, rows, words, nnz, similarity=False):
+        k = np.sort(keys.numpy().view(np.uint64))[:nnz].astype(np.int64)
+        row, col, d = k >> 40, (k >> 12) & ((1 << 28) - 1), k & 4095
+        indptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=rows))]).astype(np.int64)
+        w = (np.float32(1) / (1 + d).astype(np.float32)).astype(np.float32) if similarity else d
+        return torch.from_numpy(indptr), torch.from_numpy(col), torch.from_numpy(w)
 
     def knn_lists_finalize(self, lists, row0, rows, k, drop=1, similarity=False):
         lists = lists.numpy()

@@ -2,6 +2,8 @@
 pg_knn_lists_finalize, prograph_b200/csrc/pg_sweep_sym.cuh) with the oracle, the one-sided fused
 sweep and, at the headline size, sampled oracle rows.  Reference semantics: prograph.py:755-765
 (sort each row of distances, drop sorted position 0, keep k; ties by ascending index)."""
+import operator
+
 import numpy as np
 import pytest
 import torch
@@ -147,3 +149,94 @@ def test_public_build_crosses_into_symmetric_path(eng):
     sim = graph.build_neighbours(X, k=3, similarity=True)
     np.testing.assert_array_equal(sim.idx, got.idx[:, :3])
     np.testing.assert_array_equal(sim.w, (np.float32(1) / (1 + got.w[:, :3]).astype(np.float32)).astype(np.float32))
+
+
+# ------------------------------------------------------------------ symmetric epsilon graph
+def sym_eps(eng, tab, lut, similarity=False, world=1, mode=0, capacity=None):
+    """All ranks of a `world`-GPU symmetric epsilon build emulated on one device (graph.hamming_eps_graph)."""
+    keys, edges = [], 0
+    for r in range(world):
+        k, e = eng.hamming_eps_sym(tab, lut, r, world, mode=mode, capacity=capacity)
+        keys.append(k)
+        edges += e
+    return eng.edge_keys_to_csr(torch.cat(keys), tab.rows, tab.words, edges, similarity)
+
+
+@pytest.mark.parametrize("L,eps,alphabet", [(3, 1, 4), (20, 12, 4), (56, 2, 20), (100, 3, 20), (256, 4, 20), (300, 5, 20),
+                                            (64, 5, 200)])
+@pytest.mark.parametrize("world,mode", [(1, 0), (2, 0), (3, 1)])
+def test_symmetric_eps_vs_oracle(eng, L, eps, alphabet, world, mode):
+    """prograph.py:731-753: neighbours in ascending index order, weights = distances (or float32
+    similarities), `d > 0` guard (duplicates are not neighbours)."""
+    from prograph_b200.graph import distance_lut
+    rng = np.random.default_rng(L + eps)
+    n = 2100
+    X = mutational(rng, n, L, alphabet=alphabet, max_mut=min(8, L)) if L >= 56 else \
+        rng.integers(1, alphabet + 1, size=(n, L)).astype(np.int64)
+    tab = eng.pack(X)
+    for similarity in (False, True):
+        e = 1 / (1 + eps) if similarity else eps
+        lut = distance_lut(tab.words * 32, operator.le, e, similarity)
+        indptr, idx, w = O.to_csr(O.build_graph(X, eps=eps, similarity=similarity))
+        # a 1024-slot buffer is too small for every case here: the sweep reports what it needs and runs again
+        for capacity in (None, 1024):
+            gi, gx, gw = sym_eps(eng, tab, lut, similarity, world, mode, capacity)
+            np.testing.assert_array_equal(np_(gi), indptr)
+            np.testing.assert_array_equal(np_(gx), idx)
+            np.testing.assert_array_equal(np_(gw), w)
+            assert np_(gw).dtype == (np.float32 if similarity else np.int64)
+
+
+def test_symmetric_eps_other_comparisons_and_empty(eng):
+    from prograph_b200 import _lib
+    from prograph_b200.graph import distance_lut
+    rng = np.random.default_rng(9)
+    X = rng.integers(1, 5, size=(1500, 20)).astype(np.int64)
+    tab = eng.pack(X)
+    D = O.hamming(X, X)
+    for comp, eps in ((operator.ge, 18), (operator.gt, 17), (operator.lt, 9), (operator.eq, 10)):
+        lut = distance_lut(tab.words * 32, comp, eps, False)
+        gi, gx, gw = sym_eps(eng, tab, lut)
+        keep = comp(D, eps) & (D > 0)
+        rows, cols = np.nonzero(keep)
+        np.testing.assert_array_equal(np_(gi), np.concatenate([[0], np.cumsum(keep.sum(1))]))
+        np.testing.assert_array_equal(np_(gx), cols)
+        np.testing.assert_array_equal(np_(gw), D[rows, cols])
+    # nothing passes: all-zero indptr, empty arrays
+    gi, gx, gw = sym_eps(eng, tab, distance_lut(tab.words * 32, operator.gt, 25, False))
+    assert np_(gi).tolist() == [0] * 1501 and gx.numel() == 0 and gw.numel() == 0
+    # `!=` is not one range of distances: the symmetric sweep declines, the caller takes count / fill
+    with pytest.raises(_lib.Unsupported):
+        eng.hamming_eps_sym(tab, distance_lut(tab.words * 32, operator.ne, 10, False))
+
+
+def test_gb1_library_symmetric_eps_known_answers(eng):
+    """C3: the full 20^4 library, L=56.  eps=1: every degree = 4*19 = 76, nnz =
+    12 160 000, through the public build (symmetric sweep above graph.SYM_EPS_MIN_ROWS); the whole
+    CSR equals the one-sided count / fill passes'.  eps=2 (degree 2242) is dense: one-sided path."""
+    import itertools
+    from prograph_b200 import graph
+    wt = np.frombuffer(b"MTYKLILNGKTLKGETTTEAVDAATAEKVFKQYANDNGVDGEWTYDDATKTFTVTE", dtype=np.uint8)
+    lut256 = np.zeros(256, dtype=np.uint8)
+    for i, ch in enumerate("ACDEFGHIKLMNPQRSTVWY"):
+        lut256[ord(ch)] = i + 1
+    combos = np.array(list(itertools.product(range(1, 21), repeat=4)), dtype=np.uint8)
+    X = np.tile(lut256[wt], (len(combos), 1))
+    X[:, [38, 39, 40, 53]] = combos
+    n = len(X)
+    assert n == 160_000 >= graph.SYM_EPS_MIN_ROWS
+    eng.time_sweeps(True)
+    eng.sweep_times(reset=True)
+    got = graph.build_neighbours(X, eps=1)
+    assert len(eng.sweep_times(reset=True)) == 2                 # degree sample + symmetric sweep
+    eng.time_sweeps(False)
+    assert np.all(got.degrees() == 76) and len(got.idx) == 12_160_000
+    assert np.all(got.w == 1)
+    tab = eng.pack(X)
+    lut = graph.distance_lut(tab.words * 32, operator.le, 1, False)
+    ip, ix, w = eng.hamming_eps(tab, 0, n, tab, lut)
+    np.testing.assert_array_equal(got.indptr, np_(ip))
+    np.testing.assert_array_equal(got.idx, np_(ix))
+    np.testing.assert_array_equal(got.w, np_(w))
+    assert eng.hamming_eps_mean_degree(tab, *graph._eps_sample(n), tab,
+                                       graph.distance_lut(tab.words * 32, operator.le, 2, False)) == 2242.0

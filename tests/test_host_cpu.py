@@ -185,10 +185,16 @@ def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
     rng = np.random.default_rng(5)
     X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
     eng = CheckerEngine()
+    graph.SYM_EPS_MIN_ROWS = 0
     knn = graph.build_neighbours(X, k=k, engine=eng)
     sim = graph.build_neighbours(X, k=k, similarity=True, engine=eng)
+    eps = graph.build_neighbours(X, eps=2, engine=eng)
+    esim = graph.build_neighbours(X, eps=2, similarity=True, engine=eng)
+    odd = graph.build_neighbours(X, eps=2, comp=operator.ne, engine=eng)     # not a range: one-sided path
     np.savez(os.path.join(tmpdir, f"r{rank}.npz"), idx=knn.idx, w=knn.w, sidx=sim.idx, sw=sim.w,
-             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n), min(eng.sym_modes)]))
+             eindptr=eps.indptr, eidx=eps.idx, ew=eps.w, sindptr=esim.indptr, seidx=esim.idx, sew=esim.w,
+             oindptr=odd.indptr, oidx=odd.idx, ow=odd.w,
+             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n), min(eng.sym_modes), eng.eps_sym_calls]))
     dist.destroy_process_group()
 
 
@@ -214,3 +220,12 @@ def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
         assert z["calls"][0] == 2                       # both builds went through the symmetric sweep
         assert z["calls"][1] == (512 if boot_div == 2 else 0)
         assert z["calls"][2] == 1                       # ranks took column bands of the triangle
+        for got, want in (("e", O.build_graph(X, eps=2)), ("s", O.build_graph(X, eps=2, similarity=True)),
+                          ("o", O.build_graph(X, eps=2, comp=operator.ne))):
+            indptr, eidx, ew = O.to_csr(want)
+            np.testing.assert_array_equal(z[got + "indptr"], indptr)
+            np.testing.assert_array_equal(z[{"e": "eidx", "s": "seidx", "o": "oidx"}[got]], eidx)
+            np.testing.assert_array_equal(z[{"e": "ew", "s": "sew", "o": "ow"}[got]], ew)
+        # eps=2 and its similarity form took the symmetric sweep; `d != 2` keeps nearly every pair
+        # (dense: above graph.SYM_EPS_MAX_DEGREE for n=1301, not a range for n=700) -> one-sided passes
+        assert z["calls"][3] == 2

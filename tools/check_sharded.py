@@ -35,16 +35,16 @@ def main():
                           (3001, 56, 0)):
         # sym_min = 0 routes small tables through the symmetric build too (interleaved row blocks,
         # all-gather + merge of the candidate lists); 70000 rows take it by default
-        default_min = graph.SYM_MIN_ROWS
+        default_min, default_eps_min = graph.SYM_MIN_ROWS, graph.SYM_EPS_MIN_ROWS
         if sym_min is not None:
-            graph.SYM_MIN_ROWS = sym_min
+            graph.SYM_MIN_ROWS = graph.SYM_EPS_MIN_ROWS = sym_min
         X = make_tokens(n, L, "mutational")
         knn = build_neighbours(X, k=16)
-        graph.SYM_MIN_ROWS = default_min
-        eps = build_neighbours(X, eps=2)
+        eps = build_neighbours(X, eps=2 if n < 50000 else 1)
+        graph.SYM_MIN_ROWS, graph.SYM_EPS_MIN_ROWS = default_min, default_eps_min
         tab = eng.pack(X)
         ri, rw = eng.hamming_knn(tab, 0, n, tab, 16, drop=1)
-        ip, ei, ew = eng.hamming_eps(tab, 0, n, tab, distance_lut(tab.words * 32, operator.le, 2, False))
+        ip, ei, ew = eng.hamming_eps(tab, 0, n, tab, distance_lut(tab.words * 32, operator.le, 2 if n < 50000 else 1, False))
         good = (np.array_equal(knn.idx, ri.cpu().numpy()) and np.array_equal(knn.w, rw.cpu().numpy())
                 and np.array_equal(eps.indptr, ip.cpu().numpy()) and np.array_equal(eps.idx, ei.cpu().numpy())
                 and np.array_equal(eps.w, ew.cpu().numpy()))
