@@ -53,7 +53,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/configs.jsonl")
     args = ap.parse_args()
     from prograph_b200.engine import get_engine
-    from prograph_b200.graph import distance_lut
+    from prograph_b200.graph import distance_lut, hamming_knn_graph, hamming_eps_graph
     from prograph_b200 import _lib as L
     from bench import make_tokens
     eng = get_engine()
@@ -76,17 +76,31 @@ def main():
         rec("C3", f"hamming eps={eps} graph (count+scan+fill), CSR int64", n * n * 2.0, ms, nnz=int(ip[-1]),
             degree=int(deg[0]), degree_uniform=bool((deg == deg[0]).all()), note="pairs counts both sweeps")
     ms, _ = timed(lambda: eng.hamming_knn(tab, 0, n, tab, 16, drop=1))
-    rec("C3", "hamming kNN k=16", float(n) * n, ms)
+    rec("C3", "hamming kNN k=16, one-sided sweep", float(n) * n, ms)
+    # the shipped build_graph path: symmetric sweeps where they apply (N^2 ordered pairs counted)
+    for eps in (1, 2):
+        lut = distance_lut(tab.words * 32, operator.le, eps, False)
+        ms, (ip, ix, w) = timed(lambda: hamming_eps_graph(eng, tab, lut, False, 0, 1, None))
+        rec("C3", f"hamming eps={eps} graph, shipped path (degree sample + symmetric sweep + sort, or count/fill when dense)",
+            float(n) * n, ms, nnz=int(ip[-1]))
+    ms, _ = timed(lambda: hamming_knn_graph(eng, tab, 16, False, 0, 1, None))
+    rec("C3", "hamming kNN k=16, shipped path (bootstrap + symmetric sweep)", float(n) * n, ms)
 
     # ---- C4 ---------------------------------------------------------------------------------
     n4 = 262144 if args.quick else 1_000_000
     M = make_tokens(n4, 256, "mutational")
     tabm = eng.pack(M)
     ms, _ = timed(lambda: eng.hamming_knn(tabm, 0, n4, tabm, 16, drop=1), reps=1)
-    rec("C4-M", f"hamming kNN k=16, N={n4}", float(n4) * n4, ms)
+    rec("C4-M", f"hamming kNN k=16, N={n4}, one-sided sweep", float(n4) * n4, ms)
+    ms, _ = timed(lambda: hamming_knn_graph(eng, tabm, 16, False, 0, 1, None), reps=1)
+    rec("C4-M", f"hamming kNN k=16, N={n4}, shipped path (bootstrap + symmetric sweep)", float(n4) * n4, ms)
     lut = distance_lut(256, operator.le, 1, False)
     ms, (ip, _, _) = timed(lambda: eng.hamming_eps(tabm, 0, n4, tabm, lut), reps=1)
-    rec("C4-M", f"hamming eps=1 graph, N={n4}", float(n4) * n4 * 2, ms, nnz=int(ip[-1]), note="pairs counts both sweeps")
+    rec("C4-M", f"hamming eps=1 graph, N={n4}, one-sided count+fill", float(n4) * n4 * 2, ms, nnz=int(ip[-1]),
+        note="pairs counts both sweeps")
+    ms, (ip, _, _) = timed(lambda: hamming_eps_graph(eng, tabm, lut, False, 0, 1, None), reps=1)
+    rec("C4-M", f"hamming eps=1 graph, N={n4}, shipped path (degree sample + symmetric sweep + sort)", float(n4) * n4, ms,
+        nnz=int(ip[-1]))
     try:
         eng.hamming_eps(tabm, 0, n4, tabm, distance_lut(256, operator.le, 2, False))
     except MemoryError as e:

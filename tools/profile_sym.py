@@ -21,16 +21,22 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--dist", default="uniform")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--eps", type=int, default=0, help="epsilon graph instead of kNN (0 = kNN)")
     args = ap.parse_args()
     from bench import make_tokens
     from prograph_b200 import graph
     from prograph_b200.engine import get_engine
     eng = get_engine()
+    import operator
     tab = eng.pack(make_tokens(args.n, args.length, args.dist))
+    lut = graph.distance_lut(tab.words * 32, operator.le, args.eps, False) if args.eps else None
     for _ in range(args.reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        graph.hamming_knn_graph(eng, tab, args.k, False, 0, 1, None)
+        if args.eps:
+            graph.hamming_eps_graph(eng, tab, lut, False, 0, 1, None)
+        else:
+            graph.hamming_knn_graph(eng, tab, args.k, False, 0, 1, None)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
