@@ -412,10 +412,54 @@ __global__ void knn_part_to_lists_kernel(const unsigned long long* __restrict__ 
   }
 }
 
-// Final lists: merge n_lists sorted key lists per row (one per rank), drop, widen.
+// Final lists: merge n_lists sorted key lists per row (one per rank), drop, widen.  Every list
+// keeps a cursor and its head key in registers; a key present in several lists (the shared
+// bootstrap entries) advances all of them, so the merged order has no duplicates.
+constexpr int kMaxMergeLists = 16;
+
 __global__ void knn_lists_finalize_kernel(const unsigned long long* __restrict__ lists, int n_lists,
                                           long long list_stride, long long row0, long long rows, int k1, int k,
                                           int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  const unsigned long long* base = lists + static_cast<size_t>(row0 + r) * k1;
+  unsigned long long head[kMaxMergeLists];
+  int pos[kMaxMergeLists];
+#pragma unroll
+  for (int s = 0; s < kMaxMergeLists; ++s) {
+    pos[s] = 0;
+    head[s] = s < n_lists ? base[static_cast<size_t>(s) * list_stride] : ~0ull;
+  }
+  for (int j = 0; j < drop + k; ++j) {
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int s = 0; s < kMaxMergeLists; ++s) best = head[s] < best ? head[s] : best;
+    if (best != ~0ull) {
+#pragma unroll
+      for (int s = 0; s < kMaxMergeLists; ++s) {
+        if (head[s] == best) {
+          ++pos[s];
+          head[s] = pos[s] < k1 ? base[static_cast<size_t>(s) * list_stride + pos[s]] : ~0ull;
+        }
+      }
+    }
+    if (j >= drop) {
+      const long long at = r * k + (j - drop);
+      if (best == ~0ull) {
+        out_idx[at] = -1;
+        write_weight(out_w, at, 0, weight);
+      } else {
+        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
+        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
+      }
+    }
+  }
+}
+
+// more lists than cursors fit in registers: "smallest key above the last one", rescanning the lists
+__global__ void knn_lists_finalize_scan_kernel(const unsigned long long* __restrict__ lists, int n_lists,
+                                               long long list_stride, long long row0, long long rows, int k1, int k,
+                                               int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
   const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (r >= rows) return;
   unsigned long long last = 0;
@@ -445,7 +489,6 @@ __global__ void knn_lists_finalize_kernel(const unsigned long long* __restrict__
     }
   }
 }
-
 
 // ---- symmetric epsilon graph: edge keys -> CSR -----------------------------------------------
 struct EdgeKeyBits { int dbits, idxbits; };
@@ -880,10 +923,16 @@ int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_strid
   PG_CHECK_ARG(n_lists >= 1 && rows > 0 && row0 >= 0 && k >= 1 && drop >= 0 && k1 >= 1, "bad list geometry");
   PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
   const int threads = 128;
-  knn_lists_finalize_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0,
-                              static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const unsigned long long*>(lists), n_lists, list_stride, row0, rows, k1, k, drop, weight,
-      reinterpret_cast<long long*>(out_idx), out_w);
+  const unsigned grid = static_cast<unsigned>(ceil_div(rows, threads));
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (n_lists <= kMaxMergeLists)
+    knn_lists_finalize_kernel<<<grid, threads, 0, cs>>>(reinterpret_cast<const unsigned long long*>(lists), n_lists,
+                                                        list_stride, row0, rows, k1, k, drop, weight,
+                                                        reinterpret_cast<long long*>(out_idx), out_w);
+  else
+    knn_lists_finalize_scan_kernel<<<grid, threads, 0, cs>>>(reinterpret_cast<const unsigned long long*>(lists), n_lists,
+                                                             list_stride, row0, rows, k1, k, drop, weight,
+                                                             reinterpret_cast<long long*>(out_idx), out_w);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -90,7 +90,9 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
       __nanosleep(100);
       if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
     }
-    __threadfence();
+    // no fence on the acquiring side: the list is only ever read with ld.global.cg (L2, never L1),
+    // the loads below are issued after the CAS has returned, and the previous holder fenced its
+    // stores before it released the lock
     if (prm.stats != nullptr) {
       atomicAdd(prm.stats + 1, 1ull);
       if (spins) atomicAdd(prm.stats + 2, static_cast<unsigned long long>(spins));
