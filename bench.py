@@ -78,7 +78,8 @@ def config_of(args, world):
                        "once), bands of the triangle") + f" sharded over {world} GPU(s)",
         "n_sequences": args.n, "seq_len": args.length, "k": args.k, "distribution": args.dist,
         "parallelism": f"row-block x{world}",
-        "l2": "inputs exceed L2: 160 MB packed table + split partial lists (>400 MB) are re-read every step",
+        "l2": "inputs exceed L2 (126 MB): 160 MB packed table + 136 MB of per-row lists + 8 MB of filter words are "
+              "re-read every step",
     }
 
 

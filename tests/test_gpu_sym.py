@@ -76,8 +76,10 @@ def test_symmetric_knn_ragged_sizes_and_duplicates(eng, n):
     tab = eng.pack(X.astype(np.uint8))
     k = min(16, n - 1)
     ri, rw = O.knn_from_distances(O.hamming(X, X), k)
+    # 17 ranks: more lists than the merge kernel keeps cursors for (its rescanning variant), and
+    # more ranks than row blocks / bands with work
     for world, boot, mode in ((1, 0, 0), (2, 0, 0), (1, 512 if n >= 512 else 0, 0), (2, 0, 1),
-                              (8, 512 if n >= 512 else 0, 1)):
+                              (8, 512 if n >= 512 else 0, 1), (17, 0, 0), (17, 0, 1)):
         idx, w = sym_knn(eng, tab, k, world=world, boot=boot, mode=mode)
         np.testing.assert_array_equal(np_(idx), ri)
         np.testing.assert_array_equal(np_(w), rw)
