@@ -226,6 +226,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
   unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [2][GM][k1]
   int* slists = reinterpret_cast<int*>(lists + 2 * GM * prm.k1);                        // [2][GM][k1] exact sums
+  // tile mode (no lists): per-warp 32 x 36-word transpose buffers, 16-byte aligned
+  uint32_t* tile_stage = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_holder + 2) + 15) & ~uintptr_t(15));
+  const bool tile_fast = MODE == GM_TILE && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0 &&
+                         ((static_cast<size_t>(prm.ld) * (VK == GV_F16 ? 2 : 4)) & 15) == 0;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -350,37 +354,55 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
           v[4 * g + 3] = nx.w - 2 * static_cast<int>(dot[4 * g + 3]);
         }
         if (MODE == GM_TILE) {
-          if (valid) {
+          // Thread = query row holds 32 consecutive columns.  Storing them directly makes every
+          // store instruction touch 32 rows (32 half-used sectors); instead the warp transposes the
+          // 32 x 32 block through shared memory and writes whole 128-byte (fp16: 64-byte) row
+          // segments, four (eight) rows per instruction.
+          constexpr int WPR = VK == GV_F16 ? 16 : 32;          // 32-bit words per row segment
+          constexpr int STRIDE = WPR + 4;                      // conflict-free for 16-byte accesses
+          uint32_t* stg = tile_stage + static_cast<size_t>(warp) * 32 * 36;
+          const bool fast = tile_fast && col0 + 32 <= prm.N;   // warp-uniform
+          if (fast) {
+            uint32_t* mine = stg + lane * STRIDE;
+#pragma unroll
+            for (int g = 0; g < WPR / 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (VK == GV_F16)
+                  w[e] = value_bits<VK>(nq + v[8 * g + 2 * e], sim) | (value_bits<VK>(nq + v[8 * g + 2 * e + 1], sim) << 16);
+                else
+                  w[e] = value_bits<VK>(nq + v[4 * g + e], sim);
+              }
+              *reinterpret_cast<uint4*>(mine + 4 * g) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            __syncwarp();
+            constexpr int LPR = WPR / 4;                       // lanes per row segment
+            constexpr int RPI = 32 / LPR;                      // rows per store instruction
+            const long long wrow0 = row0 + qwarp * 32;
+#pragma unroll
+            for (int it = 0; it < 32 / RPI; ++it) {
+              const int rr = it * RPI + lane / LPR;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STRIDE + 4 * (lane % LPR));
+              if (wrow0 + rr < prm.M) {
+                unsigned char* o = static_cast<unsigned char*>(prm.out) +
+                                   (static_cast<size_t>(wrow0 + rr) * prm.ld + col0) * (VK == GV_F16 ? 2 : 4);
+                reinterpret_cast<uint4*>(o)[lane % LPR] = val;
+              }
+            }
+            __syncwarp();
+          } else if (valid) {
             const size_t at = static_cast<size_t>(row) * prm.ld + col0;
             if (VK == GV_F16) {
               unsigned short* o = static_cast<unsigned short*>(prm.out) + at;
-              if (col0 + 32 <= prm.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    w[e] = value_bits<VK>(nq + v[8 * g + 2 * e], sim) | (value_bits<VK>(nq + v[8 * g + 2 * e + 1], sim) << 16);
-                  reinterpret_cast<uint4*>(o)[g] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < prm.N) o[j] = static_cast<unsigned short>(value_bits<VK>(nq + v[j], sim));
-              }
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < prm.N) o[j] = static_cast<unsigned short>(value_bits<VK>(nq + v[j], sim));
             } else {
               uint32_t* o = static_cast<uint32_t*>(prm.out) + at;
-              if (col0 + 32 <= prm.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  reinterpret_cast<uint4*>(o)[g] =
-                      make_uint4(value_bits<VK>(nq + v[4 * g + 0], sim), value_bits<VK>(nq + v[4 * g + 1], sim),
-                                 value_bits<VK>(nq + v[4 * g + 2], sim), value_bits<VK>(nq + v[4 * g + 3], sim));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < prm.N) o[j] = value_bits<VK>(nq + v[j], sim);
-              }
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < prm.N) o[j] = value_bits<VK>(nq + v[j], sim);
             }
           }
         } else if (MODE == GM_COUNT) {
@@ -524,19 +546,19 @@ __global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long
   }
 }
 
-static size_t gemm_smem_bytes(int K, int k1, int stages) {
+static size_t gemm_smem_bytes(int K, int k1, int stages, bool tile_mode = false) {
   return static_cast<size_t>(GM) * K * (1 + stages) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 2 * GACC + 1) * sizeof(uint64_t) +
-         16 + 2 * static_cast<size_t>(GM) * k1 * 12;
+         16 + 2 * static_cast<size_t>(GM) * k1 * 12 + (tile_mode ? 16 + 8 * 32 * 36 * 4 : 0);
 }
 
 template <int VK, int MODE>
 static int launch_gemm(GemmParams prm, cudaStream_t s) {
   auto kern = mink_gemm_kernel<VK, MODE>;
   prm.stages = GSTAGES;
-  size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages);
+  size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages, MODE == GM_TILE);
   if (smem > 227 * 1024) {     // long lists: give up one ring stage before giving up the fused path
     prm.stages = GSTAGES - 1;
-    smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages);
+    smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages, MODE == GM_TILE);
   }
   if (smem > 227 * 1024) { set_error("minkowski GEMM: k or row width too large for shared memory (%zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
