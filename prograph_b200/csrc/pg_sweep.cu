@@ -793,7 +793,6 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   unsigned long long* stats_dev = reinterpret_cast<unsigned long long*>(wsb + lay.stats_off);
   const bool want_stats = std::getenv("PG_SYM_STATS") != nullptr;
   prm.stats = want_stats ? stats_dev : nullptr;
-  if (const char* ev = std::getenv("PG_SYM_NOCOL")) prm.no_col = std::atoi(ev);
   SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs, SYM_KNN};
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only

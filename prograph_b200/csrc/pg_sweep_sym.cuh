@@ -42,7 +42,6 @@ struct SymParams {
   unsigned long long* glast;  // [n_tiles * tile_cols] filter word per row: (~tau)<<32 | index of the last key
   unsigned* glock;            // [rows]
   unsigned long long* stats;  // null, or [8] slow-path counters: -, locks, lock spins, list writes, row inserts
-  int no_col;                 // experiments: skip the column side (results are then incomplete)
   long long boot_rows;        // rows [0, boot_rows) were swept one-sided against every row beforehand
   // epsilon mode (SYM_EPS): edge <=> lo <= d <= hi; edges are appended to `keys` as
   // row << sh_row | column << sh_col | d, both directions of every unordered pair
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
     }
     // invalid own rows never feed a column list; blocks of the bootstrap rows have no column side
     // (every list already holds its candidates among the bootstrap rows) and start behind them
-    const unsigned vmask = (valid && !boot && !prm.no_col) ? 0xffffffffu : 0u;
+    const unsigned vmask = (valid && !boot) ? 0xffffffffu : 0u;
     const long long diag_begin = boot ? prm.boot_rows : static_cast<long long>(rb) * kConsumers;
     const long long diag_end = boot ? (1ll << 40) : diag_begin + kConsumers;
     // epsilon mode: edge  <=>  lo <= d <= hi; an invalid own row gets an unreachable lower bound
