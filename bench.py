@@ -77,7 +77,7 @@ def config_of(args, world):
                     + ("one-sided sweep, rows" if args.one_sided else "symmetric sweep (each unordered pair evaluated "
                        "once), bands of the triangle") + f" sharded over {world} GPU(s)",
         "n_sequences": args.n, "seq_len": args.length, "k": args.k, "distribution": args.dist,
-        "parallelism": f"row-block x{world}",
+        "parallelism": (f"row-block x{world}" if args.one_sided else f"triangle bands x{world}"),
         "l2": "inputs exceed L2 (126 MB): 160 MB packed table + 136 MB of per-row lists + 8 MB of filter words are "
               "re-read every step",
     }

@@ -105,6 +105,35 @@ def test_symmetric_knn_adversarial_descending(eng):
         np.testing.assert_array_equal(np_(w), rw)
 
 
+def test_symmetric_knn_degenerate_tables(eng):
+    """All rows identical (every distance 0, every comparison a tie decided by the index) and a
+    two-point table: the lists are the lowest indices after the positional self-drop."""
+    from prograph_b200 import graph
+    n, L, k = 5000, 256, 16
+    X = np.full((n, L), 7, dtype=np.uint8)
+    tab = eng.pack(X)
+    want = np.tile(np.arange(1, k + 1), (n, 1))          # sorted (0, index) keys, position 0 dropped
+    for world, boot, mode in ((1, 0, 0), (1, 512, 0), (3, 512, 1)):
+        idx, w = sym_knn(eng, tab, k, world=world, boot=boot, mode=mode)
+        np.testing.assert_array_equal(np_(idx), want)
+        assert int(np_(w).max()) == 0
+    # two clusters far apart, through the public build above the symmetric threshold
+    n = graph.SYM_MIN_ROWS + 700
+    X = np.full((n, 64), 3, dtype=np.uint8)
+    X[1::2] = 11
+    got = graph.build_neighbours(X, k=4)
+    even, odd = np.arange(0, n, 2), np.arange(1, n, 2)
+    # row r's neighbours: the lowest indices of its own cluster in (0, index) order, sorted position 0 dropped
+    np.testing.assert_array_equal(got.idx[0], even[1:5])
+    np.testing.assert_array_equal(got.idx[2], even[1:5])         # position 0 is index 0, not the row itself
+    np.testing.assert_array_equal(got.idx[n - 1 if (n - 1) % 2 else n - 2], odd[1:5])
+    np.testing.assert_array_equal(got.idx[1], odd[1:5])
+    assert got.w.max() == 0
+    eps = graph.build_neighbours(X[:40000], eps=70)              # every cross-cluster pair: d = 64 <= 70, d > 0
+    assert np.all(eps.degrees() == 20000) and np.all(eps.w == 64)
+    np.testing.assert_array_equal(eps.idx[:20000], odd[:20000])  # row 0: all odd rows, ascending
+
+
 def test_symmetric_unsupported_shapes_fall_back(eng):
     """Lists longer than 32 entries are not covered: the engine says so and build_neighbours
     takes the one-sided sweep (never a CPU path)."""
