@@ -794,6 +794,7 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   const bool want_stats = std::getenv("PG_SYM_STATS") != nullptr;
   prm.stats = want_stats ? stats_dev : nullptr;
   SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs, SYM_KNN};
+  if (const char* ev = std::getenv("PG_SYM_DEFER")) l.defer = std::atoi(ev);      // experiment, see pg_sweep_sym.cuh
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;

@@ -125,6 +125,86 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
   if (lane == 0) atomicExch(lock, 0u);
 }
 
+constexpr int kMaxSymList = 32;   // longest list the symmetric sweep keeps (k + drop)
+constexpr int kPendFlush = 24;    // a warp merges its pending column-side candidates at this many
+
+// Lane-parallel merge (deferred column side, the DEFER instantiation): every active lane merges
+// the candidate keys slots[b], b in slot_mask, into the global list of ITS OWN row -- up to 32 rows
+// per call, so the L2 round trips of lock, list load, write-back and unlock overlap across the
+// lanes instead of costing one warp stall per event.  The critical section sits inside the try-lock
+// loop: a lane that got its lock finishes and releases it in the same iteration, whatever its
+// sibling lanes are still waiting for, so locks held by diverged lanes of different warps cannot
+// wait on each other.
+static __device__ __noinline__ void sym_merge_lanes(const SymParams& prm, bool active, long long row,
+                                                    const unsigned long long* slots, unsigned slot_mask) {
+  const int k1 = prm.k1;
+  bool done = !active;
+  unsigned tries = 0;
+  while (!__all_sync(0xffffffffu, done)) {
+    if (!done && atomicCAS(prm.glock + row, 0u, 1u) == 0u) {
+      unsigned long long* lst = prm.glist + static_cast<size_t>(row) * k1;
+      unsigned long long e[kMaxSymList];
+      for (int i = 0; i < k1; ++i) e[i] = ld_cg_u64(lst + i);
+      bool changed = false;
+      for (unsigned mk = slot_mask; mk != 0u; mk &= mk - 1u) {
+        const unsigned long long key = slots[__ffs(mk) - 1];
+        if (key >= e[k1 - 1]) continue;                // also skips empty slots (~0)
+        int i = k1 - 1;
+        for (; i > 0 && e[i - 1] > key; --i) e[i] = e[i - 1];
+        e[i] = key;
+        changed = true;
+      }
+      if (changed) {
+        for (int i = 0; i < k1; ++i) st_cg_u64(lst + i, e[i]);
+        st_cg_u64(prm.glast + row, sym_filter_word(e[k1 - 1]));
+        __threadfence();
+      }
+      atomicExch(prm.glock + row, 0u);
+      done = true;
+      if (prm.stats != nullptr) {
+        atomicAdd(prm.stats + 1, 1ull);
+        if (changed) atomicAdd(prm.stats + 3, 1ull);
+      }
+    }
+    if (++tries > (1u << 22)) __trap();                // a protocol bug traps instead of hanging the GPU
+  }
+}
+
+// Merge the warp's pending (row, key) candidates: one lane per distinct row.  The queue length
+// lives in shared memory (*pcnt, warp-private) so that it costs the hot loop no register.
+static __device__ __noinline__ void sym_flush(const SymParams& prm, const unsigned* prow, const unsigned long long* pkey,
+                                              int* pcnt, int lane) {
+  __syncwarp();
+  const int qn = *pcnt;
+  if (qn == 0) return;
+  const bool have = lane < qn;
+  const unsigned row = have ? prow[lane] : 0xffffffffu;
+  const unsigned grp = __match_any_sync(0xffffffffu, row);
+  const bool leader = have && lane == __ffs(grp) - 1;
+  sym_merge_lanes(prm, leader, row, pkey, grp);
+  __syncwarp();
+  if (lane == 0) *pcnt = 0;
+  __syncwarp();
+}
+
+// Queue the column-side candidates of stream row j (lanes with `cc`).
+static __device__ __noinline__ void sym_enqueue(const SymParams& prm, unsigned* prow, unsigned long long* pkey, int* pcnt,
+                                                unsigned j, unsigned long long key, bool cc, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, cc);
+  const int n = __popc(m);
+  if (*pcnt + n > 32) sym_flush(prm, prow, pkey, pcnt, lane);
+  const int qn = *pcnt;
+  __syncwarp();
+  if (cc) {
+    const int slot = qn + __popc(m & ((1u << lane) - 1u));
+    prow[slot] = j;
+    pkey[slot] = key;
+  }
+  if (lane == 0) *pcnt = qn + n;
+  __syncwarp();
+  if (qn + n >= kPendFlush) sym_flush(prm, prow, pkey, pcnt, lane);
+}
+
 // Row side: the warp inserts the candidates of one stream row (column `col`) into the
 // shared-memory lists of its own rows; returns the lane's updated filter.
 static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists, int k1, unsigned cand, unsigned dv,
@@ -195,7 +275,9 @@ static __device__ __noinline__ void sym_emit(const SymParams& prm, bool hit, uns
   n_real += static_cast<unsigned long long>(n);
 }
 
-template <int P, int W, int MODE>
+// DEFER (kNN mode only, experimental, PG_SYM_DEFER=1): column-side candidates are queued per warp and
+// merged lane-parallel (sym_merge_lanes) instead of being served one event at a time.
+template <int P, int W, int MODE, bool DEFER = false>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __grid_constant__ SymParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
@@ -214,6 +296,19 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   const int lane = tid & 31;
   const int k1 = prm.k1;
   unsigned long long* warp_lists = lists + static_cast<size_t>(warp << 5) * k1;
+  // DEFER: per-warp queue of pending column-side candidates, behind the lists; the pointers are
+  // rebuilt where they are needed (rare path) to keep them out of the hot loop's registers
+  auto pend_key = [&]() { return lists + static_cast<size_t>(kConsumers) * prm.k1 + (threadIdx.x & ~31u); };
+  auto pend_row = [&]() {
+    return reinterpret_cast<unsigned*>(lists + static_cast<size_t>(kConsumers) * prm.k1 + kConsumers) + (threadIdx.x & ~31u);
+  };
+  auto pend_cnt = [&]() {
+    return reinterpret_cast<int*>(lists + static_cast<size_t>(kConsumers) * prm.k1 + kConsumers) + kConsumers + (threadIdx.x >> 5);
+  };
+  if constexpr (DEFER) {
+    if (lane == 0) *pend_cnt() = 0;
+    __syncwarp();
+  }
 
   auto fill_stage = [&](int s, int t) {   // one elected thread: tile t (and its filter words) into ring stage s
     mbar_arrive_expect_tx(&full[s], STAGE_BYTES + TAU_BYTES);
@@ -305,7 +400,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
             const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(dv)) << 32) |
                                             static_cast<unsigned>(r);
             const bool cc = vmask != 0u && mine < lastk;
-            if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
+            if (__any_sync(0xffffffffu, cc)) {
+              if constexpr (DEFER) sym_enqueue(prm, pend_row(), pend_key(), pend_cnt(), col, mine, cc, lane);
+              else sym_serve_col(prm, col, mine, cc, lane);
+            }
           }
         } else {
           const bool hit = (dv + nlo) >= 0 && dv <= hi;
@@ -373,14 +471,21 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
     }
 
     if constexpr (MODE == SYM_KNN) {
-      // merge the chunk's lists into the rows' global lists (ascending keys, one row at a time)
+      // merge the chunk's lists into the rows' global lists
       __syncwarp();
       const long long wrow0 = static_cast<long long>(rb) * kConsumers + (warp << 5);
+      if constexpr (DEFER) {
+        sym_flush(prm, pend_row(), pend_key(), pend_cnt(), lane);
+        const unsigned long long* ml = warp_lists + static_cast<size_t>(lane) * k1;     // every lane: its own row
+        sym_merge_lanes(prm, wrow0 + lane < prm.rows && ml[0] != ~0ull, wrow0 + lane, ml,
+                        k1 >= 32 ? 0xffffffffu : (1u << k1) - 1u);
+      } else {
 #pragma unroll 1
-      for (int src = 0; src < 32; ++src) {
-        if (wrow0 + src >= prm.rows) break;
-        const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
-        sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
+        for (int src = 0; src < 32; ++src) {   // ascending keys, one row at a time
+          if (wrow0 + src >= prm.rows) break;
+          const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
+          sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
+        }
       }
       __syncwarp();
     }
@@ -397,16 +502,17 @@ struct SymLaunch {
   size_t list_bytes;
   cudaStream_t stream;
   int mode = SYM_KNN;
+  int defer = 0;
 };
 
 
 // grid == 0: only report the resident grid (CTAs) through *resident
-template <int P, int W, int MODE>
+template <int P, int W, int MODE, bool DEFER = false>
 int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* resident) {
-  auto kern = sweep_sym_kernel<P, W, MODE>;
+  auto kern = sweep_sym_kernel<P, W, MODE, DEFER>;
   const size_t smem = static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 +
                                                       (MODE == SYM_KNN ? TileCols<W>::value * 8 : 0)) +
-                      2 * kStages * sizeof(uint64_t) + l.list_bytes;
+                      2 * kStages * sizeof(uint64_t) + l.list_bytes + (DEFER ? kConsumers * 12 + 64 : 0);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 0;
   PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSweepThreads, smem));
@@ -421,6 +527,9 @@ int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* residen
 template <int P, int W>
 int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
   if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS>(prm, l, resident);
+  if constexpr (P == 5 && W == 8) {      // the experimental deferred merge is only built for the bench shape
+    if (l.defer) return launch_sweep_sym_mode<P, W, SYM_KNN, true>(prm, l, resident);
+  }
   return launch_sweep_sym_mode<P, W, SYM_KNN>(prm, l, resident);
 }
 
