@@ -753,7 +753,7 @@ int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int pa
   const SymLayout lay = sym_layout(rows, words);
   int t0 = 0, t1 = 0;
   sym_band(lay, rows, boot_rows, part, parts, &t0, &t1);
-  *row_begin = static_cast<int64_t>(t0) * lay.tile_cols;
+  *row_begin = std::min<int64_t>(rows, static_cast<int64_t>(t0) * lay.tile_cols);
   *row_end = std::min<int64_t>(rows, static_cast<int64_t>(t1) * lay.tile_cols);
   return PG_OK;
 }

@@ -229,3 +229,42 @@ def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
         # eps=2 and its similarity form took the symmetric sweep; `d != 2` keeps nearly every pair
         # (dense: above graph.SYM_EPS_MAX_DEGREE for n=1301, not a range for n=700) -> one-sided passes
         assert z["calls"][3] == 2
+
+
+def test_symmetric_band_planner_partitions_and_balances():
+    """pg_knn_sym_band (host-only planner of the multi-GPU symmetric builds): the bands of stream
+    rows tile [0, n) in order, start on stream-tile boundaries, and hold equal shares of the
+    triangle's pair evaluations (to within one tile column of the triangle)."""
+    import ctypes as C
+    from prograph_b200 import _lib
+    lib = _lib.load()
+
+    def band(n, words, boot, part, parts):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(lib.pg_knn_sym_band(n, words, boot, part, parts, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def evaluations(n, boot, lo, hi):
+        """pairs swept by all 256-row blocks inside stream rows [lo, hi)"""
+        total = 0
+        for a in range(0, n, 256):
+            b = min(n, a + 256)
+            start = max(boot if a < boot else a, lo)
+            total += (b - a) * max(0, hi - start)
+        return total
+
+    for n, words, boot in ((1_000_000, 8, 8192), (160_000, 2, 8192), (70_000, 8, 8192), (5000, 1, 0), (513, 16, 512)):
+        tile = 32 if words > 16 else 512 // words
+        for parts in (1, 2, 3, 8):
+            bands = [band(n, words, boot, g, parts) for g in range(parts)]
+            assert bands[0][0] == 0 and bands[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(a % tile == 0 or a == n for a, _ in bands)
+            work = [evaluations(n, boot, a, b) for a, b in bands]
+            assert sum(work) == evaluations(n, boot, 0, n)
+            if n >= 70_000:
+                ideal = sum(work) / parts
+                assert max(work) - ideal <= n * tile + 1, (n, parts, work)      # one tile column of slack
+    with pytest.raises(ValueError):
+        band(1000, 8, 0, 3, 3)
