@@ -22,6 +22,12 @@
 // shared-memory lists empty but seeds its filter from the row's global list, and merges its lists
 // into the global ones when it ends, so chunks can be short (good load balance) without the
 // cold-start insertion storm of the split lists in pg_sweep.cuh.
+// Bootstrap: the host first sweeps all rows one-sided against the first boot_rows columns
+// (pg_hamming_knn_boot) so that every filter is tight from the first symmetric tile on; the row
+// blocks of those rows ("boot" items) then run row side only, behind the bootstrap columns.
+// Epsilon mode (SYM_EPS) is the same sweep with another consumer (prograph.py:731-753): a pair whose
+// distance lies in [lo, hi] appends both directed edges as packed 64-bit keys to a global buffer,
+// which the host sorts into the CSR (pg_edge_keys_to_csr) -- no count pass, no second sweep.
 #pragma once
 #include "pg_sweep.cuh"
 

@@ -267,6 +267,8 @@ class CudaEngine:
         """Edge keys (any order, sentinels -1) -> CSR (indptr, idx, w) with rows ascending and, within
         a row, ascending neighbour index (pg_edge_keys_to_csr)."""
         keys = keys.contiguous()
+        if keys.numel() >= (1 << 31):
+            raise L.Unsupported("edge list too long for one key sort")
         alt = self.empty((keys.numel(),), torch.int64)
         indptr = self.empty((rows + 1,), torch.int64)
         idx = self.empty((nnz,), torch.int64)

@@ -233,7 +233,7 @@ def _sym_enabled(eng, packed, k1, world):
     force = os.environ.get("PG_KNN_SYM")
     if force is not None:
         return force not in ("0", "")
-    return packed.rows >= SYM_MIN_ROWS and k1 <= getattr(eng, "SYM_MAX_LIST", 0)
+    return SYM_MIN_ROWS <= packed.rows < (1 << 31) and k1 <= getattr(eng, "SYM_MAX_LIST", 0)
 
 
 def sym_boot_rows(n):
@@ -334,6 +334,8 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
             if degree > SYM_EPS_MAX_DEGREE and force is None:
                 raise L.Unsupported("dense graph")
             capacity = int(1.5 * degree * n / parts) + (4 << 20)
+            if capacity * parts >= (1 << 31):          # one radix sort takes fewer than 2^31 keys
+                raise L.Unsupported("edge list too long for one key sort")
             keys, edges = eng.hamming_eps_sym(packed, lut, rank if sharded else 0, parts, mode=1 if sharded else 0,
                                               capacity=capacity)
             if sharded:
