@@ -268,3 +268,41 @@ def test_symmetric_band_planner_partitions_and_balances():
                 assert max(work) - ideal <= n * tile + 1, (n, parts, work)      # one tile column of slack
     with pytest.raises(ValueError):
         band(1000, 8, 0, 3, 3)
+
+
+def test_symmetric_build_policies():
+    """Host-side choices around the symmetric sweeps: bootstrap size, degree-sample rows, and the
+    switches that keep small / unusual builds on the one-sided kernels."""
+    from prograph_b200 import graph
+
+    class Eng:                      # the attributes _sym_enabled looks at
+        SYM_MAX_LIST = 32
+
+        def hamming_knn_sym(self):
+            pass
+
+    class Tab:
+        def __init__(self, rows):
+            self.rows = rows
+
+    assert graph.sym_boot_rows(1_000_000) == 8192 and graph.sym_boot_rows(70_000) == 8192
+    assert graph.sym_boot_rows(65_536) == 8192 and graph.sym_boot_rows(40_000) == 4608
+    assert graph.sym_boot_rows(4000) == 0 and graph.sym_boot_rows(4096) == 512
+    assert all(graph.sym_boot_rows(n) % 512 == 0 and graph.sym_boot_rows(n) <= max(0, n // 8) for n in range(1, 200_000, 997))
+    for n in (5, 600, 32_768, 160_000, 1_000_000):
+        r0, rows = graph._eps_sample(n)
+        assert 0 <= r0 and r0 + rows <= n and rows >= min(n, 512) and rows <= 2048 and r0 % 512 == 0
+    old = os.environ.pop("PG_KNN_SYM", None)
+    try:
+        assert graph._sym_enabled(Eng(), Tab(graph.SYM_MIN_ROWS), 17, 1)
+        assert not graph._sym_enabled(Eng(), Tab(graph.SYM_MIN_ROWS - 1), 17, 1)
+        assert not graph._sym_enabled(Eng(), Tab(1_000_000), 33, 1)          # list too long for the symmetric sweep
+        assert not graph._sym_enabled(object(), Tab(1_000_000), 17, 1)       # an engine without the symmetric kernels
+        os.environ["PG_KNN_SYM"] = "0"
+        assert not graph._sym_enabled(Eng(), Tab(1_000_000), 17, 1)
+        os.environ["PG_KNN_SYM"] = "1"
+        assert graph._sym_enabled(Eng(), Tab(100), 17, 1)
+    finally:
+        os.environ.pop("PG_KNN_SYM", None)
+        if old is not None:
+            os.environ["PG_KNN_SYM"] = old
