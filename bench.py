@@ -349,7 +349,23 @@ def run_b200(args):
         torch.set_num_threads(cores)
         cpu_reference_batches(tokens, k, 1)
         p, dt, done = cpu_reference_batches(tokens, k, 16, budget_s=20.0)
-        cpu = {"value": p / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+        # second, best-effort CPU number: uint8 compare + partial selection on all
+        # cores, so that the reported baseline is not handicapped by fp16-on-CPU and the full sort
+        best = None
+        try:
+            from oracle import prograph_oracle as O
+            O.knn_batch_uint8(tokens, tokens[:8], k, threads=cores)
+            t0, nb = time.perf_counter(), 0
+            while nb < 16 and time.perf_counter() - t0 < 8.0:
+                O.knn_batch_uint8(tokens, tokens[8 * nb:8 * nb + 8], k, threads=cores)
+                nb += 1
+            bt = time.perf_counter() - t0
+            best = {"value": nb * 8 * n / bt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{nb * 8} query rows x all {n} columns (numpy uint8 compare in column chunks on "
+                              f"{cores} threads, partial selection of the k+1 smallest (distance, index) keys)"}
+        except Exception as exc:            # a reported extra, never a reason to lose the bench line
+            best = {"error": repr(exc)}
+        cpu = {"value": p / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "best_effort": best,
                "sample": f"{done * 8} query rows x all {n} columns (reference batches of 8, fp16 compare + full "
                          f"sort per row, torch CPU with {cores} threads); extrapolated full build "
                          f"{pairs / (p / dt) / 3600:.1f} h"}

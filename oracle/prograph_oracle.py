@@ -348,3 +348,29 @@ def reference_knn_batch_torch(X, batch, k, similarity=False):
         d = 1 / (1 + d)
     s = torch.sort(d, dim=1, descending=similarity, stable=True)
     return s.indices[:, 1:k + 1].numpy(), s.values[:, 1:k + 1].numpy()
+
+
+def knn_batch_uint8(tokens_u8, batch_u8, k, threads=1, chunk=32768):
+    """Best-effort CPU restatement of one kNN batch (hamming.py:34 + prograph.py:757-762) for the
+    bench's second baseline: uint8 compare instead of the fp16 staging, column chunks spread
+    over `threads` threads (numpy releases the GIL in the compare / sum), and a partial selection
+    of the k+1 smallest (distance, index) keys instead of the reference's full sort.  Same
+    result as knn_from_distances(hamming(...), k)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = tokens_u8.shape[0]
+    bounds = list(range(0, n, chunk)) + [n]
+
+    def part(i):
+        a, b = bounds[i], bounds[i + 1]
+        return (tokens_u8[None, a:b, :] != batch_u8[:, None, :]).sum(axis=2, dtype=np.int32)
+
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as pool:
+            parts = list(pool.map(part, range(len(bounds) - 1)))
+    else:
+        parts = [part(i) for i in range(len(bounds) - 1)]
+    D = np.concatenate(parts, axis=1)                                   # (batch, n) int32
+    keys = (D.astype(np.int64) << 32) | np.arange(n, dtype=np.int64)[None, :]
+    kk = min(k + 1, n)
+    sel = np.sort(np.partition(keys, kk - 1, axis=1)[:, :kk], axis=1)[:, 1:]
+    return (sel & 0xffffffff).astype(np.int64), (sel >> 32).astype(np.int64)

@@ -255,3 +255,16 @@ def test_library(g_library):
     same(O.calc_neighbours(tok, 9, eps=2), g["cn_9_eq2"])
     same(O.calc_neighbours(tok, 5, eps=0), g["cn_5_eq0"])
     same(np.where(O.neighbourhood_mask(tok, 9, 2))[0], g["nh_9_2"])
+
+
+def test_best_effort_uint8_batch_matches_the_restatement():
+    """bench.py's second CPU baseline (oracle.knn_batch_uint8) returns what the pinned
+    restatement returns, ties included."""
+    rng = np.random.default_rng(4)
+    X = rng.integers(1, 4, size=(3000, 40)).astype(np.uint8)
+    for threads, chunk in ((1, 32768), (3, 700)):
+        idx, w = O.knn_batch_uint8(X, X[100:108], 16, threads=threads, chunk=chunk)
+        D = O.hamming(X.astype(np.int64), X[100:108].astype(np.int64))
+        ri, rw = O.knn_from_distances(D, 16)
+        np.testing.assert_array_equal(idx, ri)
+        np.testing.assert_array_equal(w, rw)
