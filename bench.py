@@ -365,7 +365,19 @@ def run_b200(args):
                               f"{cores} threads, partial selection of the k+1 smallest (distance, index) keys)"}
         except Exception as exc:            # a reported extra, never a reason to lose the bench line
             best = {"error": repr(exc)}
+        # third: the C restatement (oracle/hamming_knn_cpu.c: bit planes + popcount + sorted k+1 lists on
+        # all cores), timed in a child process so that nothing it does can cost the bench line
+        best_c = None
+        try:
+            out = subprocess.run([sys.executable, "-m", "oracle.c_oracle", "--n", str(n), "--length", str(L), "--k", str(k),
+                                  "--rows", "512", "--threads", str(cores), "--dist", args.dist], cwd=ROOT,
+                                 capture_output=True, text=True, timeout=180)
+            lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+            best_c = json.loads(lines[-1]) if lines else {"error": (out.stderr or "no output")[-300:]}
+        except Exception as exc:
+            best_c = {"error": repr(exc)}
         cpu = {"value": p / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "best_effort": best,
+               "best_effort_c": best_c,
                "sample": f"{done * 8} query rows x all {n} columns (reference batches of 8, fp16 compare + full "
                          f"sort per row, torch CPU with {cores} threads); extrapolated full build "
                          f"{pairs / (p / dt) / 3600:.1f} h"}

@@ -268,3 +268,33 @@ def test_best_effort_uint8_batch_matches_the_restatement():
         ri, rw = O.knn_from_distances(D, 16)
         np.testing.assert_array_equal(idx, ri)
         np.testing.assert_array_equal(w, rw)
+
+
+def test_c_restatement_matches_the_numpy_oracle():
+    """oracle/hamming_knn_cpu.c (built by `make -C oracle`, i.e. by __graft_entry__.build()): packed
+    bit planes + popcount + sorted k+1 lists return exactly what the pinned numpy restatement
+    returns -- duplicates, heavy ties, ragged widths, fewer rows than k+1, row sub-ranges, threads."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, capture_output=True)
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(1)
+    for n, L, k, alphabet in ((3000, 256, 16, 20), (500, 40, 5, 3), (10, 3, 16, 3), (2000, 100, 31, 20), (700, 64, 1, 2)):
+        X = rng.integers(1, alphabet + 1, size=(n, L)).astype(np.uint8)
+        if n > 200:
+            X[100] = X[99]
+        planes = CO.pack(X)
+        np.testing.assert_array_equal(planes, CO.pack(X, use_c=True))
+        ri, rw = O.knn_from_distances(O.hamming(X.astype(np.int64), X.astype(np.int64)), k)
+        kk = ri.shape[1]
+        for threads in (1, 3):
+            idx, d = CO.hamming_knn(planes, L, 0, n, k, threads=threads)
+            np.testing.assert_array_equal(idx[:, :kk], ri)
+            np.testing.assert_array_equal(d[:, :kk], rw)
+            assert np.all(idx[:, kk:] == -1)
+        lo, cnt = 7, min(13, n - 7)
+        idx, d = CO.hamming_knn(planes, L, lo, cnt, k, threads=2)
+        np.testing.assert_array_equal(idx[:, :kk], ri[lo:lo + cnt])
+    with pytest.raises(OverflowError):
+        CO.pack(np.full((4, 8), 40, dtype=np.uint8))
