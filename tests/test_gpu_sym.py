@@ -134,6 +134,27 @@ def test_symmetric_knn_degenerate_tables(eng):
     np.testing.assert_array_equal(eps.idx[:20000], odd[:20000])  # row 0: all odd rows, ascending
 
 
+def test_symmetric_knn_deferred_merge_variant(eng, monkeypatch):
+    """The opt-in instantiation (PG_SYM_DEFER=1, planes 5 / words 8): column-side candidates queued
+    per warp and merged lane-parallel.  Same lists, whatever the arrival order."""
+    monkeypatch.setenv("PG_SYM_DEFER", "1")
+    rng = np.random.default_rng(77)
+    for n in (513, 3000):
+        X = mutational(rng, n, 256)
+        tab = eng.pack(X.astype(np.uint8))
+        ri, rw = O.knn_from_distances(O.hamming(X, X), 16)
+        for world, boot, mode in ((1, 0, 0), (1, 512, 0), (2, 0, 1)):
+            idx, w = sym_knn(eng, tab, 16, world=world, boot=boot, mode=mode)
+            np.testing.assert_array_equal(np_(idx), ri)
+            np.testing.assert_array_equal(np_(w), rw)
+    U = rng.integers(1, 21, size=(2100, 256)).astype(np.int64)          # heavy ties
+    tab = eng.pack(U)
+    ri, rw = O.knn_from_distances(O.hamming(U, U), 31)
+    idx, w = sym_knn(eng, tab, 31, boot=512)
+    np.testing.assert_array_equal(np_(idx), ri)
+    np.testing.assert_array_equal(np_(w), rw)
+
+
 def test_symmetric_unsupported_shapes_fall_back(eng):
     """Lists longer than 32 entries are not covered: the engine says so and build_neighbours
     takes the one-sided sweep (never a CPU path)."""
