@@ -114,8 +114,12 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
  * (256 rows) part, part + parts, ...; mode 1 gives it every row block restricted to a band of
  * stream rows (pg_knn_sym_band; bands hold equal numbers of pair evaluations), so that a row's
  * column-side candidates all meet on one rank.  The call leaves in lists[r*k1 .. r*k1+k1) the k1
- * smallest keys  distance<<32 | index  this rank saw for row r, ascending, ~0 = empty.  With several ranks the per-rank lists are all-gathered and
- * merged by pg_knn_lists_finalize.  k1 <= 32; wider lists take pg_hamming_knn.
+ * smallest keys  distance<<32 | index  this rank saw for row r, ascending, ~0 = empty.  With several
+ * ranks the per-rank lists are exchanged (all-to-all: every rank receives all ranks' lists of its own
+ * rows), merged by pg_knn_lists_merge, all-gathered as 8-byte keys and widened by
+ * pg_knn_lists_finalize.  k1 <= 32; wider lists take pg_hamming_knn.
+ * Row locks: a lock that cannot be taken within 2^24 attempts sets an error word in the workspace
+ * instead of trapping; pg_knn_sym_status (synchronises the stream) turns it into PG_ERR_CUDA.
  *
  * Bootstrap (boot_rows > 0, a multiple of 512): the caller first runs pg_hamming_knn_boot, which
  * sweeps rows [row0,row0+rows) one-sided against table rows [0,boot_rows) and writes their
@@ -130,9 +134,19 @@ int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0,
 int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int words, int k1,
                        int part, int parts, int mode, int64_t boot_rows, uint64_t* lists,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* after pg_hamming_knn_sym on the same workspace / stream: PG_OK, or PG_ERR_CUDA if the sweep gave
+ * up on a row lock (its lists are then incomplete).  Synchronises `stream`.  */
+int pg_knn_sym_status(const void* workspace, int64_t rows, int words, void* stream);
 /* host only: the stream rows [row_begin, row_end) of band `part` of `parts` (mode 1) */
 int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int parts,
                     int64_t* row_begin, int64_t* row_end);
+/* host only: the work items (row block, first tile, end tile, boot flag: 4 x int32 each) the
+ * symmetric sweeps deal to a persistent grid of `grid` CTAs, in dealing order: CTA b takes items
+ * b, b + grid, ...  Items are ordered by L2-sized column bands (PG_SYM_BAND_MB, default 24 MB) so
+ * that co-resident CTAs stream the same part of the table.  *n_items = number of items;
+ * items_host may be NULL (count only) or hold `capacity` items.  */
+int pg_knn_sym_plan(int64_t rows, int planes, int words, int64_t boot_rows, int part, int parts,
+                    int mode, int grid, int32_t* items_host, int64_t capacity, int64_t* n_items);
 /* Symmetric epsilon graph of a table against itself (prograph.py:731-753): one sweep over the
  * triangle of unordered pairs appends BOTH directed edges of every pair whose distance passes the
  * truth table `lut_host` (which must be one contiguous range of distances, else
@@ -159,6 +173,11 @@ int pg_edge_keys_to_csr(uint64_t* keys, int64_t n_keys, uint64_t* keys_alt, int6
 int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride,
                           int64_t row0, int64_t rows, int k1, int k, int drop, int weight,
                           int64_t* out_idx, void* out_w, void* stream);
+/* the same merge, keeping the 8-byte keys: out_keys[(r-row0)*k + j], ~0 = missing (what the ranks
+ * of a multi-GPU build all-gather before widening with pg_knn_lists_finalize(n_lists=1, drop=0)) */
+int pg_knn_lists_merge(const uint64_t* lists, int n_lists, int64_t list_stride,
+                       int64_t row0, int64_t rows, int k1, int k, int drop,
+                       uint64_t* out_keys, void* stream);
 
 /* epsilon graph, pass 1 (prograph.py:731-736): per own row, the number of stream rows
  * whose distance d has bit d set in `lut` (a host array of (L+32)/32 words: the

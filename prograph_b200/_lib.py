@@ -48,6 +48,9 @@ SIGNATURES = {
     "pg_edge_keys_to_csr": (_i, [_vp, _i64, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "pg_knn_sym_band": (_i, [_i64, _i, _i64, _i, _i, _pi64, _pi64]),
     "pg_knn_lists_finalize": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pg_knn_lists_merge": (_i, [_vp, _i, _i64, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "pg_knn_sym_status": (_i, [_vp, _i64, _i, _vp]),
+    "pg_knn_sym_plan": (_i, [_i64, _i, _i, _i64, _i, _i, _i, _i, _vp, _i64, _pi64]),
     "pg_hamming_eps_count": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pg_hamming_eps_fill": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "pg_hamming_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i64, _vp]),

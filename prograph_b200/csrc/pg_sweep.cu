@@ -157,43 +157,72 @@ static bool lut_as_range(const uint32_t* lut, int lut_words, int* lo, unsigned* 
   return true;
 }
 
+// ---- coalesced write-out of per-row results -------------------------------------------------
+// The merge kernels below run one thread per row; a thread that stored its k results straight to
+// out[r * k + j] would touch 32 different 128-byte lines per store instruction.  Instead every
+// thread parks its row in shared memory (row stride k + 1 keys: conflict-free 8-byte accesses) and
+// the block writes its rows * k outputs contiguously.
+__device__ __forceinline__ void emit_key(unsigned long long best, long long at, int weight, bool keys_out,
+                                         unsigned long long* out_keys, long long* out_idx, void* out_w) {
+  if (keys_out) {
+    out_keys[at] = best;
+  } else if (best == ~0ull) {
+    out_idx[at] = -1;
+    write_weight(out_w, at, 0, weight);
+  } else {
+    out_idx[at] = static_cast<long long>(best & 0xffffffffull);
+    write_weight(out_w, at, static_cast<int>(best >> 32), weight);
+  }
+}
+
+__device__ __forceinline__ void flush_rows(const unsigned long long* sm, long long row_base, long long rows, int kk,
+                                           int weight, bool keys_out, unsigned long long* out_keys, long long* out_idx,
+                                           void* out_w) {
+  __syncthreads();
+  const long long here = min(static_cast<long long>(blockDim.x), rows - row_base);
+  const int total = static_cast<int>(here) * kk;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int r = e / kk, j = e - r * kk;
+    emit_key(sm[r * (kk + 1) + j], row_base * kk + e, weight, keys_out, out_keys, out_idx, out_w);
+  }
+}
+
+static int rows_per_merge_block(int kk) { return kk <= 32 ? 128 : 32; }
+static size_t merge_smem_bytes(int kk) { return static_cast<size_t>(rows_per_merge_block(kk)) * (kk + 1) * 8; }
+
 // ---- kNN: merge the per-split lists, drop leading entries, widen ---------------------
 __global__ void knn_finalize_kernel(const unsigned long long* __restrict__ part, int n_splits, int k1, long long rows,
                                     int k, int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
-  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows) return;
-  unsigned long long last = 0;
-  bool have_last = false;
-  for (int j = 0; j < drop + k; ++j) {
-    unsigned long long best = ~0ull;
-    if (n_splits == 1) {
-      best = j < k1 ? part[static_cast<size_t>(j) * rows + r] : ~0ull;
-    } else {
-      // keys are unique (index in the low word), so "smallest key above the last one" walks
-      // the merged order; each split list is ascending, stop at the first usable entry
-      for (int s = 0; s < n_splits; ++s) {
-        const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
-        for (int i = 0; i < k1; ++i) {
-          const unsigned long long v = lst[static_cast<size_t>(i) * rows];
-          if (have_last && v <= last) continue;
-          if (v < best) best = v;
-          break;
+  extern __shared__ unsigned long long merge_sm[];
+  const long long row_base = blockIdx.x * static_cast<long long>(blockDim.x);
+  const long long r = row_base + threadIdx.x;
+  unsigned long long* mine = merge_sm + threadIdx.x * (k + 1);
+  if (r < rows) {
+    unsigned long long last = 0;
+    bool have_last = false;
+    for (int j = 0; j < drop + k; ++j) {
+      unsigned long long best = ~0ull;
+      if (n_splits == 1) {
+        best = j < k1 ? part[static_cast<size_t>(j) * rows + r] : ~0ull;
+      } else {
+        // keys are unique (index in the low word), so "smallest key above the last one" walks
+        // the merged order; each split list is ascending, stop at the first usable entry
+        for (int s = 0; s < n_splits; ++s) {
+          const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
+          for (int i = 0; i < k1; ++i) {
+            const unsigned long long v = lst[static_cast<size_t>(i) * rows];
+            if (have_last && v <= last) continue;
+            if (v < best) best = v;
+            break;
+          }
         }
       }
-    }
-    last = best;
-    have_last = true;
-    if (j >= drop) {
-      const long long at = r * k + (j - drop);
-      if (best == ~0ull) {
-        out_idx[at] = -1;
-        write_weight(out_w, at, 0, weight);
-      } else {
-        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
-        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
-      }
+      last = best;
+      have_last = true;
+      if (j >= drop) mine[j - drop] = best;
     }
   }
+  flush_rows(merge_sm, row_base, rows, k, weight, false, nullptr, out_idx, out_w);
 }
 
 __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, int n_splits, long long rows,
@@ -245,6 +274,13 @@ static size_t eps_list_bytes(long long rows) { return static_cast<size_t>(rows) 
 
 
 // ---- symmetric kNN sweep (pg_sweep_sym.cuh): host side ---------------------------------
+// Paired-lane instantiation: on by default where a half row is at least one 128-bit load
+// (PG_SYM_PAIR=0/1 overrides, for A/B measurements).
+static int sym_pair_default(int words) {
+  if (const char* ev = std::getenv("PG_SYM_PAIR")) return std::atoi(ev) != 0 && words >= 2;
+  return words >= 8 ? 1 : 0;
+}
+
 static int dispatch_sym(int planes, int words, const SymParams& prm, const SymLaunch& l, int* resident) {
 #define PG_CASE(P, W) \
   if (planes == P && words == W) return sweep_sym_p##P##_w##W(prm, l, resident);
@@ -261,24 +297,40 @@ static bool sym_shape_ok(int planes, int words) {
          (planes == 5 && words == 16);
 }
 
-// workspace: [filter words: tiles*tile_cols u64][locks: rows u32][stats][items]
+// workspace: [filter words: tiles*tile_cols u64][locks: rows u32][stats: 8 u64, error word at +64 B][items]
 struct SymLayout {
-  int tile_cols, n_tiles, n_blocks;
+  int tile_cols, n_tiles, n_blocks, band_tiles, n_bands;
   size_t gnt_bytes, lock_bytes, stats_off, item_off, item_bytes_max, total;
 };
 
-static SymLayout sym_layout(long long rows, int words) {
+// Stream tiles per L2-sized column band: co-resident CTAs work inside one band of the table so that
+// its tiles are read from DRAM once and from L2 afterwards (PG_SYM_BAND_MB, default 24 MB of the
+// 126 MB L2; the packed row is at least 5 planes wide, which bounds the band count from above).
+static int sym_band_tiles(int tile_cols, int row_bytes) {
+  double mb = 24.0;
+  if (const char* ev = std::getenv("PG_SYM_BAND_MB")) mb = std::atof(ev);
+  if (mb <= 0) return 1 << 30;                       // 0: one band (the round-1 schedule)
+  long long t = static_cast<long long>(mb * 1048576.0 / (static_cast<double>(tile_cols) * row_bytes));
+  if (t < 64) t = 64;
+  return static_cast<int>(std::min<long long>(t, 1 << 30));
+}
+
+static SymLayout sym_layout(long long rows, int words, int planes = 5) {
   SymLayout s;
   s.tile_cols = tile_cols_for(words);
   s.n_tiles = static_cast<int>(ceil_div(rows, s.tile_cols));
   s.n_blocks = static_cast<int>(ceil_div(rows, kConsumers));
+  s.band_tiles = sym_band_tiles(s.tile_cols, planes * words * 4);
+  s.n_bands = static_cast<int>(ceil_div(s.n_tiles, s.band_tiles));
   s.gnt_bytes = static_cast<size_t>(round_up(static_cast<int64_t>(s.n_tiles) * s.tile_cols * 8, 256));
   s.lock_bytes = static_cast<size_t>(round_up(rows * 4, 256));
   s.stats_off = s.gnt_bytes + s.lock_bytes;
   s.item_off = s.stats_off + 256;
-  // every row block contributes at most ceil(len / chunk) <= len / chunk + 1 items and the planner
-  // keeps sum(len) / chunk below 64 items per resident CTA (<= 4 CTAs per SM)
-  s.item_bytes_max = (2 * static_cast<size_t>(s.n_blocks) + 64ull * 4 * 160 + 1024) * sizeof(SymItem);
+  // a row block contributes at most len / chunk + 2 items per band it crosses and the planner keeps
+  // sum(len) / chunk below 64 items per resident CTA (<= 4 CTAs per SM); sized for 8 planes (most bands)
+  const int bands8 = static_cast<int>(ceil_div(s.n_tiles, sym_band_tiles(s.tile_cols, 8 * words * 4)));
+  s.item_bytes_max = (static_cast<size_t>(s.n_blocks) * (2 * static_cast<size_t>(bands8) + 2) + 64ull * 4 * 160 + 1024) *
+                         sizeof(SymItem) + 8192;       // + the per-CTA offsets
   s.total = s.item_off + s.item_bytes_max;
   return s;
 }
@@ -316,64 +368,109 @@ static void sym_band(const SymLayout& s, long long rows, long long boot_rows, in
   *t1 = bound(part + 1);
 }
 
-// Chunks of (row block, tile range), longest first, dealt to the persistent grid in snake
-// order so that every CTA gets the same number of tiles to within one short chunk.  Chunk
-// boundaries are shifted from row block to row block so that CTAs that start together do not
-// walk the same stream rows in lockstep (they would fight for the same row locks).
+// Chunks of (row block, tile range) for the persistent grid.  The column range of the sweep is cut
+// into L2-sized bands (SymLayout::band_tiles) and the chunks are handed out band by band: at any
+// time the resident CTAs stream tiles of ONE band, which then comes out of L2 instead of DRAM
+// (round 1 walked the whole 160 MB table from 296 different positions: 115 GB of DRAM reads per
+// build).  Every CTA gets its own item list (SymPlan::first): inside a band the chunks go, longest
+// first, to the CTA with the least work so far, so the CTAs reach the end of every band -- and of
+// the sweep -- together to within one short chunk.  Chunk boundaries are phase-shifted from row block
+// to row block so that CTAs that start together do not walk the same stream rows in lockstep (they
+// would fight for the same row locks).
 // mode 0: this rank takes row blocks part, part+parts, ... over their whole tile range;
 // mode 1: every row block, restricted to this rank's column band (sym_band).
-static std::vector<SymItem> sym_plan(const SymLayout& s, long long rows, int part, int parts, int mode, int grid,
-                                     long long boot_rows) {
+struct SymPlan {
+  std::vector<SymItem> items;   // CTA-major: CTA b owns items [first[b], first[b+1])
+  std::vector<int> first;       // grid + 1 offsets
+  int grid = 0;                 // CTAs that have work
+};
+
+static SymPlan sym_plan(const SymLayout& s, long long rows, int part, int parts, int mode, int grid,
+                        long long boot_rows) {
   const int boot_blocks = static_cast<int>(boot_rows / kConsumers);
   int band0 = 0, band1 = s.n_tiles;
   if (mode == 1) sym_band(s, rows, boot_rows, part, parts, &band0, &band1);
   const int rb_first = mode == 1 ? 0 : part, rb_stride = mode == 1 ? 1 : parts;
-  auto range = [&](int rb, int* a, int* b) {
-    *a = std::max(sym_first_tile(s, rb, boot_rows), band0);
-    *b = band1;
-  };
   long long total = 0;
-  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride) {
-    int a, b;
-    range(rb, &a, &b);
-    total += std::max(0, b - a);
-  }
+  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride)
+    total += std::max(0, band1 - std::max(sym_first_tile(s, rb, boot_rows), band0));
   long long chunk = ceil_div(total, static_cast<long long>(grid) * 24);
   if (const char* ev = std::getenv("PG_SYM_CHUNK")) chunk = std::atoll(ev);
+  // L2 bands of equal width over this rank's column range
+  const int span = std::max(0, band1 - band0);
+  const int n_sub = std::max(1, static_cast<int>(ceil_div(span, s.band_tiles)));
+  const int sub_w = std::max(1, static_cast<int>(ceil_div(span, n_sub)));
+  if (n_sub > 1 && chunk > sub_w / 2) chunk = sub_w / 2;     // at least two phase-shifted chunks per band crossing
   if (chunk < 32) chunk = 32;
-  std::vector<SymItem> items;
-  unsigned n_seen = 0;
-  for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride, ++n_seen) {
-    int tb, te;
-    range(rb, &tb, &te);
-    if (te <= tb) continue;
-    const int boot = rb < boot_blocks ? 1 : 0;
-    // golden-ratio phase of the first boundary, in (chunk/4, 5*chunk/4]
-    const double frac = (n_seen * 0.6180339887498949) - static_cast<long long>(n_seen * 0.6180339887498949);
-    int t = tb;
-    const int first = static_cast<int>(chunk / 4 + static_cast<long long>(frac * static_cast<double>(chunk))) + 1;
-    while (t < te) {
-      int t1 = t + (t == tb ? first : static_cast<int>(chunk));
-      if (te - t1 < chunk / 4) t1 = te;     // no crumbs at the end
-      if (t1 > te) t1 = te;
-      items.push_back(SymItem{rb, t, t1, boot});
-      t = t1;
+  std::vector<std::vector<SymItem>> per_cta(static_cast<size_t>(grid));
+  std::vector<long long> load(static_cast<size_t>(grid), 0);
+  // min-heap of (load, cta)
+  auto heavier = [&](int a, int b) { return load[a] != load[b] ? load[a] > load[b] : a > b; };
+  std::vector<int> heap(static_cast<size_t>(grid));
+  for (int sb = 0; sb < n_sub; ++sb) {
+    const int sb0 = band0 + sb * sub_w, sb1 = std::min(band1, sb0 + sub_w);
+    std::vector<SymItem> items;
+    unsigned n_seen = 0;
+    for (int rb = rb_first; rb < s.n_blocks; rb += rb_stride, ++n_seen) {
+      const int tb = std::max(sym_first_tile(s, rb, boot_rows), sb0), te = sb1;
+      if (te <= tb) continue;
+      const int boot = rb < boot_blocks ? 1 : 0;
+      // golden-ratio phase of the first boundary, in (chunk/4, 5*chunk/4]
+      const double g = (n_seen + 0.37 * sb) * 0.6180339887498949;
+      const double frac = g - static_cast<long long>(g);
+      int t = tb;
+      const int first = static_cast<int>(chunk / 4 + static_cast<long long>(frac * static_cast<double>(chunk))) + 1;
+      while (t < te) {
+        int t1 = t + (t == tb ? first : static_cast<int>(chunk));
+        if (te - t1 < chunk / 4) t1 = te;     // no crumbs at the end
+        if (t1 > te) t1 = te;
+        items.push_back(SymItem{rb, t, t1, boot});
+        t = t1;
+      }
+    }
+    std::stable_sort(items.begin(), items.end(),
+                     [](const SymItem& a, const SymItem& b) { return a.t1 - a.t0 > b.t1 - b.t0; });
+    for (int b = 0; b < grid; ++b) heap[b] = b;
+    std::make_heap(heap.begin(), heap.end(), heavier);
+    for (const SymItem& it : items) {
+      std::pop_heap(heap.begin(), heap.end(), heavier);
+      const int b = heap.back();
+      per_cta[b].push_back(it);
+      load[b] += (it.t1 - it.t0) + 4;          // + a fixed per-item cost (own-row load, list merge)
+      std::push_heap(heap.begin(), heap.end(), heavier);
     }
   }
-  std::stable_sort(items.begin(), items.end(),
-                   [](const SymItem& a, const SymItem& b) { return a.t1 - a.t0 > b.t1 - b.t0; });
-  const size_t n = items.size();
-  std::vector<SymItem> dealt(n);
-  for (size_t base = 0, round = 0; base < n; base += grid, ++round) {
-    const size_t in_round = std::min<size_t>(grid, n - base);
-    for (size_t b = 0; b < in_round; ++b) dealt[base + b] = items[base + ((round & 1) ? in_round - 1 - b : b)];
+  SymPlan plan;
+  plan.first.push_back(0);
+  for (int b = 0; b < grid; ++b) {
+    if (per_cta[b].empty()) continue;
+    plan.items.insert(plan.items.end(), per_cta[b].begin(), per_cta[b].end());
+    plan.first.push_back(static_cast<int>(plan.items.size()));
   }
-  return dealt;
+  plan.grid = static_cast<int>(plan.first.size()) - 1;
+  return plan;
+}
+
+// item table in the workspace: [first: grid + 1 ints, padded to 16 B][items]
+static size_t sym_plan_bytes(const SymPlan& p) {
+  return static_cast<size_t>(round_up(static_cast<int64_t>(p.first.size()) * 4, 16)) + p.items.size() * sizeof(SymItem);
+}
+static int sym_upload_plan(const SymPlan& p, const SymLayout& lay, char* wsb, SymParams* prm, cudaStream_t cs) {
+  PG_CHECK_ARG(sym_plan_bytes(p) <= lay.item_bytes_max, "item table overflow (%zu items)", p.items.size());
+  const size_t first_bytes = static_cast<size_t>(round_up(static_cast<int64_t>(p.first.size()) * 4, 16));
+  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off, p.first.data(), p.first.size() * 4, cudaMemcpyHostToDevice, cs));
+  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off + first_bytes, p.items.data(), p.items.size() * sizeof(SymItem),
+                          cudaMemcpyHostToDevice, cs));
+  // the vectors die with the caller: pageable copies are staged by the runtime before returning
+  prm->cta_first = reinterpret_cast<const int*>(wsb + lay.item_off);
+  prm->items = reinterpret_cast<const SymItem*>(wsb + lay.item_off + first_bytes);
+  prm->n_items = static_cast<int>(p.items.size());
+  return PG_OK;
 }
 
 __global__ void sym_init_kernel(unsigned long long* glist, long long n_keys, unsigned long long* glast, long long n_gnt, unsigned* glock,
                                 long long rows, unsigned long long* stats, int k1, int seeded) {
-  if (blockIdx.x == 0 && threadIdx.x < 8) stats[threadIdx.x] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x < 9) stats[threadIdx.x] = 0ull;      // 8 counters + the error word
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   if (!seeded)
@@ -389,104 +486,121 @@ __global__ void sym_init_kernel(unsigned long long* glist, long long n_keys, uns
 // bootstrap: merged split lists [n_splits][k1][rows] -> row-major key lists [rows][k1]
 __global__ void knn_part_to_lists_kernel(const unsigned long long* __restrict__ part, int n_splits, int k1,
                                          long long rows, unsigned long long* __restrict__ lists) {
-  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows) return;
-  unsigned long long last = 0;
-  for (int j = 0; j < k1; ++j) {
-    unsigned long long best = ~0ull;
-    for (int s = 0; s < n_splits; ++s) {
-      const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
-      for (int i = 0; i < k1; ++i) {
-        const unsigned long long v = lst[static_cast<size_t>(i) * rows];
-        if (j > 0 && v <= last) continue;
-        if (v < best) best = v;
-        break;
+  extern __shared__ unsigned long long merge_sm[];
+  const long long row_base = blockIdx.x * static_cast<long long>(blockDim.x);
+  const long long r = row_base + threadIdx.x;
+  unsigned long long* mine = merge_sm + threadIdx.x * (k1 + 1);
+  if (r < rows) {
+    unsigned long long last = 0;
+    bool ended = false;
+    for (int j = 0; j < k1; ++j) {
+      unsigned long long best = ~0ull;
+      if (!ended) {
+        for (int s = 0; s < n_splits; ++s) {
+          const unsigned long long* lst = part + static_cast<size_t>(s) * k1 * rows + r;
+          for (int i = 0; i < k1; ++i) {
+            const unsigned long long v = lst[static_cast<size_t>(i) * rows];
+            if (j > 0 && v <= last) continue;
+            if (v < best) best = v;
+            break;
+          }
+        }
       }
-    }
-    last = best;
-    lists[r * k1 + j] = best;
-    if (best == ~0ull) {
-      for (int jj = j + 1; jj < k1; ++jj) lists[r * k1 + jj] = ~0ull;
-      break;
+      last = best;
+      ended |= best == ~0ull;
+      mine[j] = best;
     }
   }
+  flush_rows(merge_sm, row_base, rows, k1, PG_W_I64, true, lists, nullptr, nullptr);
 }
 
-// Final lists: merge n_lists sorted key lists per row (one per rank), drop, widen.  Every list
-// keeps a cursor and its head key in registers; a key present in several lists (the shared
-// bootstrap entries) advances all of them, so the merged order has no duplicates.
+// Final lists: merge n_lists sorted key lists per row (one per rank), drop, then either widen to the
+// reference's (index int64, weight) arrays or keep the merged keys (KEYS_OUT: the exchange step of the
+// multi-GPU build all-gathers 8-byte keys and widens locally).  Every list keeps a cursor and its
+// head key in registers; a key present in several lists (the shared bootstrap entries) advances all
+// of them, so the merged order has no duplicates.
 constexpr int kMaxMergeLists = 16;
 
 __global__ void knn_lists_finalize_kernel(const unsigned long long* __restrict__ lists, int n_lists,
                                           long long list_stride, long long row0, long long rows, int k1, int k,
-                                          int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
-  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows) return;
-  const unsigned long long* base = lists + static_cast<size_t>(row0 + r) * k1;
-  unsigned long long head[kMaxMergeLists];
-  int pos[kMaxMergeLists];
+                                          int drop, int weight, bool keys_out, unsigned long long* __restrict__ out_keys,
+                                          long long* __restrict__ out_idx, void* out_w) {
+  extern __shared__ unsigned long long merge_sm[];
+  const long long row_base = blockIdx.x * static_cast<long long>(blockDim.x);
+  const long long r = row_base + threadIdx.x;
+  unsigned long long* mine = merge_sm + threadIdx.x * (k + 1);
+  if (r < rows) {
+    const unsigned long long* base = lists + static_cast<size_t>(row0 + r) * k1;
+    unsigned long long head[kMaxMergeLists];
+    int pos[kMaxMergeLists];
 #pragma unroll
-  for (int s = 0; s < kMaxMergeLists; ++s) {
-    pos[s] = 0;
-    head[s] = s < n_lists ? base[static_cast<size_t>(s) * list_stride] : ~0ull;
-  }
-  for (int j = 0; j < drop + k; ++j) {
-    unsigned long long best = ~0ull;
+    for (int s = 0; s < kMaxMergeLists; ++s) {
+      pos[s] = 0;
+      head[s] = s < n_lists ? base[static_cast<size_t>(s) * list_stride] : ~0ull;
+    }
+    for (int j = 0; j < drop + k; ++j) {
+      unsigned long long best = ~0ull;
 #pragma unroll
-    for (int s = 0; s < kMaxMergeLists; ++s) best = head[s] < best ? head[s] : best;
-    if (best != ~0ull) {
+      for (int s = 0; s < kMaxMergeLists; ++s) best = head[s] < best ? head[s] : best;
+      if (best != ~0ull) {
 #pragma unroll
-      for (int s = 0; s < kMaxMergeLists; ++s) {
-        if (head[s] == best) {
-          ++pos[s];
-          head[s] = pos[s] < k1 ? base[static_cast<size_t>(s) * list_stride + pos[s]] : ~0ull;
+        for (int s = 0; s < kMaxMergeLists; ++s) {
+          if (head[s] == best) {
+            ++pos[s];
+            head[s] = pos[s] < k1 ? base[static_cast<size_t>(s) * list_stride + pos[s]] : ~0ull;
+          }
         }
       }
-    }
-    if (j >= drop) {
-      const long long at = r * k + (j - drop);
-      if (best == ~0ull) {
-        out_idx[at] = -1;
-        write_weight(out_w, at, 0, weight);
-      } else {
-        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
-        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
-      }
+      if (j >= drop) mine[j - drop] = best;
     }
   }
+  flush_rows(merge_sm, row_base, rows, k, weight, keys_out, out_keys, out_idx, out_w);
 }
 
 // more lists than cursors fit in registers: "smallest key above the last one", rescanning the lists
 __global__ void knn_lists_finalize_scan_kernel(const unsigned long long* __restrict__ lists, int n_lists,
                                                long long list_stride, long long row0, long long rows, int k1, int k,
-                                               int drop, int weight, long long* __restrict__ out_idx, void* out_w) {
-  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows) return;
-  unsigned long long last = 0;
-  bool have_last = false;
-  for (int j = 0; j < drop + k; ++j) {
-    unsigned long long best = ~0ull;
-    for (int s = 0; s < n_lists; ++s) {
-      const unsigned long long* lst = lists + static_cast<size_t>(s) * list_stride + static_cast<size_t>(row0 + r) * k1;
-      for (int i = 0; i < k1; ++i) {
-        const unsigned long long v = lst[i];
-        if (have_last && v <= last) continue;
-        if (v < best) best = v;
-        break;
+                                               int drop, int weight, bool keys_out,
+                                               unsigned long long* __restrict__ out_keys, long long* __restrict__ out_idx,
+                                               void* out_w) {
+  extern __shared__ unsigned long long merge_sm[];
+  const long long row_base = blockIdx.x * static_cast<long long>(blockDim.x);
+  const long long r = row_base + threadIdx.x;
+  unsigned long long* mine = merge_sm + threadIdx.x * (k + 1);
+  if (r < rows) {
+    unsigned long long last = 0;
+    bool have_last = false;
+    for (int j = 0; j < drop + k; ++j) {
+      unsigned long long best = ~0ull;
+      for (int s = 0; s < n_lists; ++s) {
+        const unsigned long long* lst = lists + static_cast<size_t>(s) * list_stride + static_cast<size_t>(row0 + r) * k1;
+        for (int i = 0; i < k1; ++i) {
+          const unsigned long long v = lst[i];
+          if (have_last && v <= last) continue;
+          if (v < best) best = v;
+          break;
+        }
       }
+      last = best;
+      have_last = true;
+      if (j >= drop) mine[j - drop] = best;
     }
-    last = best;
-    have_last = true;
-    if (j >= drop) {
-      const long long at = r * k + (j - drop);
-      if (best == ~0ull) {
-        out_idx[at] = -1;
-        write_weight(out_w, at, 0, weight);
-      } else {
-        out_idx[at] = static_cast<long long>(best & 0xffffffffull);
-        write_weight(out_w, at, static_cast<int>(best >> 32), weight);
-      }
-    }
+  }
+  flush_rows(merge_sm, row_base, rows, k, weight, keys_out, out_keys, out_idx, out_w);
+}
+
+// One sorted list per row -> (index, weight): HBM-bound, one thread per OUTPUT element so that the
+// 8-byte loads and both stores are coalesced (the per-row version strode 136 B between lanes).
+__global__ void knn_keys_widen_kernel(const unsigned long long* __restrict__ keys, long long row0, long long rows,
+                                      int k1, int k, int drop, int weight, long long* __restrict__ out_idx,
+                                      void* out_w) {
+  const long long total = rows * k;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / k;
+    const int j = static_cast<int>(e - r * k) + drop;
+    const unsigned long long key = j < k1 ? __ldcs(keys + (row0 + r) * k1 + j) : ~0ull;
+    emit_key(key, e, weight, false, nullptr, out_idx, out_w);
   }
 }
 
@@ -588,8 +702,8 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
     rc = dispatch(planes, words, prm, l);
   }
   if (rc != PG_OK) return rc;
-  const int threads = 128;
-  knn_finalize_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
+  const int threads = rows_per_merge_block(k);
+  knn_finalize_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, merge_smem_bytes(k), l.stream>>>(
       prm.part, g.n_splits, k1, rows, k, drop, weight, reinterpret_cast<long long*>(out_idx), out_w);
   PG_LAUNCH_CHECK();
   return PG_OK;
@@ -739,8 +853,8 @@ int pg_hamming_knn_boot(const uint32_t* table, int64_t table_rows, int64_t row0,
     rc = dispatch(planes, words, prm, l);
   }
   if (rc != PG_OK) return rc;
-  const int threads = 128;
-  knn_part_to_lists_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
+  const int threads = rows_per_merge_block(k1);
+  knn_part_to_lists_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, merge_smem_bytes(k1), l.stream>>>(
       prm.part, g.n_splits, k1, rows, reinterpret_cast<unsigned long long*>(lists));
   PG_LAUNCH_CHECK();
   return PG_OK;
@@ -755,6 +869,44 @@ int pg_knn_sym_band(int64_t rows, int words, int64_t boot_rows, int part, int pa
   sym_band(lay, rows, boot_rows, part, parts, &t0, &t1);
   *row_begin = std::min<int64_t>(rows, static_cast<int64_t>(t0) * lay.tile_cols);
   *row_end = std::min<int64_t>(rows, static_cast<int64_t>(t1) * lay.tile_cols);
+  return PG_OK;
+}
+
+int pg_knn_sym_plan(int64_t rows, int planes, int words, int64_t boot_rows, int part, int parts, int mode, int grid,
+                    int32_t* items_host, int64_t capacity, int64_t* n_items) {
+  PG_CHECK_ARG(rows > 0 && words > 0 && planes > 0 && parts >= 1 && part >= 0 && part < parts && grid >= 1 && n_items &&
+                   (mode == 0 || mode == 1) && boot_rows >= 0 && boot_rows % kStreamRowPad == 0,
+               "bad plan arguments");
+  const SymLayout lay = sym_layout(rows, words, planes);
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, grid, boot_rows);
+  *n_items = static_cast<int64_t>(plan.items.size());
+  PG_CHECK_ARG(sym_plan_bytes(plan) <= lay.item_bytes_max, "item table overflow (%zu items)", plan.items.size());
+  if (items_host) {
+    int cta = 0;
+    for (size_t i = 0; i < plan.items.size() && static_cast<int64_t>(i) < capacity; ++i) {
+      while (static_cast<int>(i) >= plan.first[cta + 1]) ++cta;
+      items_host[5 * i + 0] = plan.items[i].rb;
+      items_host[5 * i + 1] = plan.items[i].t0;
+      items_host[5 * i + 2] = plan.items[i].t1;
+      items_host[5 * i + 3] = plan.items[i].boot;
+      items_host[5 * i + 4] = cta;
+    }
+  }
+  return PG_OK;
+}
+
+int pg_knn_sym_status(const void* workspace, int64_t rows, int words, void* stream) {
+  PG_CHECK_ARG(workspace && rows > 0 && words > 0, "bad status arguments");
+  const SymLayout lay = sym_layout(rows, words);
+  unsigned err = 0;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  PG_CUDA(cudaMemcpyAsync(&err, static_cast<const char*>(workspace) + lay.stats_off + 64, sizeof(err),
+                          cudaMemcpyDeviceToHost, cs));
+  PG_CUDA(cudaStreamSynchronize(cs));
+  if (err != 0) {
+    set_error("symmetric sweep: a row lock could not be taken within %u attempts (lists are incomplete)", kLockSpinLimit);
+    return PG_ERR_CUDA;
+  }
   return PG_OK;
 }
 
@@ -775,7 +927,7 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
     set_error("symmetric sweep: planes/words %d/%d or list length %d not covered", planes, words, k1);
     return PG_ERR_UNSUPPORTED;
   }
-  const SymLayout lay = sym_layout(rows, words);
+  const SymLayout lay = sym_layout(rows, words, planes);
   PG_CHECK_ARG(workspace_bytes >= lay.total, "workspace too small: %zu < %zu", workspace_bytes, lay.total);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   char* wsb = static_cast<char*>(workspace);
@@ -789,25 +941,24 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   prm.glist = reinterpret_cast<unsigned long long*>(lists);
   prm.glast = reinterpret_cast<unsigned long long*>(wsb);
   prm.glock = reinterpret_cast<unsigned*>(wsb + lay.gnt_bytes);
-  prm.items = reinterpret_cast<const SymItem*>(wsb + lay.item_off);
   unsigned long long* stats_dev = reinterpret_cast<unsigned long long*>(wsb + lay.stats_off);
   const bool want_stats = std::getenv("PG_SYM_STATS") != nullptr;
   prm.stats = want_stats ? stats_dev : nullptr;
+  prm.error = reinterpret_cast<unsigned*>(stats_dev + 8);
   SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs, SYM_KNN};
-  if (const char* ev = std::getenv("PG_SYM_DEFER")) l.defer = std::atoi(ev);      // experiment, see pg_sweep_sym.cuh
+  l.pair = sym_pair_default(words);
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;
-  const std::vector<SymItem> items = sym_plan(lay, rows, part, parts, mode, resident, boot_rows);
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, boot_rows);
   sym_init_kernel<<<num_sms() * 4, 256, 0, cs>>>(prm.glist, static_cast<long long>(rows) * k1, prm.glast,
                                                  static_cast<long long>(lay.n_tiles) * lay.tile_cols, prm.glock, rows,
                                                  stats_dev, k1, boot_rows > 0 ? 1 : 0);
   PG_LAUNCH_CHECK();
-  if (items.empty()) return PG_OK;
-  PG_CHECK_ARG(items.size() * sizeof(SymItem) <= lay.item_bytes_max, "item table overflow (%zu items)", items.size());
-  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off, items.data(), items.size() * sizeof(SymItem), cudaMemcpyHostToDevice, cs));
-  prm.n_items = static_cast<int>(items.size());
-  l.grid = static_cast<int>(std::min<size_t>(items.size(), static_cast<size_t>(resident)));
+  if (plan.items.empty()) return PG_OK;
+  rc = sym_upload_plan(plan, lay, wsb, &prm, cs);
+  if (rc != PG_OK) return rc;
+  l.grid = plan.grid;
   {
     SweepTimer t(cs);
     rc = dispatch_sym(planes, words, prm, l, nullptr);
@@ -816,8 +967,8 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
     unsigned long long st[8];
     PG_CUDA(cudaMemcpyAsync(st, stats_dev, sizeof(st), cudaMemcpyDeviceToHost, cs));
     PG_CUDA(cudaStreamSynchronize(cs));
-    fprintf(stderr, "[pg sym] rows=%lld boot=%lld items=%zu grid=%d | locks %llu, lock spins %llu, list writes %llu | row "
-            "inserts %llu\n", static_cast<long long>(rows), static_cast<long long>(boot_rows), items.size(), l.grid,
+    fprintf(stderr, "[pg sym] rows=%lld boot=%lld items=%d grid=%d | locks %llu, lock spins %llu, list writes %llu | row "
+            "inserts %llu\n", static_cast<long long>(rows), static_cast<long long>(boot_rows), prm.n_items, l.grid,
             st[1], st[2], st[3], st[4]);
   }
   return rc;
@@ -848,7 +999,7 @@ int pg_hamming_eps_sym(const uint32_t* table, int64_t rows, int planes, int word
   }
   prm.hi = prm.lo == 0x7fffffff ? -1 : prm.lo + static_cast<int>(span);
   if (prm.lo == 0x7fffffff) prm.lo = 1 << 20;            // empty predicate: nothing passes
-  const SymLayout lay = sym_layout(rows, words);
+  const SymLayout lay = sym_layout(rows, words, planes);
   PG_CHECK_ARG(workspace_bytes >= lay.total, "workspace too small: %zu < %zu", workspace_bytes, lay.total);
   const EdgeKeyBits kb = edge_key_bits(rows, words);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
@@ -857,23 +1008,22 @@ int pg_hamming_eps_sym(const uint32_t* table, int64_t rows, int planes, int word
   prm.rows = rows;
   prm.one = 1u;
   prm.k1 = 1;
-  prm.items = reinterpret_cast<const SymItem*>(wsb + lay.item_off);
   prm.sh_col = kb.dbits;
   prm.sh_row = kb.dbits + kb.idxbits;
   prm.keys = reinterpret_cast<unsigned long long*>(keys);
   prm.capacity = capacity;
   prm.counters = reinterpret_cast<unsigned long long*>(counters);
   SymLaunch l{0, 0, cs, SYM_EPS};
+  l.pair = sym_pair_default(words);
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);
   if (rc != PG_OK) return rc;
-  const std::vector<SymItem> items = sym_plan(lay, rows, part, parts, mode, resident, 0);
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, 0);
   PG_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(uint64_t), cs));
-  if (items.empty()) return PG_OK;
-  PG_CHECK_ARG(items.size() * sizeof(SymItem) <= lay.item_bytes_max, "item table overflow (%zu items)", items.size());
-  PG_CUDA(cudaMemcpyAsync(wsb + lay.item_off, items.data(), items.size() * sizeof(SymItem), cudaMemcpyHostToDevice, cs));
-  prm.n_items = static_cast<int>(items.size());
-  l.grid = static_cast<int>(std::min<size_t>(items.size(), static_cast<size_t>(resident)));
+  if (plan.items.empty()) return PG_OK;
+  rc = sym_upload_plan(plan, lay, wsb, &prm, cs);
+  if (rc != PG_OK) return rc;
+  l.grid = plan.grid;
   {
     SweepTimer t(cs);
     rc = dispatch_sym(planes, words, prm, l, nullptr);
@@ -917,24 +1067,44 @@ int pg_edge_keys_to_csr(uint64_t* keys, int64_t n_keys, uint64_t* keys_alt, int6
 }
 
 
-int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1,
-                          int k, int drop, int weight, int64_t* out_idx, void* out_w, void* stream) {
-  PG_CHECK_ARG(lists && out_idx && out_w, "null pointer");
+static int knn_lists_launch(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1,
+                            int k, int drop, int weight, uint64_t* out_keys, int64_t* out_idx, void* out_w, void* stream) {
+  PG_CHECK_ARG(lists && (out_keys || (out_idx && out_w)), "null pointer");
   PG_CHECK_ARG(n_lists >= 1 && rows > 0 && row0 >= 0 && k >= 1 && drop >= 0 && k1 >= 1, "bad list geometry");
   PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32 || weight == PG_W_I32, "bad weight kind %d", weight);
-  const int threads = 128;
+  const int threads = rows_per_merge_block(k);
+  const size_t msm = merge_smem_bytes(k);
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, threads));
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  if (n_lists <= kMaxMergeLists)
-    knn_lists_finalize_kernel<<<grid, threads, 0, cs>>>(reinterpret_cast<const unsigned long long*>(lists), n_lists,
-                                                        list_stride, row0, rows, k1, k, drop, weight,
-                                                        reinterpret_cast<long long*>(out_idx), out_w);
-  else
-    knn_lists_finalize_scan_kernel<<<grid, threads, 0, cs>>>(reinterpret_cast<const unsigned long long*>(lists), n_lists,
-                                                             list_stride, row0, rows, k1, k, drop, weight,
-                                                             reinterpret_cast<long long*>(out_idx), out_w);
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(lists);
+  unsigned long long* ok = reinterpret_cast<unsigned long long*>(out_keys);
+  if (n_lists == 1 && out_keys == nullptr) {
+    const long long blocks = std::min<long long>(ceil_div(rows * k, 256), static_cast<long long>(num_sms()) * 16);
+    knn_keys_widen_kernel<<<static_cast<unsigned>(blocks), 256, 0, cs>>>(src, row0, rows, k1, k, drop, weight,
+                                                                        reinterpret_cast<long long*>(out_idx), out_w);
+  } else if (n_lists <= kMaxMergeLists) {
+    knn_lists_finalize_kernel<<<grid, threads, msm, cs>>>(src, n_lists, list_stride, row0, rows, k1, k, drop, weight,
+                                                        out_keys != nullptr, ok, reinterpret_cast<long long*>(out_idx), out_w);
+  } else {
+    knn_lists_finalize_scan_kernel<<<grid, threads, msm, cs>>>(src, n_lists, list_stride, row0, rows, k1, k, drop, weight,
+                                                             out_keys != nullptr, ok, reinterpret_cast<long long*>(out_idx),
+                                                             out_w);
+  }
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+int pg_knn_lists_finalize(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1,
+                          int k, int drop, int weight, int64_t* out_idx, void* out_w, void* stream) {
+  PG_CHECK_ARG(out_idx && out_w, "null output pointer");
+  return knn_lists_launch(lists, n_lists, list_stride, row0, rows, k1, k, drop, weight, nullptr, out_idx, out_w, stream);
+}
+
+int pg_knn_lists_merge(const uint64_t* lists, int n_lists, int64_t list_stride, int64_t row0, int64_t rows, int k1, int k,
+                       int drop, uint64_t* out_keys, void* stream) {
+  PG_CHECK_ARG(out_keys, "null output pointer");
+  return knn_lists_launch(lists, n_lists, list_stride, row0, rows, k1, k, drop, PG_W_I64, out_keys, nullptr, nullptr,
+                          stream);
 }
 
 

@@ -18,13 +18,26 @@
 // everything behind the vote is rare and out of line.  A stale filter word is only ever larger
 // than the current one, so no candidate is lost; the locked insertion compares full keys, so the
 // result is the k1 smallest (distance, index) keys whatever the arrival order.
-// Work items are (row block, tile range) chunks from a host-built table; a chunk starts its
+// Work items are (row block, tile range) chunks from a host-built table (one list per CTA, ordered
+// by L2-sized column bands, see sym_plan in pg_sweep.cu); a chunk starts its
 // shared-memory lists empty but seeds its filter from the row's global list, and merges its lists
 // into the global ones when it ends, so chunks can be short (good load balance) without the
 // cold-start insertion storm of the split lists in pg_sweep.cuh.
 // Bootstrap: the host first sweeps all rows one-sided against the first boot_rows columns
 // (pg_hamming_knn_boot) so that every filter is tight from the first symmetric tile on; the row
 // blocks of those rows ("boot" items) then run row side only, behind the bootstrap columns.
+// Paired lanes (PAIR): lanes 2i and 2i+1 share their two own rows -- each lane keeps ONE HALF of
+// the plane words of both rows in registers (the same P*W registers as before), reads only its half
+// of every stream row (5 instead of 10 LDS.128 at W=8) and finishes its own row's distance with one
+// SHFL of the partner's partial sum.  Per pair: half the shared-memory wavefronts and half the
+// stream registers in flight; LOP3 / POPC counts unchanged.
+// Lock protocol: atom.acquire.gpu CAS by lane 0, __syncwarp, list edited in registers, st.cg of the
+// list and the filter word, __syncwarp, st.release.gpu of the lock by lane 0 (bar.warp.sync orders the
+// other lanes' stores before the cumulative release).  A lock that cannot be taken within 2^24
+// attempts raises the error word the host reads back (PG_ERR_CUDA) instead of trapping the context.
+// The filter words are a monotone hint: they are read through the async proxy (bulk copy) while
+// other CTAs store to them; ANY value a row's word ever held is a valid (looser) filter, and an
+// aligned 8-byte store cannot tear, so the hint needs no ordering.
 // Epsilon mode (SYM_EPS) is the same sweep with another consumer (prograph.py:731-753): a pair whose
 // distance lies in [lo, hi] appends both directed edges as packed 64-bit keys to a global buffer,
 // which the host sorts into the CSR (pg_edge_keys_to_csr) -- no count pass, no second sweep.
@@ -40,7 +53,8 @@ struct SymItem { int rb, t0, t1, boot; };   // row block, stream tiles [t0, t1);
 struct SymParams {
   const uint32_t* tab;        // packed table, own == stream
   long long rows;             // valid rows
-  const SymItem* items;
+  const SymItem* items;       // CTA-major: CTA b owns items [cta_first[b], cta_first[b+1])
+  const int* cta_first;
   int n_items;
   unsigned one;               // opaque 1 (see SweepParams::one)
   int k1;                     // list length, <= 32
@@ -48,6 +62,7 @@ struct SymParams {
   unsigned long long* glast;  // [n_tiles * tile_cols] filter word per row: (~tau)<<32 | index of the last key
   unsigned* glock;            // [rows]
   unsigned long long* stats;  // null, or [8] slow-path counters: -, locks, lock spins, list writes, row inserts
+  unsigned* error;            // set to 1 when a row lock could not be taken (the host turns it into PG_ERR_CUDA)
   long long boot_rows;        // rows [0, boot_rows) were swept one-sided against every row beforehand
   // epsilon mode (SYM_EPS): edge <=> lo <= d <= hi; edges are appended to `keys` as
   // row << sh_row | column << sh_col | d, both directions of every unordered pair
@@ -66,6 +81,15 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
 __device__ __forceinline__ void st_cg_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned atom_cas_acquire_gpu(unsigned* p, unsigned cmp, unsigned val) {
+  unsigned old;
+  asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr unsigned kLockSpinLimit = 1u << 24;
 // filter word of a list whose last key is `last` (~0 = list not full)
 __host__ __device__ __forceinline__ unsigned long long sym_filter_word(unsigned long long last) {
   const unsigned tau = (last == ~0ull) ? static_cast<unsigned>(kTauInf) : static_cast<unsigned>(last >> 32);
@@ -89,20 +113,24 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
   unsigned cand = __ballot_sync(0xffffffffu, is_cand);
   if (cand == 0u) return;
   unsigned* lock = prm.glock + j;
+  unsigned got = 1u;
   if (lane == 0) {
     unsigned spins = 0;
-    while (atomicCAS(lock, 0u, 1u) != 0u) {
+    while (atom_cas_acquire_gpu(lock, 0u, 1u) != 0u) {
       __nanosleep(100);
-      if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
+      if (++spins > kLockSpinLimit) {     // a protocol bug is reported to the host, the context survives
+        got = 0u;
+        atomicExch(prm.error, 1u);
+        break;
+      }
     }
-    // no fence on the acquiring side: the list is only ever read with ld.global.cg (L2, never L1),
-    // the loads below are issued after the CAS has returned, and the previous holder fenced its
-    // stores before it released the lock
     if (prm.stats != nullptr) {
       atomicAdd(prm.stats + 1, 1ull);
       if (spins) atomicAdd(prm.stats + 2, static_cast<unsigned long long>(spins));
     }
   }
+  // bar.warp.sync orders lane 0's acquire before the other lanes' loads of the list
+  if (__shfl_sync(0xffffffffu, got, 0) == 0u) return;
   __syncwarp();
   unsigned long long e = lane < k1 ? ld_cg_u64(lst + lane) : ~0ull;
   bool changed = false;
@@ -125,91 +153,12 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
       st_cg_u64(prm.glast + j, sym_filter_word(last));
       if (prm.stats != nullptr) atomicAdd(prm.stats + 3, 1ull);
     }
-    __threadfence();
   }
-  __syncwarp();
-  if (lane == 0) atomicExch(lock, 0u);
+  __syncwarp();                                   // every lane's stores happen before lane 0's release
+  if (lane == 0) st_release_gpu_u32(lock, 0u);
 }
 
 constexpr int kMaxSymList = 32;   // longest list the symmetric sweep keeps (k + drop)
-constexpr int kPendFlush = 24;    // a warp merges its pending column-side candidates at this many
-
-// Lane-parallel merge (deferred column side, the DEFER instantiation): every active lane merges
-// the candidate keys slots[b], b in slot_mask, into the global list of ITS OWN row -- up to 32 rows
-// per call, so the L2 round trips of lock, list load, write-back and unlock overlap across the
-// lanes instead of costing one warp stall per event.  The critical section sits inside the try-lock
-// loop: a lane that got its lock finishes and releases it in the same iteration, whatever its
-// sibling lanes are still waiting for, so locks held by diverged lanes of different warps cannot
-// wait on each other.
-static __device__ __noinline__ void sym_merge_lanes(const SymParams& prm, bool active, long long row,
-                                                    const unsigned long long* slots, unsigned slot_mask) {
-  const int k1 = prm.k1;
-  bool done = !active;
-  unsigned tries = 0;
-  while (!__all_sync(0xffffffffu, done)) {
-    if (!done && atomicCAS(prm.glock + row, 0u, 1u) == 0u) {
-      unsigned long long* lst = prm.glist + static_cast<size_t>(row) * k1;
-      unsigned long long e[kMaxSymList];
-      for (int i = 0; i < k1; ++i) e[i] = ld_cg_u64(lst + i);
-      bool changed = false;
-      for (unsigned mk = slot_mask; mk != 0u; mk &= mk - 1u) {
-        const unsigned long long key = slots[__ffs(mk) - 1];
-        if (key >= e[k1 - 1]) continue;                // also skips empty slots (~0)
-        int i = k1 - 1;
-        for (; i > 0 && e[i - 1] > key; --i) e[i] = e[i - 1];
-        e[i] = key;
-        changed = true;
-      }
-      if (changed) {
-        for (int i = 0; i < k1; ++i) st_cg_u64(lst + i, e[i]);
-        st_cg_u64(prm.glast + row, sym_filter_word(e[k1 - 1]));
-        __threadfence();
-      }
-      atomicExch(prm.glock + row, 0u);
-      done = true;
-      if (prm.stats != nullptr) {
-        atomicAdd(prm.stats + 1, 1ull);
-        if (changed) atomicAdd(prm.stats + 3, 1ull);
-      }
-    }
-    if (++tries > (1u << 22)) __trap();                // a protocol bug traps instead of hanging the GPU
-  }
-}
-
-// Merge the warp's pending (row, key) candidates: one lane per distinct row.  The queue length
-// lives in shared memory (*pcnt, warp-private) so that it costs the hot loop no register.
-static __device__ __noinline__ void sym_flush(const SymParams& prm, const unsigned* prow, const unsigned long long* pkey,
-                                              int* pcnt, int lane) {
-  __syncwarp();
-  const int qn = *pcnt;
-  if (qn == 0) return;
-  const bool have = lane < qn;
-  const unsigned row = have ? prow[lane] : 0xffffffffu;
-  const unsigned grp = __match_any_sync(0xffffffffu, row);
-  const bool leader = have && lane == __ffs(grp) - 1;
-  sym_merge_lanes(prm, leader, row, pkey, grp);
-  __syncwarp();
-  if (lane == 0) *pcnt = 0;
-  __syncwarp();
-}
-
-// Queue the column-side candidates of stream row j (lanes with `cc`).
-static __device__ __noinline__ void sym_enqueue(const SymParams& prm, unsigned* prow, unsigned long long* pkey, int* pcnt,
-                                                unsigned j, unsigned long long key, bool cc, int lane) {
-  const unsigned m = __ballot_sync(0xffffffffu, cc);
-  const int n = __popc(m);
-  if (*pcnt + n > 32) sym_flush(prm, prow, pkey, pcnt, lane);
-  const int qn = *pcnt;
-  __syncwarp();
-  if (cc) {
-    const int slot = qn + __popc(m & ((1u << lane) - 1u));
-    prow[slot] = j;
-    pkey[slot] = key;
-  }
-  if (lane == 0) *pcnt = qn + n;
-  __syncwarp();
-  if (qn + n >= kPendFlush) sym_flush(prm, prow, pkey, pcnt, lane);
-}
 
 // Row side: the warp inserts the candidates of one stream row (column `col`) into the
 // shared-memory lists of its own rows; returns the lane's updated filter.
@@ -228,11 +177,12 @@ static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists,
   return tau;
 }
 
+// Position of a CTA in its own item list: the (item, ring tile) that goes into a stage next.
 struct SymCursor {
-  int idx, t, t1;
+  int idx, end, t, t1;
   __device__ __forceinline__ void start(int i, const SymParams& prm) {
     idx = i;
-    if (idx < prm.n_items) {
+    if (idx < end) {
       const int4 it = __ldg(reinterpret_cast<const int4*>(prm.items) + idx);
       t = it.y;
       t1 = it.z;
@@ -240,9 +190,9 @@ struct SymCursor {
       t = t1 = 0;
     }
   }
-  __device__ __forceinline__ bool valid(const SymParams& prm) const { return idx < prm.n_items; }
-  __device__ __forceinline__ void advance(const SymParams& prm, int stride) {
-    if (++t == t1) start(idx + stride, prm);
+  __device__ __forceinline__ bool valid() const { return idx < end; }
+  __device__ __forceinline__ void advance(const SymParams& prm) {
+    if (++t == t1) start(idx + 1, prm);
   }
 };
 
@@ -281,9 +231,53 @@ static __device__ __noinline__ void sym_emit(const SymParams& prm, bool hit, uns
   n_real += static_cast<unsigned long long>(n);
 }
 
-// DEFER (kNN mode only, experimental, PG_SYM_DEFER=1): column-side candidates are queued per warp and
-// merged lane-parallel (sym_merge_lanes) instead of being served one event at a time.
-template <int P, int W, int MODE, bool DEFER = false>
+// Paired lanes: distance of this lane's own row to one stream row.  q holds [0] the lane's half
+// (words h*W/2 .. of every plane) of its OWN row and [1] the same half of its PARTNER lane's row;
+// colh points at that half of the stream row.  The partner computes the other halves; one SHFL
+// exchanges the partial sums of the rows the lanes do not own.
+template <int P, int W>
+__device__ __forceinline__ int ham_pair(const uint32_t (&q)[P * W], const uint32_t* __restrict__ colh, unsigned one) {
+  constexpr int H = W / 2;
+  static_assert(W >= 2 && W % 2 == 0, "paired lanes split a row into two halves");
+  uint32_t m0[H], m1[H];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    uint32_t v[H];
+    if constexpr (H % 4 == 0) {
+#pragma unroll
+      for (int g = 0; g < H / 4; ++g) {
+        const uint4 t = *reinterpret_cast<const uint4*>(colh + p * W + 4 * g);
+        v[4 * g + 0] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+      }
+    } else if constexpr (H == 2) {
+      const uint2 t = *reinterpret_cast<const uint2*>(colh + p * W);
+      v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+      for (int w = 0; w < H; ++w) v[w] = colh[p * W + w];
+    }
+#pragma unroll
+    for (int w = 0; w < H; ++w) {
+      if (p == 0) {
+        m0[w] = q[w] ^ v[w];
+        m1[w] = q[P * H + w] ^ v[w];
+      } else {
+        m0[w] |= q[p * H + w] ^ v[w];
+        m1[w] |= q[P * H + p * H + w] ^ v[w];
+      }
+    }
+  }
+  unsigned s0 = __popc(m0[0]), s1 = __popc(m1[0]);
+#pragma unroll
+  for (int w = 1; w < H; ++w) {
+    s0 = mad_u32(__popc(m0[w]), one, s0);
+    s1 = mad_u32(__popc(m1[w]), one, s1);
+  }
+  const unsigned other = __shfl_xor_sync(0xffffffffu, s1, 1);
+  return static_cast<int>(mad_u32(other, one, s0));
+}
+
+template <int P, int W, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __grid_constant__ SymParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
@@ -302,19 +296,6 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   const int lane = tid & 31;
   const int k1 = prm.k1;
   unsigned long long* warp_lists = lists + static_cast<size_t>(warp << 5) * k1;
-  // DEFER: per-warp queue of pending column-side candidates, behind the lists; the pointers are
-  // rebuilt where they are needed (rare path) to keep them out of the hot loop's registers
-  auto pend_key = [&]() { return lists + static_cast<size_t>(kConsumers) * prm.k1 + (threadIdx.x & ~31u); };
-  auto pend_row = [&]() {
-    return reinterpret_cast<unsigned*>(lists + static_cast<size_t>(kConsumers) * prm.k1 + kConsumers) + (threadIdx.x & ~31u);
-  };
-  auto pend_cnt = [&]() {
-    return reinterpret_cast<int*>(lists + static_cast<size_t>(kConsumers) * prm.k1 + kConsumers) + kConsumers + (threadIdx.x >> 5);
-  };
-  if constexpr (DEFER) {
-    if (lane == 0) *pend_cnt() = 0;
-    __syncwarp();
-  }
 
   auto fill_stage = [&](int s, int t) {   // one elected thread: tile t (and its filter words) into ring stage s
     mbar_arrive_expect_tx(&full[s], STAGE_BYTES + TAU_BYTES);
@@ -322,8 +303,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
     if constexpr (MODE == SYM_KNN) bulk_g2s(taus + s * BN, prm.glast + static_cast<size_t>(t) * BN, TAU_BYTES, &full[s]);
   };
 
+  const int item_first = __ldg(prm.cta_first + blockIdx.x), item_end = __ldg(prm.cta_first + blockIdx.x + 1);
   SymCursor la;
-  la.start(blockIdx.x, prm);
+  la.end = item_end;
+  la.start(item_first, prm);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
@@ -335,31 +318,58 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   __syncthreads();
 #pragma unroll 1
   for (int s = 0; s < kStages; ++s) {
-    if (tid == 0 && la.valid(prm)) fill_stage(s, la.t);
-    if (la.valid(prm)) la.advance(prm, gridDim.x);
+    if (tid == 0 && la.valid()) fill_stage(s, la.t);
+    if (la.valid()) la.advance(prm);
   }
 
   int stage = 0;
   uint32_t phase = 0;
   const unsigned one = prm.one;
+  // paired lanes: word offset of this lane's half inside a stream row
+  const int hoff = PAIR ? (lane & 1) * (W / 2) : 0;
   // epsilon mode: the warp's current chunk of the edge buffer
   long long ch_base = -1;
   int ch_used = 0;
   unsigned long long n_real = 0;
 
-  for (int ii = blockIdx.x; ii < prm.n_items; ii += gridDim.x) {
+  for (int ii = item_first; ii < item_end; ++ii) {
     const int4 it = __ldg(reinterpret_cast<const int4*>(prm.items) + ii);
     const int rb = it.x, t0 = it.y, t1 = it.z;
     const bool boot = it.w != 0;
     const long long r = static_cast<long long>(rb) * kConsumers + tid;
     const bool valid = r < prm.rows;
     uint32_t q[COLW];
-    {
+    if constexpr (PAIR) {
+      // [0 .. P*H): this lane's half of its own row; [P*H .. 2*P*H): the same half of the partner's row
+      constexpr int H = W / 2;
+      const long long rp = r ^ 1ll;
+      const bool pvalid = rp < prm.rows;
+      const uint32_t* src = prm.tab + static_cast<size_t>(valid ? r : 0) * COLW + hoff;
+      const uint32_t* psrc = prm.tab + static_cast<size_t>(pvalid ? rp : 0) * COLW + hoff;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+#pragma unroll
+        for (int w = 0; w < H; ++w) {
+          q[p * H + w] = valid ? __ldg(src + p * W + w) : 0u;
+          q[P * H + p * H + w] = pvalid ? __ldg(psrc + p * W + w) : 0u;
+        }
+      }
+    } else {
       const uint32_t* src = prm.tab + static_cast<size_t>(valid ? r : 0) * COLW;
 #pragma unroll
       for (int j = 0; j < COLW; ++j) q[j] = valid ? __ldg(src + j) : 0u;
     }
     const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
+    // distance of the own row to the stream row at `col` (shared memory)
+    auto dist = [&](const uint32_t* col) -> int {
+      if constexpr (PAIR) {
+        return ham_pair<P, W>(q, col + hoff, one);
+      } else {
+        int d[1];
+        ham_rows<P, W, 1>(qq, col, d, one);
+        return d[0];
+      }
+    };
     // kNN: the row's global list already bounds what can still matter: ties at its last distance
     // stay admissible (the index decides), hence the +1
     int tau_seed = 0, tau = 0;
@@ -406,10 +416,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
             const unsigned long long mine = (static_cast<unsigned long long>(static_cast<unsigned>(dv)) << 32) |
                                             static_cast<unsigned>(r);
             const bool cc = vmask != 0u && mine < lastk;
-            if (__any_sync(0xffffffffu, cc)) {
-              if constexpr (DEFER) sym_enqueue(prm, pend_row(), pend_key(), pend_cnt(), col, mine, cc, lane);
-              else sym_serve_col(prm, col, mine, cc, lane);
-            }
+            if (__any_sync(0xffffffffu, cc)) sym_serve_col(prm, col, mine, cc, lane);
           }
         } else {
           const bool hit = (dv + nlo) >= 0 && dv <= hi;
@@ -422,11 +429,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
 
 #pragma unroll 1
       for (; c + 4 <= ncols; c += 4) {
-        int d0[1], d1[1], d2[1], d3[1];
-        ham_rows<P, W, 1>(qq, tile + (c + 0) * COLW, d0, one);
-        ham_rows<P, W, 1>(qq, tile + (c + 1) * COLW, d1, one);
-        ham_rows<P, W, 1>(qq, tile + (c + 2) * COLW, d2, one);
-        ham_rows<P, W, 1>(qq, tile + (c + 3) * COLW, d3, one);
+        const int d0 = dist(tile + (c + 0) * COLW);
+        const int d1 = dist(tile + (c + 1) * COLW);
+        const int d2 = dist(tile + (c + 2) * COLW);
+        const int d3 = dist(tile + (c + 3) * COLW);
         int any;
         if constexpr (MODE == SYM_KNN) {
           // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
@@ -434,45 +440,44 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
           const int4 nb = *reinterpret_cast<const int4*>(tnt + c + 2);
           const unsigned cm = c >= c_mid ? vmask : 0u;
           // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
-          const int s0 = mad_s32(d0[0], one, -tau), s1 = mad_s32(d1[0], one, -tau);
-          const int s2 = mad_s32(d2[0], one, -tau), s3 = mad_s32(d3[0], one, -tau);
-          const int u0 = mad_s32(d0[0], one, na.y), u1 = mad_s32(d1[0], one, na.w);
-          const int u2 = mad_s32(d2[0], one, nb.y), u3 = mad_s32(d3[0], one, nb.w);
+          const int s0 = mad_s32(d0, one, -tau), s1 = mad_s32(d1, one, -tau);
+          const int s2 = mad_s32(d2, one, -tau), s3 = mad_s32(d3, one, -tau);
+          const int u0 = mad_s32(d0, one, na.y), u1 = mad_s32(d1, one, na.w);
+          const int u2 = mad_s32(d2, one, nb.y), u3 = mad_s32(d3, one, nb.w);
           any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
         } else {
           // sign bit set <=> no edge: d - lo < 0 or hi - d < 0; all four miss <=> the AND keeps the sign
-          const int a0 = mad_s32(d0[0], one, nlo), a1 = mad_s32(d1[0], one, nlo);
-          const int a2 = mad_s32(d2[0], one, nlo), a3 = mad_s32(d3[0], one, nlo);
-          const int b0 = mad_s32(d0[0], mone, hi), b1 = mad_s32(d1[0], mone, hi);
-          const int b2 = mad_s32(d2[0], mone, hi), b3 = mad_s32(d3[0], mone, hi);
+          const int a0 = mad_s32(d0, one, nlo), a1 = mad_s32(d1, one, nlo);
+          const int a2 = mad_s32(d2, one, nlo), a3 = mad_s32(d3, one, nlo);
+          const int b0 = mad_s32(d0, mone, hi), b1 = mad_s32(d1, mone, hi);
+          const int b2 = mad_s32(d2, mone, hi), b3 = mad_s32(d3, mone, hi);
           any = ~((a0 | b0) & (a1 | b1) & (a2 | b2) & (a3 | b3));
         }
         if (__any_sync(0xffffffffu, any < 0)) {
           const bool col_on = c >= c_mid;
-          rare(d0[0], c + 0, col_on);
-          rare(d1[0], c + 1, col_on);
-          rare(d2[0], c + 2, col_on);
-          rare(d3[0], c + 3, col_on);
+          rare(d0, c + 0, col_on);
+          rare(d1, c + 1, col_on);
+          rare(d2, c + 2, col_on);
+          rare(d3, c + 3, col_on);
         }
       }
 #pragma unroll 1
       for (; c < ncols; ++c) {   // ragged end of the table (last tile only)
-        int d[1];
-        ham_rows<P, W, 1>(qq, tile + c * COLW, d, one);
-        rare(d[0], c, c >= c_mid);
+        const int d = dist(tile + c * COLW);
+        rare(d, c, c >= c_mid);
       }
 
       __syncwarp();
       if (lane == 0) {
         if (atom_add_acq_rel_cta(&done[stage], 1u) == kConsumerWarps - 1) {
           done[stage] = 0;
-          if (la.valid(prm)) {
+          if (la.valid()) {
             fence_proxy_async();
             fill_stage(stage, la.t);
           }
         }
       }
-      if (la.valid(prm)) la.advance(prm, gridDim.x);
+      if (la.valid()) la.advance(prm);
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
 
@@ -480,18 +485,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
       // merge the chunk's lists into the rows' global lists
       __syncwarp();
       const long long wrow0 = static_cast<long long>(rb) * kConsumers + (warp << 5);
-      if constexpr (DEFER) {
-        sym_flush(prm, pend_row(), pend_key(), pend_cnt(), lane);
-        const unsigned long long* ml = warp_lists + static_cast<size_t>(lane) * k1;     // every lane: its own row
-        sym_merge_lanes(prm, wrow0 + lane < prm.rows && ml[0] != ~0ull, wrow0 + lane, ml,
-                        k1 >= 32 ? 0xffffffffu : (1u << k1) - 1u);
-      } else {
 #pragma unroll 1
-        for (int src = 0; src < 32; ++src) {   // ascending keys, one row at a time
-          if (wrow0 + src >= prm.rows) break;
-          const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
-          sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
-        }
+      for (int src = 0; src < 32; ++src) {   // ascending keys, one row at a time
+        if (wrow0 + src >= prm.rows) break;
+        const unsigned long long lk = lane < k1 ? warp_lists[static_cast<size_t>(src) * k1 + lane] : ~0ull;
+        sym_serve_col(prm, wrow0 + src, lk, lk != ~0ull, lane);
       }
       __syncwarp();
     }
@@ -508,17 +506,17 @@ struct SymLaunch {
   size_t list_bytes;
   cudaStream_t stream;
   int mode = SYM_KNN;
-  int defer = 0;
+  int pair = 0;       // paired-lane instantiation (words >= 2)
 };
 
 
 // grid == 0: only report the resident grid (CTAs) through *resident
-template <int P, int W, int MODE, bool DEFER = false>
+template <int P, int W, int MODE, bool PAIR>
 int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* resident) {
-  auto kern = sweep_sym_kernel<P, W, MODE, DEFER>;
+  auto kern = sweep_sym_kernel<P, W, MODE, PAIR>;
   const size_t smem = static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 +
                                                       (MODE == SYM_KNN ? TileCols<W>::value * 8 : 0)) +
-                      2 * kStages * sizeof(uint64_t) + l.list_bytes + (DEFER ? kConsumers * 12 + 64 : 0);
+                      2 * kStages * sizeof(uint64_t) + l.list_bytes;
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 0;
   PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSweepThreads, smem));
@@ -532,11 +530,14 @@ int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* residen
 
 template <int P, int W>
 int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
-  if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS>(prm, l, resident);
-  if constexpr (P == 5 && W == 8) {      // the experimental deferred merge is only built for the bench shape
-    if (l.defer) return launch_sweep_sym_mode<P, W, SYM_KNN, true>(prm, l, resident);
+  if constexpr (W >= 2) {
+    if (l.pair) {
+      if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS, true>(prm, l, resident);
+      return launch_sweep_sym_mode<P, W, SYM_KNN, true>(prm, l, resident);
+    }
   }
-  return launch_sweep_sym_mode<P, W, SYM_KNN>(prm, l, resident);
+  if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS, false>(prm, l, resident);
+  return launch_sweep_sym_mode<P, W, SYM_KNN, false>(prm, l, resident);
 }
 
 #define PG_DECL_SWEEP_SYM(P, W) int sweep_sym_p##P##_w##W(const SymParams& prm, const SymLaunch& l, int* resident);

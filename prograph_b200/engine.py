@@ -1,5 +1,5 @@
-"""Device engine: torch owns memory and streams, every computation is a C-ABI call into
-libprograph_b200.so (hand-written sm_100a kernels).  No CPU fallback anywhere.
+"""Device engine: torch owns memory and streams, every distance / selection / compaction kernel
+is a C-ABI call into libprograph_b200.so (hand-written sm_100a kernels).  No CPU fallback anywhere.
 """
 import ctypes as C
 
@@ -180,7 +180,21 @@ class CudaEngine:
         L.check(self.lib.pg_hamming_knn_sym(_ptr(table.data), table.rows, table.planes, table.words, int(k1),
                                             int(rank), int(world), int(mode), int(boot_rows), _ptr(lists), _ptr(ws),
                                             nbytes, self._stream()))
+        self._sym_pending = (ws, table.rows, table.words)
         return lists
+
+    def sym_check(self):
+        """Status of the last symmetric kNN sweep (pg_knn_sym_status): raises if the kernel gave up
+        on a row lock.  Synchronises the stream, so callers queue the rest of the build first."""
+        pending, self._sym_pending = getattr(self, "_sym_pending", None), None
+        if pending is not None:
+            ws, rows, words = pending
+            L.check(self.lib.pg_knn_sym_status(_ptr(ws), int(rows), int(words), self._stream()))
+
+    def sym_plan(self, rows, planes, words, boot_rows=0, rank=0, world=1, mode=0, grid=296):
+        """Work items (row block, first tile, end tile, boot, CTA) of the symmetric sweeps
+        (host-only planner, pg_knn_sym_plan): (n, 5) int32."""
+        return sym_plan(rows, planes, words, boot_rows, rank, world, mode, grid)
 
     def sym_band(self, rows, words, boot_rows, rank, world):
         """Stream rows [begin, end) of this rank's band (mode 1 of hamming_knn_sym)."""
@@ -202,6 +216,16 @@ class CudaEngine:
                                                int(drop), weight, _ptr(idx), _ptr(w), self._stream()))
         return idx, w
 
+    def knn_lists_merge(self, lists, k, drop=1):
+        """(n_lists, rows, k1) sorted key lists -> (rows, k) merged keys after dropping the first `drop`
+        (pg_knn_lists_merge); -1 = missing."""
+        lists = lists.contiguous()
+        n_lists, rows, k1 = lists.shape
+        out = self.empty((rows, k), torch.int64)
+        L.check(self.lib.pg_knn_lists_merge(_ptr(lists), n_lists, rows * k1, 0, rows, k1, int(k), int(drop), _ptr(out),
+                                            self._stream()))
+        return out
+
     def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
         """prograph.py:731-753 for own rows [row0,row0+rows): CSR (indptr, idx, w) of the
         stream rows whose distance d has bit d set in `lut` (uint32 words, host)."""
@@ -215,7 +239,7 @@ class CudaEngine:
                                               _ptr(ws), nbytes, self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
-        self._check_edge_budget(nnz)
+        self.check_edge_budget(nnz)
         weight = L.W_SIM_F32 if similarity else L.W_I64
         idx = self.empty((nnz,), torch.int64)
         w = self.empty((nnz,), torch.float32 if similarity else torch.int64)
@@ -251,7 +275,7 @@ class CudaEngine:
         cap = int(capacity) if capacity is not None else 96 * table.rows // max(1, world) + (4 << 20)
         counters = self.empty((2,), torch.int64)
         for attempt in range(2):
-            self._check_edge_budget(cap)
+            self.check_edge_budget(cap)
             keys = self.empty((cap,), torch.int64)
             L.check(self.lib.pg_hamming_eps_sym(_ptr(table.data), table.rows, table.planes, table.words, lut_p, len(lut),
                                                 int(rank), int(world), int(mode), _ptr(keys), cap, _ptr(counters), _ptr(ws),
@@ -289,7 +313,7 @@ class CudaEngine:
                                          self._stream()))
         return out
 
-    def _check_edge_budget(self, nnz):
+    def check_edge_budget(self, nnz):
         """An epsilon graph can be dense (the reference would run out of host memory the same way):
         refuse before allocating instead of taking the GPU down."""
         free, _ = torch.cuda.mem_get_info(self.device)
@@ -384,7 +408,7 @@ class CudaEngine:
                                                       _ptr(counts), self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
-        self._check_edge_budget(nnz)
+        self.check_edge_budget(nnz)
         idx = self.empty((nnz,), torch.int64)
         val = self.empty((nnz,), torch.float16 if value_kind == 0 else torch.float32)
         if nnz:
@@ -412,7 +436,7 @@ class CudaEngine:
                                                  1 if swap else 0, int(guard), _ptr(counts), self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
-        self._check_edge_budget(nnz)
+        self.check_edge_budget(nnz)
         idx = self.empty((nnz,), torch.int64)
         val = self.empty((nnz,), tile.dtype) if values else None
         if nnz:
@@ -491,6 +515,19 @@ class CudaEngine:
         n = C.c_int64(0)
         self.lib.pg_sweep_times(buf, cap, C.byref(n), 1 if reset else 0)
         return [buf[i] for i in range(min(cap, n.value))]
+
+
+def sym_plan(rows, planes, words, boot_rows=0, rank=0, world=1, mode=0, grid=296):
+    """Host-only planner of the symmetric sweeps (no GPU needed): (n_items, 5) int32 array of
+    (row block, first tile, end tile, boot flag, CTA) -- every CTA walks its items in this order."""
+    lib = L.load()
+    n = C.c_int64(0)
+    L.check(lib.pg_knn_sym_plan(int(rows), int(planes), int(words), int(boot_rows), int(rank), int(world), int(mode),
+                                int(grid), None, 0, C.byref(n)))
+    items = np.zeros((n.value, 5), dtype=np.int32)
+    L.check(lib.pg_knn_sym_plan(int(rows), int(planes), int(words), int(boot_rows), int(rank), int(world), int(mode),
+                                int(grid), items.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return items
 
 
 _ENGINE = None

@@ -16,8 +16,12 @@ Dispatch:
   * any other callable honouring the ``fn(X, Y, similarity=...) -> (M, N)`` protocol is
     called per row block exactly as the reference calls it and its device tile goes
     through the same consumers.
-Rows are sharded across the ranks of an initialised torch.distributed group; every rank
-ends up with the whole graph (all-gather of the result shards).
+The work is sharded across the ranks of an initialised torch.distributed group (shard.py);
+by default every rank ends up with the whole graph, ``output="sharded"`` leaves every rank with
+the rows of its own block (``row0`` of the returned table) and skips the final all-gather.
+Phases are wrapped in NVTX ranges (trace.py).  Off the kernel path torch is used for plumbing
+only: allocation, copies, collectives, concatenation of shards and the prefix sum / gather of
+the user-callable tile path.
 """
 import functools
 import operator
@@ -31,6 +35,7 @@ from . import shard as _shard
 from .distance.hamming import hamming, value_dtype
 from .distance.minkowski import minkowski, staged_dtype
 from .engine import get_engine
+from .trace import phase
 
 _CMP_CODES = {operator.lt: L.LT, operator.le: L.LE, operator.eq: L.EQ,
               operator.ne: L.NE, operator.ge: L.GE, operator.gt: L.GT}
@@ -45,8 +50,9 @@ class NeighbourTable:
     """Adjacency in CSR form on the host: row r owns idx[indptr[r]:indptr[r+1]] (int64,
     ascending for epsilon graphs, (distance, index) order for kNN) and the matching w."""
 
-    def __init__(self, indptr, idx, w):
+    def __init__(self, indptr, idx, w, row0=0):
         self.indptr, self.idx, self.w = indptr, idx, w
+        self.row0 = row0            # first row of this table in the whole graph (output="sharded")
 
     @property
     def n_rows(self):
@@ -71,8 +77,9 @@ class NeighbourTable:
 class KnnTable:
     """Fixed-degree kNN result: idx (N, k) int64 and w (N, k)."""
 
-    def __init__(self, idx, w):
+    def __init__(self, idx, w, row0=0):
         self.idx, self.w = idx, w
+        self.row0 = row0            # first row of this table in the whole graph (output="sharded")
 
     @property
     def n_rows(self):
@@ -183,8 +190,7 @@ def pack_table(eng, X, rank, world, group):
     (NCCL over NVLink) straight into one table -- 160 B per sequence instead of each rank
     pushing the whole token matrix through its PCIe link."""
     n = X.shape[0]
-    if (world <= 1 or n < world or not _shard.is_tile_aligned(n, world)
-            or not getattr(eng, "sharded_pack", False)):
+    if world <= 1 or n < world or not _shard.is_tile_aligned(n, world) or not eng.sharded_pack:
         return eng.pack(X)
     row0, rows = _shard.row_range(n, rank, world)
     per = _shard.rows_per_rank(n, world)
@@ -196,7 +202,15 @@ def pack_table(eng, X, rank, world, group):
     if lo < 0 or hi >= 256:
         raise OverflowError("values are not integer tokens in [0, 256)")
     planes = 5 if hi < 32 else 8
-    part = eng.pack(mine, planes=planes)
+    # a shard may be unpackable on its own (fractional values on one rank only): the decision to
+    # leave the bit-plane path is taken by all ranks together, before the all-gather below
+    part, code = None, _shard.OK
+    try:
+        part = eng.pack(mine, planes=planes)
+    except OverflowError:
+        code = _shard.UNPACKABLE
+    if _shard.agree(code, world, group, mine.device) != _shard.OK:
+        raise OverflowError("values are not integer tokens in [0, 256) on some rank")
     words = part.words
     shard_buf = torch.zeros((per, planes, words), dtype=torch.int32, device=part.data.device)
     shard_buf[: min(per, part.data.shape[0])] = part.data[:per]
@@ -228,56 +242,82 @@ SYM_BOOT_DIV = 8          # ... but at most 1/8 of the table
 
 
 def _sym_enabled(eng, packed, k1, world):
-    if not hasattr(eng, "hamming_knn_sym"):
-        return False
     force = os.environ.get("PG_KNN_SYM")
     if force is not None:
         return force not in ("0", "")
-    return SYM_MIN_ROWS <= packed.rows < (1 << 31) and k1 <= getattr(eng, "SYM_MAX_LIST", 0)
+    return SYM_MIN_ROWS <= packed.rows < (1 << 31) and k1 <= eng.SYM_MAX_LIST
 
 
 def sym_boot_rows(n):
-    """Bootstrap columns for a table of n rows: a multiple of the 512-row packed tile."""
-    return max(0, min(SYM_BOOT_ROWS, n // SYM_BOOT_DIV // _shard.ROW_ALIGN * _shard.ROW_ALIGN))
+    """Bootstrap columns for a table of n rows: a multiple of the 512-row packed tile
+    (PG_SYM_BOOT overrides the default of 8192 for experiments)."""
+    want = int(os.environ.get("PG_SYM_BOOT", SYM_BOOT_ROWS))
+    return max(0, min(want, n // SYM_BOOT_DIV) // _shard.ROW_ALIGN * _shard.ROW_ALIGN)
 
 
-def hamming_knn_graph(eng, packed, k, similarity, rank, world, group):
-    """kNN lists of EVERY row of `packed` against itself (prograph.py:755-765), on every rank.
+def hamming_knn_graph(eng, packed, k, similarity, rank, world, group, output="replicated"):
+    """kNN lists of EVERY row of `packed` against itself (prograph.py:755-765): (idx, w, row0).
+    ``output="replicated"``: all rows on every rank (row0 = 0); ``"sharded"``: this rank's row block.
 
     Large tables take the symmetric sweep: d(i,j) == d(j,i), so each unordered pair is evaluated
     once and offered to both rows' lists.  Ranks own bands of stream rows of the triangle (equal
-    numbers of pair evaluations); the per-rank candidate lists of all rows are all-gathered
-    (NCCL) and merged -- the exchange step of this path.  Small tables and long lists take the one-sided sweep on this rank's row
-    block followed by the all-gather of the result rows."""
+    numbers of pair evaluations); the exchange step of this path is an all-to-all of the per-rank
+    candidate lists (every rank receives all ranks' lists of its own rows and merges them),
+    followed by the all-gather of the merged keys.  Small tables and long lists take the one-sided
+    sweep on this rank's row block followed by the all-gather of the result rows."""
     n = packed.rows
     kk = min(k, n - 1)
     if kk > 0 and _sym_enabled(eng, packed, kk + 1, world):
         try:
-            return _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group)
+            return _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group, output)
         except L.Unsupported:
             pass
     row0, rows = _shard.row_range(n, rank, world)
-    part = hamming_knn_device(eng, packed, packed, k, similarity, row0, rows) if rows else None
-    return _shard.gather_rows(part, n, rank, world, group, eng)
+    with phase("sweep"):
+        part = hamming_knn_device(eng, packed, packed, k, similarity, row0, rows) if rows else None
+    if output == "sharded":
+        return part + (row0,)
+    with phase("gather"):
+        return _shard.gather_rows(part, n, rank, world, group, eng) + (0,)
 
 
-def _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group):
+def _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group, output):
     n, k1 = packed.rows, kk + 1
     sharded = world > 1 and n >= world
     if not sharded:
         rank, world = 0, 1
     boot = sym_boot_rows(n)
     seed = None
+    row0, rows = _shard.row_range(n, rank, world)
     if boot:
-        row0, rows = _shard.row_range(n, rank, world)
-        seed = eng.hamming_knn_boot(packed, row0, rows, boot, k1)
-        seed = _shard.gather_rows((seed,), n, rank, world, group, eng)[0].contiguous()
+        with phase("boot"):
+            seed = eng.hamming_knn_boot(packed, row0, rows, boot, k1)
+        with phase("boot_gather"):
+            seed = _shard.gather_rows((seed,), n, rank, world, group, eng)[0].contiguous()
     # several ranks: column bands (mode 1) -- all column-side candidates of a row meet on one rank,
     # so its filter tightens as fast as on a single GPU
-    lists = eng.hamming_knn_sym(packed, k1, rank, world, lists=seed, boot_rows=boot, mode=1 if sharded else 0)
-    if sharded:
-        lists = _shard.all_gather_stack(lists, world, group)          # (world, n, k1)
-    return eng.knn_lists_finalize(lists, 0, n, kk, 1, similarity)
+    with phase("sweep"):
+        lists = eng.hamming_knn_sym(packed, k1, rank, world, lists=seed, boot_rows=boot, mode=1 if sharded else 0)
+    if not sharded:
+        with phase("finalize"):
+            out = eng.knn_lists_finalize(lists, 0, n, kk, 1, similarity)
+        eng.sym_check()
+        return out + (0,)
+    with phase("exchange"):
+        mine = _shard.exchange_lists(lists, n, rank, world, group)        # (world, rows, k1): my rows, every rank's view
+    with phase("merge"):
+        keys = eng.knn_lists_merge(mine, kk, drop=1)                      # (rows, kk) merged keys
+    if output == "sharded":
+        with phase("finalize"):
+            out = eng.knn_lists_finalize(keys, 0, rows, kk, 0, similarity)
+        eng.sym_check()
+        return out + (row0,)
+    with phase("gather"):
+        keys = _shard.gather_rows((keys,), n, rank, world, group, eng)[0].contiguous()
+    with phase("finalize"):
+        out = eng.knn_lists_finalize(keys, 0, n, kk, 0, similarity)
+    eng.sym_check()
+    return out + (0,)
 
 
 def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
@@ -313,6 +353,17 @@ def _eps_sample(n):
     return (row0, rows) if row0 + rows <= n else (0, rows)
 
 
+def _raise_code(code, exc=None):
+    """Raise on every rank what some rank ran into (its own exception where it has one)."""
+    if exc is not None:
+        raise exc
+    if code == _shard.NO_MEMORY:
+        raise MemoryError("the requested graph does not fit in device memory on some rank; lower eps or build a "
+                          "kNN graph")
+    if code == _shard.UNPACKABLE:
+        raise OverflowError("values are not integer tokens on some rank")
+
+
 def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     """Epsilon graph (CSR of every row) of `packed` against itself, on every rank
     (prograph.py:731-753).  Large, sparse graphs whose edge test is one contiguous distance range
@@ -322,32 +373,54 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     key buffer and sends dense graphs (bound by writing their edges, not by distances) to the
     count / fill passes.  Ranks sweep bands of the triangle and all-gather their key buffers.
     Everything else: count / fill with the one-sided sweep on this rank's row block, then the CSR
-    all-gather."""
+    all-gather.  Rank-local failures (edge budget) are agreed on before every collective."""
     n = packed.rows
+    dev = eng.device
+    sharded = world > 1 and n >= world
     force = os.environ.get("PG_EPS_SYM")
-    use_sym = hasattr(eng, "hamming_eps_sym") and (n >= SYM_EPS_MIN_ROWS if force is None else force not in ("0", ""))
+    use_sym = n >= SYM_EPS_MIN_ROWS if force is None else force not in ("0", "")
     if use_sym:
-        try:
-            sharded = world > 1 and n >= world
-            parts = world if sharded else 1
+        # every rank samples the same rows -> the same degree, capacity and branch on all of them
+        parts = world if sharded else 1
+        with phase("sample"):
             degree = eng.hamming_eps_mean_degree(packed, *_eps_sample(n), packed, lut)
-            if degree > SYM_EPS_MAX_DEGREE and force is None:
-                raise L.Unsupported("dense graph")
-            capacity = int(1.5 * degree * n / parts) + (4 << 20)
-            if capacity * parts >= (1 << 31):          # one radix sort takes fewer than 2^31 keys
-                raise L.Unsupported("edge list too long for one key sort")
-            keys, edges = eng.hamming_eps_sym(packed, lut, rank if sharded else 0, parts, mode=1 if sharded else 0,
-                                              capacity=capacity)
-            if sharded:
-                keys, edges = _shard.gather_edge_keys(keys, edges, world, group)
-            if hasattr(eng, "_check_edge_budget"):
-                eng._check_edge_budget(edges)
-            return eng.edge_keys_to_csr(keys, n, packed.words, edges, similarity)
+        capacity = int(1.5 * degree * n / parts) + (4 << 20)
+        if (degree > SYM_EPS_MAX_DEGREE and force is None) or capacity * parts >= (1 << 31):
+            use_sym = False        # dense graph, or more keys than one radix sort takes
+    if use_sym:
+        code, keys, edges, exc = _shard.OK, None, 0, None
+        try:
+            with phase("sweep"):
+                keys, edges = eng.hamming_eps_sym(packed, lut, rank if sharded else 0, parts, mode=1 if sharded else 0,
+                                                  capacity=capacity)
         except L.Unsupported:
-            pass
+            code = _shard.UNSUPPORTED          # shape / predicate: the same on every rank
+        except MemoryError as e:
+            code, exc = _shard.NO_MEMORY, e
+        code = _shard.agree(code, world, group, dev) if sharded else code
+        _raise_code(code, exc)
+        if code == _shard.OK:
+            if sharded:
+                with phase("exchange"):
+                    keys, edges = _shard.gather_edge_keys(keys, edges, world, group)
+            code = _shard.OK
+            try:
+                eng.check_edge_budget(edges)
+            except MemoryError as e:
+                code, exc = _shard.NO_MEMORY, e
+            _raise_code(_shard.agree(code, world, group, dev) if sharded else code, exc)
+            with phase("csr"):
+                return eng.edge_keys_to_csr(keys, n, packed.words, edges, similarity)
     row0, rows = _shard.row_range(n, rank, world)
-    part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
-    return _shard.gather_csr(part, n, rank, world, group, eng)
+    code, part, exc = _shard.OK, None, None
+    try:
+        with phase("sweep"):
+            part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
+    except MemoryError as e:
+        code, exc = _shard.NO_MEMORY, e
+    _raise_code(_shard.agree(code, world, group, dev) if sharded else code, exc)
+    with phase("gather"):
+        return _shard.gather_csr(part, n, rank, world, group, eng)
 
 
 # ---------------------------------------------------------------------------------
@@ -451,11 +524,26 @@ def _tile_eps(eng, tiles, eps, comp, similarity):
 # ---------------------------------------------------------------------------------
 # public entry
 # ---------------------------------------------------------------------------------
+def _shard_csr(csr, n, rank, world):
+    """Rows of this rank's block out of a whole-graph CSR on the device: (indptr, idx, w, row0)."""
+    indptr, idx, w = csr
+    row0, rows = _shard.row_range(n, rank, world)
+    a, b = (int(v) for v in indptr[[row0, row0 + rows]].tolist())
+    return indptr[row0:row0 + rows + 1] - a, idx[a:b], w[a:b], row0
+
+
 def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, comp=operator.le,
-                     batch_size=8, idxs=None, engine=None, group=None, packed=None):
+                     batch_size=8, idxs=None, engine=None, group=None, packed=None, output="replicated"):
     """Device implementation of ``Prograph.build_graph`` (prograph.py:656-765) on a
-    representation matrix.  Returns a NeighbourTable (epsilon) or KnnTable (k)."""
+    representation matrix.  Returns a NeighbourTable (epsilon) or KnnTable (k) of host arrays.
+
+    output : "replicated" (default) -- the whole graph on every rank of the process group, what a
+        drop-in ``build_graph`` returns; "sharded" -- every rank keeps and copies to the host only
+        the rows of its own block (``table.row0``, ``shard.row_range``): the graph then exists once
+        across the job's host memory and the final all-gather is skipped."""
     validate(eps, k)
+    if output not in ("replicated", "sharded"):
+        raise ValueError("output must be 'replicated' or 'sharded'")
     if similarity and eps:
         eps = 1 / (1 + eps)                                   # prograph.py:720-721
     eng = engine if engine is not None else get_engine()
@@ -473,7 +561,8 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
         packed = None
     if kind == "hamming" and packed is None:
         try:
-            packed = pack_table(eng, X, rank, world, group)
+            with phase("pack"):
+                packed = pack_table(eng, X, rank, world, group)
         except OverflowError:
             packed = None
     if packed is not None and (packed.words > 56 or (packed.words > 8 and packed.planes != 5)):
@@ -482,16 +571,21 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
     if packed is not None:
         if eps:
             lut = distance_lut(packed.words * 32, comp, eps, similarity)
-            indptr, idx, w = hamming_eps_graph(eng, packed, lut, similarity, rank, world, group)
-            return NeighbourTable(_to_host(indptr), _to_host(idx), _to_host(w))
+            csr = hamming_eps_graph(eng, packed, lut, similarity, rank, world, group)
+            shard0 = 0
+            if output == "sharded":
+                *csr, shard0 = _shard_csr(csr, n, rank, world)
+            with phase("d2h"):
+                return NeighbourTable(*(_to_host(t) for t in csr), row0=shard0)
         else:
-            idx, w = hamming_knn_graph(eng, packed, k, similarity, rank, world, group)
-            return KnnTable(_to_host(idx), _to_host(w))
+            idx, w, shard0 = hamming_knn_graph(eng, packed, k, similarity, rank, world, group, output)
+            with phase("d2h"):
+                return KnnTable(_to_host(idx), _to_host(w), row0=shard0)
     else:
         # prograph.py:726: every representation is rounded to fp16 before the metric sees it
         Xh = eng.to_device(X).to(torch.float16)
         gemm = None
-        if kind == "minkowski" and float(p) == 2.0 and Xh.shape[1] <= getattr(eng, "GEMM_MAX_WIDTH", 0):
+        if kind == "minkowski" and float(p) == 2.0 and Xh.shape[1] <= eng.GEMM_MAX_WIDTH:
             # integer tokens <= 31: the fp16 chain is a function of the exact integer
             # |x|^2 + |y|^2 - 2 x.y  ->  int8 tensor-core contraction (pg_gemm.cu)
             try:
@@ -524,8 +618,9 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
             else:
                 part = _tile_knn(eng, tiles, k, similarity, n) if rows else None
 
+    sharded_out = output == "sharded"
     if eps:
-        indptr, idx, w = _shard.gather_csr(part, n, rank, world, group, eng)
-        return NeighbourTable(_to_host(indptr), _to_host(idx), _to_host(w))
-    idx, w = _shard.gather_rows(part, n, rank, world, group, eng)
-    return KnnTable(_to_host(idx), _to_host(w))
+        indptr, idx, w = part if sharded_out else _shard.gather_csr(part, n, rank, world, group, eng)
+        return NeighbourTable(_to_host(indptr), _to_host(idx), _to_host(w), row0=row0 if sharded_out else 0)
+    idx, w = part if sharded_out else _shard.gather_rows(part, n, rank, world, group, eng)
+    return KnnTable(_to_host(idx), _to_host(w), row0=row0 if sharded_out else 0)

@@ -1,13 +1,20 @@
-"""Row-block sharding of the graph build across the GPUs of one box.
+"""Sharding of the graph build across the GPUs of one box (torch.distributed: NCCL over NVLink
+on the GPU box, gloo in the CPU tests).  There is no collective inside a distance sweep.
 
-Every output row (its kNN list, its edge list, its query result) depends on that row and
-the whole table only, so rank g owns query rows [g*ceil(N/G), (g+1)*ceil(N/G)) against all
-N columns: no cross-rank merge, tie semantics untouched.  The only
-collectives are all-gathers of the result shards over torch.distributed (NCCL over NVLink
-on the GPU box, gloo in the CPU tests); there is no collective inside the distance sweep.
-The symmetric kNN build (graph.hamming_knn_graph) shards the triangle of unordered pairs by
-interleaved 256-row blocks instead; there every rank holds candidate lists for all rows and
-the all-gather of those lists is followed by a merge (pg_knn_lists_finalize).
+One-sided sweeps (epsilon count / fill, queries, small or long-list kNN): every output row
+depends on that row and the whole table only, so rank g owns the query rows of `row_range`
+against all N columns -- no cross-rank merge, tie semantics untouched -- and the
+result shards are all-gathered.
+
+Symmetric sweeps (graph.hamming_knn_graph / hamming_eps_graph on large tables): the triangle of
+unordered pairs is cut into bands of stream rows holding equal numbers of pair evaluations
+(pg_knn_sym_band); rank g sweeps every row block against its band.  kNN: every rank then holds
+candidate lists for ALL rows, and the exchange step is an all-to-all -- rank g receives every
+rank's lists of ITS rows (`exchange_lists`), merges them (pg_knn_lists_merge) and the merged
+8-byte keys are all-gathered.  Epsilon: the ranks' edge-key buffers are all-gathered and sorted.
+
+`agree` makes rank-local failures collective: a rank that cannot go on (unpackable shard, edge
+budget exceeded) must not leave its peers waiting in the next collective.
 """
 import torch
 import torch.distributed as dist
@@ -85,6 +92,30 @@ def all_gather_stack(t, world, group):
     out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t.contiguous(), group=group)
     return out.reshape((world,) + tuple(t.shape))
+
+
+def exchange_lists(lists, n, rank, world, group):
+    """Candidate lists of ALL n rows on every rank, (n, k1) -> (world, my rows, k1): list s of my
+    row r as found by rank s (one all-to-all; rank g receives only its row block's lists)."""
+    sizes = [row_range(n, r, world)[1] for r in range(world)]
+    mine = sizes[rank]
+    out = torch.empty((world * mine,) + tuple(lists.shape[1:]), dtype=lists.dtype, device=lists.device)
+    dist.all_to_all_single(out, lists.contiguous(), output_split_sizes=[mine] * world, input_split_sizes=sizes,
+                           group=group)
+    return out.reshape((world, mine) + tuple(lists.shape[1:]))
+
+
+OK, UNPACKABLE, UNSUPPORTED, NO_MEMORY = 0, 1, 2, 3
+
+
+def agree(code, world, group, device):
+    """MAX over the ranks of a small status code: every rank learns whether any rank failed a
+    rank-local step and all of them take the same branch before the next collective."""
+    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        return int(code)
+    t = torch.tensor([int(code)], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
 
 
 def gather_edge_keys(keys, edges, world, group):

@@ -16,10 +16,30 @@ class _Packed:
 
 
 class CheckerEngine:
+    """The full engine interface graph.py uses on the fused Hamming path, answered by the oracle."""
     device = torch.device("cpu")
+    sharded_pack = False          # tables are packed whole on every rank
+    GEMM_MAX_WIDTH = 0            # no tensor-core path
 
     def __init__(self):
         self.rows_seen = (0, 0)
+        self.sym_checks = 0
+
+    def sym_check(self):
+        self.sym_checks += 1
+
+    def check_edge_budget(self, nnz):
+        pass
+
+    def knn_lists_merge(self, lists, k, drop=1):
+        """(n_lists, rows, k1) -> (rows, k) merged unique keys after `drop`, -1 = missing."""
+        lists = lists.numpy()
+        rows = lists.shape[1]
+        out = np.full((rows, k), -1, dtype=np.int64)
+        for r in range(rows):
+            keys = sorted(set(int(v) for v in lists[:, r].reshape(-1) if v != -1))[drop:drop + k]
+            out[r, :len(keys)] = keys
+        return torch.from_numpy(out)
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype)

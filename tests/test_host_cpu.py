@@ -201,7 +201,8 @@ def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
 @pytest.mark.parametrize("n,boot_div", [(700, 8), (1301, 2)])
 def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
     """world_size 2 on CPU, symmetric kNN build: ranks take column bands of the triangle, exchange
-    their candidate lists (all-gather) and merge; with and without the bootstrap pass."""
+    their candidate lists (all-to-all: every rank receives all ranks' lists of its rows), merge and
+    all-gather the merged keys; with and without the bootstrap pass."""
     import torch.multiprocessing as mp
     from oracle import prograph_oracle as O
     k, world = 5, 2
@@ -275,11 +276,8 @@ def test_symmetric_build_policies():
     switches that keep small / unusual builds on the one-sided kernels."""
     from prograph_b200 import graph
 
-    class Eng:                      # the attributes _sym_enabled looks at
+    class Eng:                      # the attribute _sym_enabled looks at
         SYM_MAX_LIST = 32
-
-        def hamming_knn_sym(self):
-            pass
 
     class Tab:
         def __init__(self, rows):
@@ -297,7 +295,6 @@ def test_symmetric_build_policies():
         assert graph._sym_enabled(Eng(), Tab(graph.SYM_MIN_ROWS), 17, 1)
         assert not graph._sym_enabled(Eng(), Tab(graph.SYM_MIN_ROWS - 1), 17, 1)
         assert not graph._sym_enabled(Eng(), Tab(1_000_000), 33, 1)          # list too long for the symmetric sweep
-        assert not graph._sym_enabled(object(), Tab(1_000_000), 17, 1)       # an engine without the symmetric kernels
         os.environ["PG_KNN_SYM"] = "0"
         assert not graph._sym_enabled(Eng(), Tab(1_000_000), 17, 1)
         os.environ["PG_KNN_SYM"] = "1"
