@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Headline benchmark: Gpairs/s of the Hamming all-pairs + kNN (k=16) graph build on a
-synthetic library of N=1M sequences, L=256 (BASELINE.json configs[3]), at 1/2/4/8 B200.
+synthetic library of N=1M sequences, L=256 (BASELINE.json configs[3]), at 1/2/4/8 B200, with the
+threshold (epsilon) graphs of the same path as a second block of the same JSON line.
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -8,17 +9,26 @@ synthetic library of N=1M sequences, L=256 (BASELINE.json configs[3]), at 1/2/4/
     python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port)
 
 A step = one full graph build: pack the token table into bit planes, build the kNN lists of
-all N rows with the fused Hamming+top-k sweeps, finalise, and all-gather.  The build is the
-symmetric one (prograph_b200/csrc/pg_sweep_sym.cuh): d(i,j) == d(j,i), so after a one-sided
-bootstrap pass over the first 8192 columns every unordered pair is evaluated ONCE and offered
-to both rows' lists.  The metric still counts all N^2 ordered pairs -- what the reference
-evaluates and what `--one-sided` (the previous kernel) evaluates -- while the roofline is
-computed on the pair evaluations actually issued (`pairs_evaluated`).  `value` times the
-build with the uint8 token table resident in HBM; `e2e` times the public API call
-(prograph_b200.build_neighbours) on a pinned HOST token table, i.e. H2D + the same work +
-D2H of the neighbour lists.  Ranks own interleaved row blocks of the triangle (total work
-fixed -> "strong" scaling) and all-gather their candidate lists; times are CUDA-event times,
-max over ranks.  One JSON line is printed by rank 0.
+all N rows with the fused Hamming+top-k sweeps, finalise, exchange.  The build is the symmetric
+one (prograph_b200/csrc/pg_sweep_sym.cuh): d(i,j) == d(j,i), so after a one-sided bootstrap pass
+over the first 8192 columns every unordered pair is evaluated ONCE and offered to both rows'
+lists.  The metric still counts all N^2 ordered pairs -- what the reference evaluates and what
+`--one-sided` (the previous kernel) evaluates -- while the roofline is computed on the pair
+evaluations actually issued (`pairs_evaluated`).  `value` times the build with the uint8 token
+table resident in HBM and the whole graph left on every GPU; `e2e` times the public API call
+(prograph_b200.build_neighbours) on a pinned HOST token table: H2D of every rank's rows + the
+same sweeps + D2H of the neighbour lists (with several ranks: output="sharded", every rank copies
+the rows of its own block, so the graph reaches host memory exactly once).  Ranks own bands of
+stream rows of the triangle holding equal numbers of pair evaluations (total work fixed ->
+"strong" scaling); the exchange is an all-to-all of candidate lists + an all-gather of merged
+keys.  Times are CUDA-event times, max over ranks.  One JSON line is printed by rank 0.
+
+After the timed regions (never inside them) the run checks itself and exits non-zero on a
+mismatch: the whole symmetric result against the one-sided sweep on the device, sampled rows
+(band and bootstrap edges, block edges, last row, random rows) against the CPU oracle, every
+rank against rank 0 (`parity`).  The `eps` block does the same for the threshold graphs:
+C4-M (mutational library, N=1M) eps=1 as a CSR, eps=2 as a degree census (its CSR would hold
+1.6e10 edges = 250 GB), and the GB1-style 160 000 x 56 library (C3) with its known answers.
 """
 import argparse
 import json
@@ -50,6 +60,8 @@ def parse_args():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "mutational"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eps", action="store_true", help="skip the threshold-graph block")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity checks")
     ap.add_argument("--one-sided", action="store_true",
                     help="evaluate all N^2 ordered pairs with the one-sided sweep (no symmetry)")
     return ap.parse_args()
@@ -67,6 +79,23 @@ def make_tokens(n, L, kind):
         rows = np.nonzero(m > j)[0]
         pos = rng.integers(0, L, size=len(rows))
         X[rows, pos] = (X[rows, pos] - 1 + rng.integers(1, 20, size=len(rows))) % 20 + 1
+    return X
+
+
+GB1 = "MTYKLILNGKTLKGETTTEAVDAATAEKVFKQYANDNGVDGEWTYDDATKTFTVTE"
+GB1_SITES = (38, 39, 40, 53)
+ALPHABET = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def make_gb1_library():
+    """every combination of the 20 residues at 4 sites of the 56-residue GB1 domain,
+    in itertools.product order -> (160 000, 56) uint8 tokens 1..20."""
+    tok = {a: i + 1 for i, a in enumerate(ALPHABET)}
+    wt = np.array([tok[c] for c in GB1], dtype=np.uint8)
+    X = np.tile(wt, (20 ** 4, 1))
+    idx = np.indices((20, 20, 20, 20)).reshape(4, -1)
+    for s, site in enumerate(GB1_SITES):
+        X[:, site] = idx[s] + 1
     return X
 
 
@@ -189,11 +218,12 @@ class ClockSampler:
 
 def ncu_traffic_bytes(n, world, capture):
     """dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel, per launch, from the
-    committed `ncu --set full` capture of this exact configuration (profiles/); None otherwise."""
+    committed ncu capture of this exact configuration (profiles/); None otherwise.  ncu is the only
+    source of DRAM counters, so this figure cannot be measured inside an un-profiled run."""
     if n != 1_000_000 or world != 1:
         return None
     path = os.path.join(ROOT, "profiles", capture)
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total = 0.0
     try:
         for line in open(path):
@@ -203,6 +233,64 @@ def ncu_traffic_bytes(n, world, capture):
     except OSError:
         return None
     return total or None
+
+
+def triangle_pairs(n, boot, band):
+    """Pair evaluations of the symmetric sweep inside the stream-row band [band[0], band[1]): every
+    256-row block sweeps the stream rows from its own block on (bootstrap blocks: from `boot` on)."""
+    total = 0.0
+    for rb in range(0, -(-n // 256)):
+        a, b = rb * 256, min(n, rb * 256 + 256)
+        lo = max(boot if a < boot else a, band[0])
+        total += float(b - a) * max(0, band[1] - lo)
+    return total
+
+
+# ----------------------------------------------------------------------------------------
+# parity helpers (run after the timed regions)
+# ----------------------------------------------------------------------------------------
+def sample_rows(n, world, eng, words, boot, count=256, seed=7):
+    """Rows whose lists meet every seam of the build: bootstrap edge, row-block and tile edges, the
+    band edges of every rank, the row-block shard edges, first / last row -- plus random rows."""
+    from prograph_b200 import shard
+    rows = {0, 1, 255, 256, 511, 512, n - 1, n - 2, n // 2}
+    if boot:
+        rows |= {boot - 1, boot, boot + 1, boot + 255, boot + 256}
+    for r in range(world):
+        if world > 1:
+            a, b = eng.sym_band(n, words, boot, r, world)
+            rows |= {a - 1, a, a + 1, b - 1, b}
+        r0, rr = shard.row_range(n, r, world)
+        rows |= {r0 - 1, r0, r0 + rr - 1}
+    rows = {r for r in rows if 0 <= r < n}
+    rng = np.random.default_rng(seed)
+    while len(rows) < min(count, n):
+        rows.add(int(rng.integers(0, n)))
+    return np.array(sorted(rows), dtype=np.int64)
+
+
+def all_true(flag, world, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def same_on_all_ranks(tensors, rank, world):
+    """Every rank holds bit-identical copies of `tensors` (compared with rank 0's)."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return True
+    ok = True
+    for t in tensors:
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        ok &= bool(torch.equal(ref, t))
+        del ref
+    return all_true(ok, world, tensors[0].device)
 
 
 # ----------------------------------------------------------------------------------------
@@ -220,10 +308,11 @@ def run_b200(args):
     if args.one_sided:
         os.environ["PG_KNN_SYM"] = "0"
     from prograph_b200 import build_neighbours
-    from prograph_b200 import graph, shard
+    from prograph_b200 import graph, shard, trace
     from prograph_b200.engine import get_engine
     eng = get_engine()
     n, L, k = args.n, args.length, args.k
+    cores = len(os.sched_getaffinity(0))
 
     tokens = make_tokens(n, L, args.dist)
     host = torch.from_numpy(tokens).pin_memory()
@@ -234,10 +323,6 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step_resident():
-        tab = eng.pack(dev)
-        return graph.hamming_knn_graph(eng, tab, k, False, rank, world, None)
 
     def timed(fn, steps):
         barrier()
@@ -252,6 +337,21 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def max_over_ranks(d):
+        """{phase: ms} -> max over ranks per phase (rank 0's key set)."""
+        keys = sorted(d)
+        t = torch.tensor([d[key] for key in keys], device=eng.device, dtype=torch.float64)
+        if world > 1 and len(keys):
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {key: float(v) for key, v in zip(keys, t.tolist())}
+
+    last = {}
+
+    def step_resident():
+        with trace.phase("pack"):
+            tab = eng.pack(dev)
+        last["knn"] = graph.hamming_knn_graph(eng, tab, k, False, rank, world, None)[:2]
+
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local)
@@ -260,7 +360,10 @@ def run_b200(args):
     eng.launch_count(reset=True)
     eng.time_sweeps(True)
     eng.sweep_time(reset=True)
+    trace.enable_timing(True)
     ms_total = timed(step_resident, args.steps)
+    phases = max_over_ranks({key: v / args.steps for key, v in trace.phases().items()})
+    trace.enable_timing(False)
     sweep_list = eng.sweep_times(reset=True)
     eng.time_sweeps(False)
     launches = eng.launch_count(reset=True)
@@ -271,52 +374,116 @@ def run_b200(args):
     # ---- end to end through the public API, host buffers in, host arrays out -------------
     e2e = None
     if not args.no_e2e:
+        out_mode = "sharded" if world > 1 else "replicated"
+        got = {}
+
         def step_e2e():
-            return build_neighbours(host, k=k)
+            got["t"] = build_neighbours(host, k=k, output=out_mode)
         step_e2e()
         e2e_steps = max(1, min(args.steps, 3))
+        trace.enable_timing(True)
         e2e_ms = timed(step_e2e, e2e_steps)
+        e2e_phases = max_over_ranks({key: v / e2e_steps for key, v in trace.phases().items()})
+        trace.enable_timing(False)
         kk = min(k, n - 1)
         e2e = {"value": pairs * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": int(n * kk * 16) * world,
-               "ms_per_step": e2e_ms / e2e_steps,
-               "api": "prograph_b200.build_neighbours(pinned uint8 tokens, k=16) -> numpy idx/weights on every rank"}
+               # every rank uploads only its own rows and reads back only its own rows: one copy of the
+               # token table in, one copy of the graph out, summed over the ranks
+               "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(n * kk * 16),
+               "ms_per_step": e2e_ms / e2e_steps, "phases_ms": e2e_phases,
+               "api": f"prograph_b200.build_neighbours(pinned uint8 tokens, k={k}, output='{out_mode}') -> numpy "
+                      "idx/weights" + (" of this rank's row block (the graph reaches host memory once)"
+                                       if world > 1 else "")}
+        # the API result of the last step must be what the resident build produced
+        if not args.no_parity:
+            t = got["t"]
+            gi, gw = last["knn"]
+            e2e["matches_resident"] = all_true(
+                bool(np.array_equal(t.idx, gi[t.row0:t.row0 + t.n_rows].cpu().numpy())
+                     and np.array_equal(t.w, gw[t.row0:t.row0 + t.n_rows].cpu().numpy())), world, eng.device)
+        del got
+
+    # ---- parity of the timed result (outside every timed region) --------------------------------
+    words = eng.packed_words(L)
+    symmetric = (not args.one_sided) and len(sweep_list) == 2 * args.steps
+    boot = graph.sym_boot_rows(n) if symmetric else 0
+    parity = None
+    if not args.no_parity:
+        gi, gw = last["knn"]
+        tab = eng.pack(dev)
+        # (a) every entry of this rank's row block against the one-sided sweep (all rows at N=1)
+        oi, ow = eng.hamming_knn(tab, row0, rows, tab, min(k, n - 1), drop=1)
+        full = all_true(bool(torch.equal(oi, gi[row0:row0 + rows]) and torch.equal(ow, gw[row0:row0 + rows])),
+                        world, eng.device)
+        del oi, ow
+        # (b) all ranks hold the same graph
+        ident = same_on_all_ranks([gi, gw], rank, world)
+        # (c) sampled rows against the CPU oracle (rank 0; C restatement, pinned by tests/ to the numpy
+        #     oracle, which is pinned to fixtures generated from the unmodified reference)
+        ok_oracle, n_oracle = True, 0
+        if rank == 0:
+            from oracle import c_oracle as CO
+            srows = sample_rows(n, world, eng, words, boot)
+            planes = CO.pack(tokens)
+            ri, rd = CO.hamming_knn_rows(planes, L, srows, min(k, n - 1), threads=cores)
+            sel = torch.from_numpy(srows).to(eng.device)
+            ok_oracle = bool(np.array_equal(gi[sel].cpu().numpy(), ri) and np.array_equal(gw[sel].cpu().numpy(), rd))
+            n_oracle = len(srows)
+            del planes
+        ok_oracle = all_true(ok_oracle, world, eng.device)
+        parity = {"rows_vs_oracle": n_oracle, "oracle_ok": ok_oracle, "full_vs_onesided": full,
+                  "ranks_identical": ident, "ok": bool(ok_oracle and full and ident),
+                  "how": "one-sided sweep (pg_hamming_knn) over every row of each rank's block; rows sampled at "
+                         "band / bootstrap / block edges + random ones against oracle/hamming_knn_cpu.c; "
+                         "broadcast of rank 0's idx/w compared on every rank"}
+        if e2e is not None and "matches_resident" in e2e:
+            parity["ok"] = bool(parity["ok"] and e2e["matches_resident"])
+        del tab
+    last.clear()
+
+    # ---- threshold graphs: the second headline ----------------------------------------------------
+    eps_block = None
+    if not args.no_eps and not args.one_sided:
+        del dev, host
+        torch.cuda.empty_cache()
+        eps_block = run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores)
+        if parity is not None and eps_block is not None:
+            parity["eps_ok"] = bool(all(c.get("parity", {}).get("ok", True) for c in eps_block["cases"]))
+            parity["ok"] = bool(parity["ok"] and parity["eps_ok"])
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.exit(1)
         return
 
     # ---- roofline of the dominant kernel, on the pair evaluations it actually issued ---------
-    words = eng.packed_words(L)
     lane_ops_per_pair = 7 * words                       # 5 LOP3 + 1 POPC + 1 IADD per 32 residues
-    symmetric = (not args.one_sided) and len(sweep_list) == 2 * args.steps
-    boot = graph.sym_boot_rows(n) if symmetric else 0
     if symmetric:
         # rank 0's share: bootstrap rectangle + its piece of the triangle (one GPU: everything;
         # several: the band of stream rows the library's planner gives rank 0)
         boot_pairs = float(shard.row_range(n, 0, world)[1]) * boot
         band = (0, n) if world == 1 else eng.sym_band(n, words, boot, 0, world)
-        tri_pairs = 0.0
-        for rb in range(0, -(-n // 256)):
-            a, b = rb * 256, min(n, rb * 256 + 256)
-            lo = max(boot if a < boot else a, band[0])
-            tri_pairs += float(b - a) * max(0, band[1] - lo)
+        tri_pairs = triangle_pairs(n, boot, band)
         kernel_ms = sum(sweep_list[1::2]) / args.steps
         boot_ms = sum(sweep_list[0::2]) / args.steps
-        pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8>"
-        capture = "r1_ncu_sym.csv"
+        pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8,KNN,paired lanes>"
+        capture = "r2_ncu_sym_1m_dram.csv"
     else:
         boot_pairs, boot_ms = 0.0, 0.0
         kernel_ms = sum(sweep_list) / max(1, len(sweep_list))
         pairs_per_launch, kernel_name = float(rows) * float(n), "pg::sweep_kernel<5,8,KNN>"
         capture = "r1_ncu_sweep_r1d.csv"
-    peak_ops, _ = eng.int_peak(mix=0, iters=2048)
+    mix_ops, _ = eng.int_peak(mix=0, iters=2048)
     lop_ops, _ = eng.int_peak(mix=1, iters=2048)
     popc_ops, _ = eng.int_peak(mix=2, iters=2048)
     roofline = None
     if sweep_list:
         achieved = lane_ops_per_pair * pairs_per_launch / (kernel_ms * 1e-3)
+        # the binding pipe is the ALU pipe's LOP3 rate: 5 of the 7 lane-ops of a word-pair are LOP3s, so
+        # a kernel that keeps that pipe full runs at 7/5 of the measured LOP3 rate
+        peak_ops = lop_ops * 7.0 / 5.0
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -324,10 +491,13 @@ def run_b200(args):
             pass
         packed_bytes = float(n) * 5 * words * 4
         hbm_algo = packed_bytes + float(n) * (k + 1) * 8     # table read once + lists written once
+        traffic = ncu_traffic_bytes(n, world, capture)
         roofline = {
             "bound": "int-alu", "kernel": kernel_name, "achieved": achieved / 1e12,
             "peak": peak_ops / 1e12, "unit": "Tlane-op/s", "frac": achieved / peak_ops,
-            "peak_source": "measured live: pg_measure_int_peak (register-only kernel, 5 LOP3 : 1 POPC : 1 IMAD like the sweep)",
+            "peak_source": "measured live, conservative: 7/5 x the LOP3-only rate of pg_measure_int_peak (a register-only "
+                           "kernel); 5 of the 7 lane-ops per 32 residues and pair are LOP3s on the ALU pipe",
+            "frac_of_mix_probe": achieved / mix_ops, "mix_probe_tlops": mix_ops / 1e12,
             "lane_ops_per_pair": lane_ops_per_pair, "pairs_evaluated_per_launch": pairs_per_launch,
             "ordered_pairs_counted_per_step": float(n) * float(n),
             "kernel_ms": kernel_ms, "kernel_launches": args.steps,
@@ -336,7 +506,9 @@ def run_b200(args):
             "bootstrap": ({"rows": boot, "pairs_evaluated": boot_pairs, "kernel": "pg::sweep_kernel<5,8,KNN>",
                            "kernel_ms": boot_ms} if symmetric else None),
             "lop3_peak_tlops": lop_ops / 1e12, "popc_peak_tlops": popc_ops / 1e12,
-            "traffic": ncu_traffic_bytes(n, world, capture),
+            "traffic": traffic,
+            "traffic_source": (f"profiles/{capture} (ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel at "
+                               "this size; DRAM counters exist only under ncu)" if traffic else None),
             "hbm": {"algorithmic_bytes_per_launch": hbm_algo, "achieved_gbs": hbm_algo / (kernel_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
@@ -345,7 +517,6 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = len(os.sched_getaffinity(0))
         torch.set_num_threads(cores)
         cpu_reference_batches(tokens, k, 1)
         p, dt, done = cpu_reference_batches(tokens, k, 16, budget_s=20.0)
@@ -387,11 +558,169 @@ def run_b200(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8 tokens -> 5 bit planes, int32 popcount distances", "data": "synthetic",
         "config": config_of(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "phases_ms": phases, "parity": parity, "roofline": roofline, "eps": eps_block, "cpu_baseline": cpu,
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(1)
+
+
+# ----------------------------------------------------------------------------------------
+# threshold (epsilon) graphs: C4-M eps=1 (CSR), eps=2 (degree census), C3 eps=1 / eps=2
+# ----------------------------------------------------------------------------------------
+def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
+    import operator
+    import torch
+    import torch.distributed as dist
+    from prograph_b200 import build_neighbours, graph, shard, trace
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    lop_ops, _ = eng.int_peak(mix=1, iters=2048)
+    int_peak = lop_ops * 7.0 / 5.0
+    steps = max(1, min(args.steps, 3))
+    cases = []
+
+    def run_case(name, tokens, eps, mode, known_degree=None, oracle_rows=48):
+        """mode 'csr': the public graph build (symmetric sweep -> edge keys -> radix sort -> CSR, or the
+        one-sided count / fill passes for dense graphs), CSR left on every rank; 'census': degrees only."""
+        n, L = tokens.shape
+        words = eng.packed_words(L)
+        host = torch.from_numpy(tokens).pin_memory()
+        dev = host.to(eng.device)
+        row0, rows = shard.row_range(n, rank, world)
+        lut = graph.distance_lut(words * 32, operator.le, eps, False)
+        res = {}
+
+        def step():
+            with trace.phase("pack"):
+                tab = eng.pack(dev)
+            if mode == "csr":
+                res["csr"] = graph.hamming_eps_graph(eng, tab, lut, False, rank, world, None)
+            else:
+                with trace.phase("sweep"):
+                    part = eng.hamming_eps_degrees(tab, row0, rows, tab, lut)
+                with trace.phase("gather"):
+                    res["deg"] = shard.gather_rows((part,), n, rank, world, None, eng)[0]
+
+        step()
+        step()
+        eng.time_sweeps(True)
+        eng.sweep_times(reset=True)
+        trace.enable_timing(True)
+        ms = timed(step, steps) / steps
+        ph = max_over_ranks({key: v / steps for key, v in trace.phases().items()})
+        trace.enable_timing(False)
+        sw = eng.sweep_times(reset=True)
+        eng.time_sweeps(False)
+        # sweep launches per step: [degree sample, symmetric sweep] or [sample, count(, fill)] or [count]
+        per = max(1, len(sw) // steps)
+        main_ms = max(sum(sw[i::per]) / steps for i in range(per)) if sw else None
+        case = {"name": name, "n": n, "L": L, "eps": eps, "mode": mode, "ms_per_build": ms,
+                "gpairs_per_s": float(n) * n / (ms * 1e-3) / 1e9, "phases_ms": ph}
+        if mode == "csr":
+            indptr, idx, w = res["csr"]
+            nnz = int(indptr[-1].item())
+            deg = indptr[1:] - indptr[:-1]
+            symmetric = "csr" in ph                       # the key-sort phase only exists on the symmetric path
+            if symmetric:
+                band = (0, n) if world == 1 else eng.sym_band(n, words, 0, 0, world)
+                evaluated = triangle_pairs(n, 0, band)
+            else:
+                evaluated = float(shard.row_range(n, 0, world)[1]) * n          # per launch (count, and fill if it ran)
+            csr_bytes = nnz * 16.0 + (n + 1) * 8.0
+            csr_ms = ph.get("csr") if symmetric else None
+            case.update({"nnz": nnz, "path": "symmetric sweep + key sort" if symmetric else "one-sided count / fill",
+                         "roofline_sweep": ({"bound": "int-alu", "achieved": 7.0 * words * evaluated / (main_ms * 1e-3) / 1e12,
+                                             "peak": int_peak / 1e12, "unit": "Tlane-op/s",
+                                             "frac": 7.0 * words * evaluated / (main_ms * 1e-3) / int_peak,
+                                             "kernel_ms": main_ms, "pairs_evaluated_per_launch": evaluated}
+                                            if main_ms else None),
+                         "roofline_csr": ({"bound": "hbm", "achieved": csr_bytes / (csr_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                           "unit": "GB/s", "frac": csr_bytes / (csr_ms * 1e-3) / 1e9 / hbm_peak,
+                                           "algorithmic_bytes": csr_bytes, "ms": csr_ms,
+                                           "note": "radix sort of the 8-byte edge keys + decode; algorithmic bytes = the "
+                                                   "CSR written (nnz*16 + (N+1)*8), the sort's own passes are overhead"}
+                                          if csr_ms else None)})
+        else:
+            deg = res["deg"]
+            nnz = int(deg.sum().item())
+            evaluated = float(shard.row_range(n, 0, world)[1]) * n
+            case.update({"nnz": nnz, "path": "one-sided count sweep (degrees only)",
+                         "csr_bytes_if_materialised": nnz * 16.0 + (n + 1) * 8.0,
+                         "why_census": "the CSR of this graph (int64 index + int64 weight per edge) exceeds the 180 GB of "
+                                       "one B200; the reference would exhaust host memory on it as well",
+                         "roofline_sweep": ({"bound": "int-alu", "achieved": 7.0 * words * evaluated / (main_ms * 1e-3) / 1e12,
+                                             "peak": int_peak / 1e12, "unit": "Tlane-op/s",
+                                             "frac": 7.0 * words * evaluated / (main_ms * 1e-3) / int_peak,
+                                             "kernel_ms": main_ms, "pairs_evaluated_per_launch": evaluated}
+                                            if main_ms else None)})
+        # ---- parity (outside the timed region) ----
+        if not args.no_parity:
+            ok, ident = True, True
+            how = []
+            if known_degree is not None:
+                ok &= bool(torch.all(deg == known_degree).item()) and nnz == known_degree * n
+                how.append(f"known answer: every degree == {known_degree}")
+            if mode == "csr":
+                # degrees of this rank's row block against the one-sided count sweep (every row at N=1)
+                tab = eng.pack(dev)
+                cnt = eng.hamming_eps_degrees(tab, row0, rows, tab, lut)
+                ok &= bool(torch.equal(cnt, deg[row0:row0 + rows]))
+                how.append("degrees of every row vs the one-sided count sweep")
+                ident = same_on_all_ranks([indptr, idx, w], rank, world)
+                del tab, cnt
+            else:
+                ident = same_on_all_ranks([deg], rank, world)
+            n_rows = 0
+            if rank == 0:
+                from oracle import c_oracle as CO
+                srows = sample_rows(n, world, eng, words, 0, count=oracle_rows, seed=11)
+                D = CO.hamming_rows(CO.pack(tokens), L, srows, threads=cores)
+                keep = (D <= eps) & (D > 0)                          # prograph.py:736
+                if mode == "csr":
+                    ip = indptr.cpu().numpy()
+                    for i, r in enumerate(srows):
+                        cols = np.nonzero(keep[i])[0]
+                        a, b = ip[r], ip[r + 1]
+                        ok &= bool(b - a == len(cols) and np.array_equal(idx[a:b].cpu().numpy(), cols)
+                                   and np.array_equal(w[a:b].cpu().numpy(), D[i, cols]))
+                else:
+                    ok &= bool(np.array_equal(deg[torch.from_numpy(srows).to(deg.device)].cpu().numpy(), keep.sum(1)))
+                n_rows = len(srows)
+                how.append(f"{n_rows} sampled rows (index lists and weights) vs oracle/hamming_knn_cpu.c distances")
+            ok = all_true(ok, world, eng.device)
+            case["parity"] = {"ok": bool(ok and ident), "rows_vs_oracle": n_rows, "ranks_identical": ident,
+                              "how": "; ".join(how)}
+        res.clear()
+        # ---- end to end: public API, host tokens in, host CSR out (every rank its own rows) ----
+        if mode == "csr" and not args.no_e2e:
+            out_mode = "sharded" if world > 1 else "replicated"
+            build_neighbours(host, eps=eps, output=out_mode)
+            e_ms = timed(lambda: build_neighbours(host, eps=eps, output=out_mode), 1)
+            case["e2e"] = {"ms_per_build": e_ms, "gpairs_per_s": float(n) * n / (e_ms * 1e-3) / 1e9,
+                           "h2d_bytes": int(host.numel()), "d2h_bytes": int(nnz * 16 + (n + world) * 8),
+                           "api": f"prograph_b200.build_neighbours(pinned uint8 tokens, eps={eps}, output='{out_mode}')"}
+        del dev, host
+        torch.cuda.empty_cache()
+        cases.append(case)
+
+    M = make_tokens(args.n, args.length, "mutational")
+    run_case("C4-M eps=1", M, 1, "csr")
+    run_case("C4-M eps=2", M, 2, "census")
+    del M
+    G = make_gb1_library()
+    run_case("C3 GB1 20^4 eps=1", G, 1, "csr", known_degree=76)
+    run_case("C3 GB1 20^4 eps=2", G, 2, "csr", known_degree=2242)
+    if world > 1:
+        dist.barrier()
+    return {"metric": "threshold (epsilon) Hamming graphs, N^2 ordered pairs counted per build", "unit": "Gpairs/s",
+            "steps": steps, "int_peak_tlops": int_peak / 1e12, "hbm_peak_gbs": hbm_peak, "cases": cases}
 
 
 def main():

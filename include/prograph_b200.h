@@ -179,6 +179,9 @@ int pg_knn_lists_merge(const uint64_t* lists, int n_lists, int64_t list_stride,
                        int64_t row0, int64_t rows, int k1, int k, int drop,
                        uint64_t* out_keys, void* stream);
 
+/* workspace of a count pass that only counts (no capture of the first hits): the degree census of
+ * a graph too dense to materialise */
+size_t pg_eps_count_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words);
 /* epsilon graph, pass 1 (prograph.py:731-736): per own row, the number of stream rows
  * whose distance d has bit d set in `lut` (a host array of (L+32)/32 words: the
  * truth table of  comp(d, eps) & (d > 0)  -- or any other predicate of d -- evaluated

@@ -28,6 +28,11 @@ def load():
         lib.pgo_hamming_knn.restype = C.c_int
         lib.pgo_hamming_knn.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]
+        lib.pgo_hamming_knn_rows.restype = C.c_int
+        lib.pgo_hamming_knn_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p]
+        lib.pgo_hamming_rows.restype = C.c_int
+        lib.pgo_hamming_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -63,6 +68,29 @@ def hamming_knn(planes, L, q0, nq, k, threads=1):
     if rc != 0:
         raise ValueError(f"pgo_hamming_knn failed ({rc})")
     return idx, d
+
+
+def hamming_knn_rows(planes, L, rows, k, threads=1):
+    """The same for an arbitrary list of query rows: (idx, d) int64 (len(rows), k)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    idx = np.empty((len(rows), k), dtype=np.int64)
+    d = np.empty((len(rows), k), dtype=np.int64)
+    rc = load().pgo_hamming_knn_rows(planes.ctypes.data, planes.shape[0], L, rows.ctypes.data, len(rows), k, threads,
+                                     idx.ctypes.data, d.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"pgo_hamming_knn_rows failed ({rc})")
+    return idx, d
+
+
+def hamming_rows(planes, L, rows, threads=1):
+    """hamming.py:34 for the given query rows against every row: (len(rows), n) int32."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    out = np.empty((len(rows), planes.shape[0]), dtype=np.int32)
+    rc = load().pgo_hamming_rows(planes.ctypes.data, planes.shape[0], L, rows.ctypes.data, len(rows), threads,
+                                 out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"pgo_hamming_rows failed ({rc})")
+    return out
 
 
 def main():

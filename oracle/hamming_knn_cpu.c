@@ -52,7 +52,11 @@ struct knn_job {
   int64_t n, q0, nq;
   int W, k, tid, threads;
   int64_t *out_idx, *out_d;
+  const int64_t* rows;     /* optional: the query rows (nq indices); NULL = rows q0 .. q0+nq-1 */
+  int32_t* out_all;        /* pgo_hamming_rows: [nq][n] distances */
 };
+
+static inline int64_t query_row(const struct knn_job* jb, int64_t i) { return jb->rows ? jb->rows[i] : jb->q0 + i; }
 
 #define QB 8   /* query rows a thread sweeps together: the table is streamed once per block, not per row */
 
@@ -71,7 +75,7 @@ static void* knn_worker(void* arg) {
     for (int64_t j = 0; j < jb->n; ++j) {
       const uint64_t* x = jb->planes + (size_t)j * PLANES * W;
       for (int qi = 0; qi < nb; ++qi) {
-        const uint64_t* q = jb->planes + (size_t)(jb->q0 + qb0 + qi) * PLANES * W;
+        const uint64_t* q = jb->planes + (size_t)query_row(jb, qb0 + qi) * PLANES * W;
         const uint64_t key = ((uint64_t)distance(q, x, W) << 32) | (uint64_t)j;
         if (have[qi] == k1 && key >= last[qi]) continue;
         int i = have[qi] < k1 ? have[qi]++ : k1 - 1;      /* insertion into the ascending array */
@@ -98,22 +102,60 @@ static void* knn_worker(void* arg) {
   return NULL;
 }
 
+static int run_jobs(void* (*worker)(void*), struct knn_job proto, int threads) {
+  pthread_t tids[1024];
+  struct knn_job jobs[1024];
+  for (int t = 0; t < threads; ++t) {
+    jobs[t] = proto;
+    jobs[t].tid = t;
+    jobs[t].threads = threads;
+    if (t > 0 && pthread_create(&tids[t], NULL, worker, &jobs[t]) != 0) {
+      for (int u = 1; u < t; ++u) pthread_join(tids[u], NULL);
+      return -2;
+    }
+  }
+  worker(&jobs[0]);
+  for (int t = 1; t < threads; ++t) pthread_join(tids[t], NULL);
+  return 0;
+}
+
 /* kNN of query rows [q0, q0+nq) of `planes` against all n rows on `threads` threads: out_idx /
  * out_d [nq][k] hold sorted positions 1..k of every row in (distance, index) order; missing
  * entries (n < k+1) get -1 / 0 */
 int pgo_hamming_knn(const uint64_t* planes, int64_t n, int L, int64_t q0, int64_t nq, int k, int threads,
                     int64_t* out_idx, int64_t* out_d) {
   if (k < 1 || k + 1 > 256 || q0 < 0 || nq < 0 || q0 + nq > n || threads < 1 || threads > 1024) return -1;
-  pthread_t tids[1024];
-  struct knn_job jobs[1024];
-  for (int t = 0; t < threads; ++t) {
-    jobs[t] = (struct knn_job){planes, n, q0, nq, (L + 63) / 64, k, t, threads, out_idx, out_d};
-    if (t > 0 && pthread_create(&tids[t], NULL, knn_worker, &jobs[t]) != 0) {
-      for (int u = 1; u < t; ++u) pthread_join(tids[u], NULL);
-      return -2;
-    }
+  struct knn_job proto = {planes, n, q0, nq, (L + 63) / 64, k, 0, threads, out_idx, out_d, NULL, NULL};
+  return run_jobs(knn_worker, proto, threads);
+}
+
+/* the same for an arbitrary list of query rows (bench.py samples band edges and random rows) */
+int pgo_hamming_knn_rows(const uint64_t* planes, int64_t n, int L, const int64_t* rows, int64_t nq, int k, int threads,
+                         int64_t* out_idx, int64_t* out_d) {
+  if (k < 1 || k + 1 > 256 || nq < 0 || !rows || threads < 1 || threads > 1024) return -1;
+  for (int64_t i = 0; i < nq; ++i)
+    if (rows[i] < 0 || rows[i] >= n) return -1;
+  struct knn_job proto = {planes, n, 0, nq, (L + 63) / 64, k, 0, threads, out_idx, out_d, rows, NULL};
+  return run_jobs(knn_worker, proto, threads);
+}
+
+static void* rows_worker(void* arg) {
+  const struct knn_job* jb = (const struct knn_job*)arg;
+  const int W = jb->W;
+  for (int64_t i = jb->tid; i < jb->nq; i += jb->threads) {
+    const uint64_t* q = jb->planes + (size_t)query_row(jb, i) * PLANES * W;
+    int32_t* out = jb->out_all + (size_t)i * jb->n;
+    for (int64_t j = 0; j < jb->n; ++j) out[j] = distance(q, jb->planes + (size_t)j * PLANES * W, W);
   }
-  knn_worker(&jobs[0]);
-  for (int t = 1; t < threads; ++t) pthread_join(tids[t], NULL);
-  return 0;
+  return NULL;
+}
+
+/* hamming.py:34 for a list of query rows against all n rows: out [nq][n] int32 */
+int pgo_hamming_rows(const uint64_t* planes, int64_t n, int L, const int64_t* rows, int64_t nq, int threads,
+                     int32_t* out) {
+  if (nq < 0 || !rows || !out || threads < 1 || threads > 1024) return -1;
+  for (int64_t i = 0; i < nq; ++i)
+    if (rows[i] < 0 || rows[i] >= n) return -1;
+  struct knn_job proto = {planes, n, 0, nq, (L + 63) / 64, 0, 0, threads, NULL, NULL, rows, out};
+  return run_jobs(rows_worker, proto, threads);
 }

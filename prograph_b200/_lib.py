@@ -40,6 +40,7 @@ SIGNATURES = {
     "pg_pack_chars": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp]),
     "pg_sweep_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),
     "pg_eps_workspace_bytes": (_sz, [_i64, _i64, _i]),
+    "pg_eps_count_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "pg_hamming_knn": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "pg_knn_sym_workspace_bytes": (_sz, [_i64, _i]),
     "pg_hamming_knn_boot": (_i, [_vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _sz, _vp]),

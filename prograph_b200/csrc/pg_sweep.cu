@@ -668,6 +668,12 @@ size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) 
   return bytes;
 }
 
+size_t pg_eps_count_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) {
+  if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
+  // counts only: a count pass with this workspace keeps no captures (degree census of a dense graph)
+  return eps_counts_bytes(make_geometry(own_rows, stream_rows, words, kConsumers, 0), own_rows) + 256;
+}
+
 int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows, const uint32_t* stream_tab,
                    int64_t stream_rows, int planes, int words, int k, int drop, int weight, int64_t* out_idx,
                    void* out_w, void* workspace, size_t workspace_bytes, void* stream) {

@@ -249,18 +249,23 @@ class CudaEngine:
                                                  weight, _ptr(idx), _ptr(w), _ptr(ws), nbytes, self._stream()))
         return indptr, idx, w
 
-    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
-        """Mean number of edges per row over own rows [row0,row0+rows) (pg_hamming_eps_count on a
-        row sample): sizes the edge buffer of the symmetric sweep and tells dense graphs apart."""
+    def hamming_eps_degrees(self, own, row0, rows, stream, lut):
+        """Number of edges of own rows [row0,row0+rows) (pg_hamming_eps_count without captures): the
+        degree census of a graph, whether or not its CSR could be materialised.  (rows,) int64."""
         self._check_pair(own, stream)
         lut, lut_p = _host_u32(lut)
         counts = self.empty((rows,), torch.int64)
-        nbytes = int(self.lib.pg_eps_workspace_bytes(int(rows), int(stream.rows), int(own.words)))
+        nbytes = int(self.lib.pg_eps_count_workspace_bytes(int(rows), int(stream.rows), int(own.words)))
         ws = self.empty((nbytes,), torch.uint8)
         L.check(self.lib.pg_hamming_eps_count(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
                                               stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(counts),
                                               _ptr(ws), nbytes, self._stream()))
-        return float(counts.sum().item()) / rows
+        return counts
+
+    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
+        """Mean number of edges per row over a row sample: sizes the edge buffer of the symmetric
+        sweep and tells dense graphs apart."""
+        return float(self.hamming_eps_degrees(own, row0, rows, stream, lut).sum().item()) / rows
 
     def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):
         """Symmetric epsilon sweep (pg_hamming_eps_sym): this rank's piece of the triangle of

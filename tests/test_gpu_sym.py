@@ -134,25 +134,62 @@ def test_symmetric_knn_degenerate_tables(eng):
     np.testing.assert_array_equal(eps.idx[:20000], odd[:20000])  # row 0: all odd rows, ascending
 
 
-def test_symmetric_knn_deferred_merge_variant(eng, monkeypatch):
-    """The opt-in instantiation (PG_SYM_DEFER=1, planes 5 / words 8): column-side candidates queued
-    per warp and merged lane-parallel.  Same lists, whatever the arrival order."""
-    monkeypatch.setenv("PG_SYM_DEFER", "1")
-    rng = np.random.default_rng(77)
-    for n in (513, 3000):
-        X = mutational(rng, n, 256)
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("L", [40, 100, 256, 300])
+def test_symmetric_sweeps_paired_and_plain_lanes(eng, monkeypatch, pair, L):
+    """Both instantiations of the symmetric sweeps (PG_SYM_PAIR: lanes 2i / 2i+1 share their two own
+    rows, each holding one half of the plane words, vs. one whole row per lane) give the oracle's kNN
+    lists and epsilon graph, whatever the arrival order; odd row counts leave a lane without partner."""
+    from prograph_b200.graph import distance_lut
+    monkeypatch.setenv("PG_SYM_PAIR", pair)
+    rng = np.random.default_rng(77 + L)
+    for n in (513, 3001):
+        X = mutational(rng, n, L)
         tab = eng.pack(X.astype(np.uint8))
-        ri, rw = O.knn_from_distances(O.hamming(X, X), 16)
+        D = O.hamming(X, X)
+        ri, rw = O.knn_from_distances(D, 16)
         for world, boot, mode in ((1, 0, 0), (1, 512, 0), (2, 0, 1)):
             idx, w = sym_knn(eng, tab, 16, world=world, boot=boot, mode=mode)
             np.testing.assert_array_equal(np_(idx), ri)
             np.testing.assert_array_equal(np_(w), rw)
-    U = rng.integers(1, 21, size=(2100, 256)).astype(np.int64)          # heavy ties
+        keys, edges = eng.hamming_eps_sym(tab, distance_lut(tab.words * 32, operator.le, 3, False))
+        ip, ei, ew = eng.edge_keys_to_csr(keys, n, tab.words, edges)
+        keep = (D <= 3) & (D > 0)
+        r, c = np.nonzero(keep)
+        np.testing.assert_array_equal(np_(ip), np.concatenate([[0], np.cumsum(keep.sum(1))]))
+        np.testing.assert_array_equal(np_(ei), c)
+        np.testing.assert_array_equal(np_(ew), D[r, c])
+    U = rng.integers(1, 21, size=(2100, L)).astype(np.int64)          # heavy ties
     tab = eng.pack(U)
     ri, rw = O.knn_from_distances(O.hamming(U, U), 31)
     idx, w = sym_knn(eng, tab, 31, boot=512)
     np.testing.assert_array_equal(np_(idx), ri)
     np.testing.assert_array_equal(np_(w), rw)
+
+
+def test_exchange_merge_then_widen_equals_direct_finalize(eng):
+    """The multi-GPU exchange path: per-rank lists -> pg_knn_lists_merge (8-byte keys of a row block)
+    -> pg_knn_lists_finalize(n_lists=1, drop=0), against the direct G-way finalize."""
+    rng = np.random.default_rng(9)
+    n, k = 3000, 16
+    X = mutational(rng, n, 256)
+    tab = eng.pack(X.astype(np.uint8))
+    seed = eng.hamming_knn_boot(tab, 0, n, 512, k + 1)
+    lists = torch.stack([eng.hamming_knn_sym(tab, k + 1, r, 3, lists=seed.clone(), boot_rows=512, mode=1) for r in range(3)])
+    want_i, want_w = eng.knn_lists_finalize(lists, 0, n, k, 1)
+    for sim in (False, True):
+        parts = []
+        for r0, r1 in ((0, 1024), (1024, 2048), (2048, n)):
+            keys = eng.knn_lists_merge(lists[:, r0:r1].contiguous(), k, drop=1)
+            assert keys.shape == (r1 - r0, k)
+            parts.append(keys)
+        keys = torch.cat(parts)
+        gi, gw = eng.knn_lists_finalize(keys, 0, n, k, 0, sim)
+        np.testing.assert_array_equal(np_(gi), np_(want_i))
+        ri, rw = O.knn_from_distances(O.hamming(X, X, similarity=sim), k, descending=sim)
+        np.testing.assert_array_equal(np_(gi), ri)
+        np.testing.assert_array_equal(np_(gw), rw)
+    eng.sym_check()                                                      # no lock was ever given up
 
 
 def test_symmetric_unsupported_shapes_fall_back(eng):

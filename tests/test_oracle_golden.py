@@ -296,5 +296,14 @@ def test_c_restatement_matches_the_numpy_oracle():
         lo, cnt = 7, min(13, n - 7)
         idx, d = CO.hamming_knn(planes, L, lo, cnt, k, threads=2)
         np.testing.assert_array_equal(idx[:, :kk], ri[lo:lo + cnt])
+        # arbitrary query rows (what bench.py's parity block samples) and plain distance rows
+        rows = np.array([n - 1, 0, n // 2, 3, 3], dtype=np.int64)
+        idx, d = CO.hamming_knn_rows(planes, L, rows, k, threads=2)
+        np.testing.assert_array_equal(idx[:, :kk], ri[rows])
+        np.testing.assert_array_equal(d[:, :kk], rw[rows])
+        D = CO.hamming_rows(planes, L, rows, threads=3)
+        np.testing.assert_array_equal(D, O.hamming(X.astype(np.int64), X[rows].astype(np.int64)))
+    with pytest.raises(ValueError):
+        CO.hamming_knn_rows(planes, L, np.array([n]), k)
     with pytest.raises(OverflowError):
         CO.pack(np.full((4, 8), 40, dtype=np.uint8))
