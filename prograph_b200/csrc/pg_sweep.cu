@@ -274,13 +274,6 @@ static size_t eps_list_bytes(long long rows) { return static_cast<size_t>(rows) 
 
 
 // ---- symmetric kNN sweep (pg_sweep_sym.cuh): host side ---------------------------------
-// Paired-lane instantiation: on by default where a half row is at least one 128-bit load
-// (PG_SYM_PAIR=0/1 overrides, for A/B measurements).
-static int sym_pair_default(int words) {
-  if (const char* ev = std::getenv("PG_SYM_PAIR")) return std::atoi(ev) != 0 && words >= 2;
-  return words >= 8 ? 1 : 0;
-}
-
 static int dispatch_sym(int planes, int words, const SymParams& prm, const SymLaunch& l, int* resident) {
 #define PG_CASE(P, W) \
   if (planes == P && words == W) return sweep_sym_p##P##_w##W(prm, l, resident);
@@ -952,7 +945,6 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   prm.stats = want_stats ? stats_dev : nullptr;
   prm.error = reinterpret_cast<unsigned*>(stats_dev + 8);
   SymLaunch l{0, static_cast<size_t>(k1) * kConsumers * 8, cs, SYM_KNN};
-  l.pair = sym_pair_default(words);
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;
@@ -1020,7 +1012,6 @@ int pg_hamming_eps_sym(const uint32_t* table, int64_t rows, int planes, int word
   prm.capacity = capacity;
   prm.counters = reinterpret_cast<unsigned long long*>(counters);
   SymLaunch l{0, 0, cs, SYM_EPS};
-  l.pair = sym_pair_default(words);
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);
   if (rc != PG_OK) return rc;

@@ -26,11 +26,6 @@
 // Bootstrap: the host first sweeps all rows one-sided against the first boot_rows columns
 // (pg_hamming_knn_boot) so that every filter is tight from the first symmetric tile on; the row
 // blocks of those rows ("boot" items) then run row side only, behind the bootstrap columns.
-// Paired lanes (PAIR): lanes 2i and 2i+1 share their two own rows -- each lane keeps ONE HALF of
-// the plane words of both rows in registers (the same P*W registers as before), reads only its half
-// of every stream row (5 instead of 10 LDS.128 at W=8) and finishes its own row's distance with one
-// SHFL of the partner's partial sum.  Per pair: half the shared-memory wavefronts and half the
-// stream registers in flight; LOP3 / POPC counts unchanged.
 // Lock protocol: atom.acquire.gpu CAS by lane 0, __syncwarp, list edited in registers, st.cg of the
 // list and the filter word, __syncwarp, st.release.gpu of the lock by lane 0 (bar.warp.sync orders the
 // other lanes' stores before the cumulative release).  A lock that cannot be taken within 2^24
@@ -231,53 +226,7 @@ static __device__ __noinline__ void sym_emit(const SymParams& prm, bool hit, uns
   n_real += static_cast<unsigned long long>(n);
 }
 
-// Paired lanes: distance of this lane's own row to one stream row.  q holds [0] the lane's half
-// (words h*W/2 .. of every plane) of its OWN row and [1] the same half of its PARTNER lane's row;
-// colh points at that half of the stream row.  The partner computes the other halves; one SHFL
-// exchanges the partial sums of the rows the lanes do not own.
-template <int P, int W>
-__device__ __forceinline__ int ham_pair(const uint32_t (&q)[P * W], const uint32_t* __restrict__ colh, unsigned one) {
-  constexpr int H = W / 2;
-  static_assert(W >= 2 && W % 2 == 0, "paired lanes split a row into two halves");
-  uint32_t m0[H], m1[H];
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    uint32_t v[H];
-    if constexpr (H % 4 == 0) {
-#pragma unroll
-      for (int g = 0; g < H / 4; ++g) {
-        const uint4 t = *reinterpret_cast<const uint4*>(colh + p * W + 4 * g);
-        v[4 * g + 0] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
-      }
-    } else if constexpr (H == 2) {
-      const uint2 t = *reinterpret_cast<const uint2*>(colh + p * W);
-      v[0] = t.x; v[1] = t.y;
-    } else {
-#pragma unroll
-      for (int w = 0; w < H; ++w) v[w] = colh[p * W + w];
-    }
-#pragma unroll
-    for (int w = 0; w < H; ++w) {
-      if (p == 0) {
-        m0[w] = q[w] ^ v[w];
-        m1[w] = q[P * H + w] ^ v[w];
-      } else {
-        m0[w] |= q[p * H + w] ^ v[w];
-        m1[w] |= q[P * H + p * H + w] ^ v[w];
-      }
-    }
-  }
-  unsigned s0 = __popc(m0[0]), s1 = __popc(m1[0]);
-#pragma unroll
-  for (int w = 1; w < H; ++w) {
-    s0 = mad_u32(__popc(m0[w]), one, s0);
-    s1 = mad_u32(__popc(m1[w]), one, s1);
-  }
-  const unsigned other = __shfl_xor_sync(0xffffffffu, s1, 1);
-  return static_cast<int>(mad_u32(other, one, s0));
-}
-
-template <int P, int W, int MODE, bool PAIR = false>
+template <int P, int W, int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __grid_constant__ SymParams prm) {
   constexpr int BN = TileCols<W>::value;
   constexpr int COLW = P * W;
@@ -325,8 +274,6 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
   int stage = 0;
   uint32_t phase = 0;
   const unsigned one = prm.one;
-  // paired lanes: word offset of this lane's half inside a stream row
-  const int hoff = PAIR ? (lane & 1) * (W / 2) : 0;
   // epsilon mode: the warp's current chunk of the edge buffer
   long long ch_base = -1;
   int ch_used = 0;
@@ -339,36 +286,17 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
     const long long r = static_cast<long long>(rb) * kConsumers + tid;
     const bool valid = r < prm.rows;
     uint32_t q[COLW];
-    if constexpr (PAIR) {
-      // [0 .. P*H): this lane's half of its own row; [P*H .. 2*P*H): the same half of the partner's row
-      constexpr int H = W / 2;
-      const long long rp = r ^ 1ll;
-      const bool pvalid = rp < prm.rows;
-      const uint32_t* src = prm.tab + static_cast<size_t>(valid ? r : 0) * COLW + hoff;
-      const uint32_t* psrc = prm.tab + static_cast<size_t>(pvalid ? rp : 0) * COLW + hoff;
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-#pragma unroll
-        for (int w = 0; w < H; ++w) {
-          q[p * H + w] = valid ? __ldg(src + p * W + w) : 0u;
-          q[P * H + p * H + w] = pvalid ? __ldg(psrc + p * W + w) : 0u;
-        }
-      }
-    } else {
+    {
       const uint32_t* src = prm.tab + static_cast<size_t>(valid ? r : 0) * COLW;
 #pragma unroll
       for (int j = 0; j < COLW; ++j) q[j] = valid ? __ldg(src + j) : 0u;
     }
     const uint32_t(&qq)[1][COLW] = reinterpret_cast<const uint32_t(&)[1][COLW]>(q);
-    // distance of the own row to the stream row at `col` (shared memory)
+    // distance of the own row to the stream row at `col` (shared memory, broadcast loads)
     auto dist = [&](const uint32_t* col) -> int {
-      if constexpr (PAIR) {
-        return ham_pair<P, W>(q, col + hoff, one);
-      } else {
-        int d[1];
-        ham_rows<P, W, 1>(qq, col, d, one);
-        return d[0];
-      }
+      int d[1];
+      ham_rows<P, W, 1>(qq, col, d, one);
+      return d[0];
     };
     // kNN: the row's global list already bounds what can still matter: ties at its last distance
     // stay admissible (the index decides), hence the +1
@@ -427,39 +355,44 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
         }
       };
 
+      // filter test + rare path of the four stream rows cg .. cg+3 with distances e0 .. e3
+      auto vote = [&](int cg, int e0, int e1, int e2, int e3) {
+        int any;
+        if constexpr (MODE == SYM_KNN) {
+          // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
+          const int4 na = *reinterpret_cast<const int4*>(tnt + cg);
+          const int4 nb = *reinterpret_cast<const int4*>(tnt + cg + 2);
+          const unsigned cm = cg >= c_mid ? vmask : 0u;
+          // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
+          const int s0 = mad_s32(e0, one, -tau), s1 = mad_s32(e1, one, -tau);
+          const int s2 = mad_s32(e2, one, -tau), s3 = mad_s32(e3, one, -tau);
+          const int u0 = mad_s32(e0, one, na.y), u1 = mad_s32(e1, one, na.w);
+          const int u2 = mad_s32(e2, one, nb.y), u3 = mad_s32(e3, one, nb.w);
+          any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
+        } else {
+          // sign bit set <=> no edge: d - lo < 0 or hi - d < 0; all four miss <=> the AND keeps the sign
+          const int a0 = mad_s32(e0, one, nlo), a1 = mad_s32(e1, one, nlo);
+          const int a2 = mad_s32(e2, one, nlo), a3 = mad_s32(e3, one, nlo);
+          const int b0 = mad_s32(e0, mone, hi), b1 = mad_s32(e1, mone, hi);
+          const int b2 = mad_s32(e2, mone, hi), b3 = mad_s32(e3, mone, hi);
+          any = ~((a0 | b0) & (a1 | b1) & (a2 | b2) & (a3 | b3));
+        }
+        if (__any_sync(0xffffffffu, any < 0)) {
+          const bool col_on = cg >= c_mid;
+          rare(e0, cg + 0, col_on);
+          rare(e1, cg + 1, col_on);
+          rare(e2, cg + 2, col_on);
+          rare(e3, cg + 3, col_on);
+        }
+      };
+
 #pragma unroll 1
       for (; c + 4 <= ncols; c += 4) {
         const int d0 = dist(tile + (c + 0) * COLW);
         const int d1 = dist(tile + (c + 1) * COLW);
         const int d2 = dist(tile + (c + 2) * COLW);
         const int d3 = dist(tile + (c + 3) * COLW);
-        int any;
-        if constexpr (MODE == SYM_KNN) {
-          // filter words of the four stream rows: .y / .w = ~tau_j, .x / .z = index of the last key
-          const int4 na = *reinterpret_cast<const int4*>(tnt + c);
-          const int4 nb = *reinterpret_cast<const int4*>(tnt + c + 2);
-          const unsigned cm = c >= c_mid ? vmask : 0u;
-          // sign bit set <=> candidate: d - tau < 0 (row side), d + ~tau_j < 0 i.e. d <= tau_j (column side)
-          const int s0 = mad_s32(d0, one, -tau), s1 = mad_s32(d1, one, -tau);
-          const int s2 = mad_s32(d2, one, -tau), s3 = mad_s32(d3, one, -tau);
-          const int u0 = mad_s32(d0, one, na.y), u1 = mad_s32(d1, one, na.w);
-          const int u2 = mad_s32(d2, one, nb.y), u3 = mad_s32(d3, one, nb.w);
-          any = (s0 | s1 | s2) | s3 | static_cast<int>(static_cast<unsigned>((u0 | u1 | u2) | u3) & cm);
-        } else {
-          // sign bit set <=> no edge: d - lo < 0 or hi - d < 0; all four miss <=> the AND keeps the sign
-          const int a0 = mad_s32(d0, one, nlo), a1 = mad_s32(d1, one, nlo);
-          const int a2 = mad_s32(d2, one, nlo), a3 = mad_s32(d3, one, nlo);
-          const int b0 = mad_s32(d0, mone, hi), b1 = mad_s32(d1, mone, hi);
-          const int b2 = mad_s32(d2, mone, hi), b3 = mad_s32(d3, mone, hi);
-          any = ~((a0 | b0) & (a1 | b1) & (a2 | b2) & (a3 | b3));
-        }
-        if (__any_sync(0xffffffffu, any < 0)) {
-          const bool col_on = c >= c_mid;
-          rare(d0, c + 0, col_on);
-          rare(d1, c + 1, col_on);
-          rare(d2, c + 2, col_on);
-          rare(d3, c + 3, col_on);
-        }
+        vote(c, d0, d1, d2, d3);
       }
 #pragma unroll 1
       for (; c < ncols; ++c) {   // ragged end of the table (last tile only)
@@ -506,14 +439,13 @@ struct SymLaunch {
   size_t list_bytes;
   cudaStream_t stream;
   int mode = SYM_KNN;
-  int pair = 0;       // paired-lane instantiation (words >= 2)
 };
 
 
 // grid == 0: only report the resident grid (CTAs) through *resident
-template <int P, int W, int MODE, bool PAIR>
+template <int P, int W, int MODE>
 int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* resident) {
-  auto kern = sweep_sym_kernel<P, W, MODE, PAIR>;
+  auto kern = sweep_sym_kernel<P, W, MODE>;
   const size_t smem = static_cast<size_t>(kStages) * (TileCols<W>::value * P * W * 4 +
                                                       (MODE == SYM_KNN ? TileCols<W>::value * 8 : 0)) +
                       2 * kStages * sizeof(uint64_t) + l.list_bytes;
@@ -530,14 +462,8 @@ int launch_sweep_sym_mode(const SymParams& prm, const SymLaunch& l, int* residen
 
 template <int P, int W>
 int launch_sweep_sym(const SymParams& prm, const SymLaunch& l, int* resident) {
-  if constexpr (W >= 2) {
-    if (l.pair) {
-      if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS, true>(prm, l, resident);
-      return launch_sweep_sym_mode<P, W, SYM_KNN, true>(prm, l, resident);
-    }
-  }
-  if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS, false>(prm, l, resident);
-  return launch_sweep_sym_mode<P, W, SYM_KNN, false>(prm, l, resident);
+  if (l.mode == SYM_EPS) return launch_sweep_sym_mode<P, W, SYM_EPS>(prm, l, resident);
+  return launch_sweep_sym_mode<P, W, SYM_KNN>(prm, l, resident);
 }
 
 #define PG_DECL_SWEEP_SYM(P, W) int sweep_sym_p##P##_w##W(const SymParams& prm, const SymLaunch& l, int* resident);

@@ -134,14 +134,14 @@ def test_symmetric_knn_degenerate_tables(eng):
     np.testing.assert_array_equal(eps.idx[:20000], odd[:20000])  # row 0: all odd rows, ascending
 
 
-@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("band_mb", ["0", "0.25", "24"])
 @pytest.mark.parametrize("L", [40, 100, 256, 300])
-def test_symmetric_sweeps_paired_and_plain_lanes(eng, monkeypatch, pair, L):
-    """Both instantiations of the symmetric sweeps (PG_SYM_PAIR: lanes 2i / 2i+1 share their two own
-    rows, each holding one half of the plane words, vs. one whole row per lane) give the oracle's kNN
-    lists and epsilon graph, whatever the arrival order; odd row counts leave a lane without partner."""
+def test_symmetric_sweeps_under_every_schedule(eng, monkeypatch, band_mb, L):
+    """The work-item schedule of the symmetric sweeps (PG_SYM_BAND_MB: width of the L2 column bands the
+    per-CTA item lists are ordered by; 0 = one band, 0.25 = many narrow bands even on these small
+    tables) never changes the kNN lists or the epsilon graph: any arrival order gives the oracle's."""
     from prograph_b200.graph import distance_lut
-    monkeypatch.setenv("PG_SYM_PAIR", pair)
+    monkeypatch.setenv("PG_SYM_BAND_MB", band_mb)
     rng = np.random.default_rng(77 + L)
     for n in (513, 3001):
         X = mutational(rng, n, L)

@@ -1,8 +1,10 @@
 #!/usr/bin/env python3
-"""A/B timing of the symmetric sweeps' build-time knobs in ONE process (the library reads its
-environment at every call): paired lanes on/off, L2 band size, bootstrap columns, emulated ranks.
+"""A/B timing of the symmetric sweeps' schedule knobs in ONE process (the library reads its
+environment at every call): L2 band size, bootstrap columns, emulated ranks.  (--pair / --delay
+selected the paired-lane and delayed-vote instantiations measured in profiles/r2_notes.md; both lost
+and were removed, the flags are accepted and ignored.)
 
-    python tools/sym_variants.py --n 1000000 --pair 0,1 --band 0,24,40 [--eps 1] [--world 8 --rank 0]
+    python tools/sym_variants.py --n 1000000 --band 0,24,40 [--eps 1] [--world 8 --rank 0]
 """
 import argparse
 import itertools
@@ -23,6 +25,7 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--dist", default="uniform")
     ap.add_argument("--pair", default="0,1")
+    ap.add_argument("--delay", default="0")
     ap.add_argument("--band", default="0,24")
     ap.add_argument("--boot", default="8192")
     ap.add_argument("--eps", type=int, default=0)
@@ -41,8 +44,10 @@ def main():
     lut = graph.distance_lut(tab.words * 32, operator.le, args.eps, False) if args.eps else None
     if args.stats:
         os.environ["PG_SYM_STATS"] = "1"
-    for pair, band, boot in itertools.product(args.pair.split(","), args.band.split(","), args.boot.split(",")):
+    for pair, delay, band, boot in itertools.product(args.pair.split(","), args.delay.split(","), args.band.split(","),
+                                                     args.boot.split(",")):
         os.environ["PG_SYM_PAIR"], os.environ["PG_SYM_BAND_MB"], os.environ["PG_SYM_BOOT"] = pair, band, boot
+        os.environ["PG_SYM_DELAY"] = delay
         best = None
         for _ in range(args.reps):
             eng.time_sweeps(True)
@@ -69,7 +74,7 @@ def main():
             if best is None or ms < best[0]:
                 best = (ms, sw)
         print(json.dumps({"n": n, "dist": args.dist, "eps": args.eps, "world": args.world, "rank": args.rank, "pair": pair,
-                          "band_mb": band, "boot": boot, "build_ms": round(best[0], 2),
+                          "delay": delay, "band_mb": band, "boot": boot, "build_ms": round(best[0], 2),
                           "sweeps_ms": [round(v, 2) for v in best[1]],
                           "gpairs_n2": round(n * n / best[0] / 1e6, 1)}), flush=True)
 
