@@ -468,7 +468,7 @@ def run_b200(args):
         tri_pairs = triangle_pairs(n, boot, band)
         kernel_ms = sum(sweep_list[1::2]) / args.steps
         boot_ms = sum(sweep_list[0::2]) / args.steps
-        pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8,KNN,paired lanes>"
+        pairs_per_launch, kernel_name = tri_pairs, "pg::sweep_sym_kernel<5,8,KNN>"
         capture = "r2_ncu_sym_1m_dram.csv"
     else:
         boot_pairs, boot_ms = 0.0, 0.0
