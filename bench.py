@@ -67,12 +67,15 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_tokens(n, L, kind):
-    """U = iid uniform residues (adversarial ties), M = mutational library."""
+def make_tokens(n, L, kind, seed=0):
+    """U = iid uniform residues (adversarial ties), M = mutational library.
+    `seed` != 0 draws another set of rows around the SAME wild type (the query set of C5)."""
     rng = np.random.default_rng(0)
     if kind == "uniform":
-        return rng.integers(1, 21, size=(n, L), dtype=np.uint8)
+        return np.random.default_rng(seed).integers(1, 21, size=(n, L), dtype=np.uint8)
     wt = rng.integers(1, 21, size=L, dtype=np.uint8)
+    if seed != 0:
+        rng = np.random.default_rng(seed)
     X = np.tile(wt, (n, 1))
     m = rng.integers(1, 9, size=n)
     for j in range(8):

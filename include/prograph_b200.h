@@ -50,7 +50,8 @@ typedef enum { PG_LT = 0, PG_LE = 1, PG_EQ = 2, PG_NE = 3, PG_GE = 4, PG_GT = 5 
 typedef enum {
   PG_W_I64 = 0,   /* d as int64                      (hamming.py:34)                */
   PG_W_SIM_F32 = 1,/* 1/(1+d) as float32             (hamming.py:37-38)             */
-  PG_W_I32 = 2    /* d as int32 (library-internal tiles)                            */
+  PG_W_I32 = 2,   /* d as int32 (library-internal tiles)                            */
+  PG_W_FLAG_U8 = 3/* lo <= d <= hi as one byte 0/1 (pg_hamming_flags_tile only)      */
 } pgWeight;
 
 int         pg_version(void);
@@ -106,6 +107,17 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
                    int planes, int words, int k, int drop, int weight,
                    int64_t* out_idx, void* out_w,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* (qrows, N) membership flags of query rows [q0,q0+qrows) against all data rows:
+ * out[(q-q0)*ld + n] = 1 if d_lo <= d(q, n) <= d_hi else 0 (uint8).  One fused sweep answers a whole
+ * batch of neighbourhood queries (prograph.py:571-588 `hamming(...) <= eps`, and the batched frontier
+ * of neighbourhood_clustering, prograph.py:590-615) without materialising distances.  q0 % 512 == 0.  */
+int pg_hamming_flags_tile(const uint32_t* data, int64_t data_rows, const uint32_t* queries,
+                          int64_t query_rows, int64_t q0, int64_t qrows, int planes, int words,
+                          int d_lo, int d_hi, uint8_t* out, int64_t ld, void* stream);
+/* covered[n] |= OR over the rows r with accept_host[r] != 0 of flags[r*ld + n]  (uint8 0/1 arrays) */
+int pg_flags_or_rows(const uint8_t* flags, int64_t rows, int64_t N, int64_t ld,
+                     const uint8_t* accept_host, uint8_t* covered, void* stream);
 
 /* Symmetric kNN of a table against itself (the case build_graph runs, prograph.py:755-765):
  * d(i,j) == d(j,i), so every unordered pair is evaluated once and offered to the lists of both

@@ -15,7 +15,8 @@ from .protein import Protein  # noqa: E402
 from .prograph import Prograph  # noqa: E402
 from .graph import build_neighbours, NeighbourTable, KnnTable  # noqa: E402
 from .io import save  # noqa: E402
+from . import query  # noqa: E402,F401  (distance-to-dataset queries fused with their consumers)
 
 __all__ = ["Prograph", "Protein", "hamming", "minkowski", "clean_input", "build_neighbours",
-           "NeighbourTable", "KnnTable", "save"]
+           "NeighbourTable", "KnnTable", "save", "query"]
 __version__ = "0.1.0"

@@ -17,7 +17,7 @@ U8, I16, I32, I64, F16, F32, F64 = range(7)
 # pgCmp
 LT, LE, EQ, NE, GE, GT = range(6)
 # pgWeight
-W_I64, W_SIM_F32, W_I32 = range(3)
+W_I64, W_SIM_F32, W_I32, W_FLAG_U8 = range(4)
 
 
 class Unsupported(RuntimeError):
@@ -55,6 +55,8 @@ SIGNATURES = {
     "pg_hamming_eps_count": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pg_hamming_eps_fill": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "pg_hamming_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i64, _vp]),
+    "pg_hamming_flags_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "pg_flags_or_rows": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pg_exclusive_scan_i64": (_i, [_vp, _i64, _vp, _vp]),
     "pg_minkowski_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _dbl, _i, _vp, _i64, _vp]),
     "pg_hamming_values_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i64, _vp]),

@@ -95,32 +95,114 @@ __global__ void pack_kernel(const T* __restrict__ tokens, long long N, int L, lo
   }
 }
 
-// ---- fused tokeniser + pack: raw residue letters -> bit planes ------------------------------
-// Replaces tokenize (prograph.py:454-474: twenty np.where passes producing an (N, L) int64
-// array) followed by the fp16 staging: one pass over the sequence bytes through a 256-entry
-// letter -> token table, ballots build the plane words.  Byte 0 (numpy's pad of shorter
-// strings) and letters outside the alphabet map to token 0, as in the reference.
+// ---- byte tokens (and raw residue letters) -> bit planes, vectorised ---------------------------
+// One thread per (row, word): it loads its 32 one-byte tokens with two 128-bit loads (32-bit or byte
+// loads when the row pitch does not allow it), optionally maps letters to tokens through a 256-byte
+// table in shared memory (fused tokeniser, prograph.py:454-474: twenty np.where passes producing an
+// (N, L) int64 array; byte 0 -- numpy's pad of shorter strings -- and letters outside the alphabet
+// map to token 0, as in the reference), and gathers bit p of the four tokens of a 32-bit register
+// with one multiply:  ((x & 0x01010101 << p) * (0x01020408 << 4-p)) >> 28  leaves the four bits in the
+// top nibble, a funnel shift appends it to the plane word.  3 instructions per 4 tokens and plane
+// instead of a byte load and a ballot per token and plane; consecutive threads read consecutive
+// 32-byte pieces of a row and write consecutive words of a plane.  HBM-bound: reads L bytes and
+// writes planes * words * 4 bytes per row.
 struct CharLut { uint8_t t[256]; };
 
-__global__ void pack_chars_kernel(const uint8_t* __restrict__ chars, long long N, int L, long long ld, CharLut lut,
-                                  uint32_t* __restrict__ packed, long long rows_padded, int planes, int words) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  for (long long row = warp0; row < rows_padded; row += nwarps) {
-    uint32_t* dst = packed + static_cast<size_t>(row) * planes * words;
-    for (int w = 0; w < words; ++w) {
-      const int l = w * 32 + lane;
-      unsigned tok = 0;
-      if (row < N && l < L) tok = lut.t[chars[static_cast<size_t>(row) * ld + l]];
-      uint32_t mine = 0;
-      for (int p = 0; p < planes; ++p) {
-        const uint32_t word = __ballot_sync(0xffffffffu, (tok >> p) & 1u);
-        if (lane == p) mine = word;
-      }
-      if (lane < planes) dst[lane * words + w] = mine;
+template <int PLANES>
+__device__ __forceinline__ void planes_of_32_tokens(const uint32_t (&x)[8], uint32_t (&out)[PLANES]) {
+#pragma unroll
+  for (int p = 0; p < PLANES; ++p) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      // tokens 4i .. 4i+3: bit p of every byte -> top nibble of the product
+      const uint32_t y = p < 4 ? (x[i] & (0x01010101u << p)) : ((x[i] >> 4) & (0x01010101u << (p - 4)));
+      const uint32_t prod = y * (0x01020408u << (4 - (p < 4 ? p : p - 4)));
+      word = __funnelshift_l(prod, word, 4);        // word = word << 4 | prod >> 28
     }
+    out[p] = word;
   }
+}
+
+template <int PLANES, bool CHARS>
+__global__ void __launch_bounds__(256) pack_bytes_kernel(const uint8_t* __restrict__ src, long long N, int L, long long ld,
+                                                         CharLut lut, uint32_t* __restrict__ packed, long long rows_padded,
+                                                         int words, int* __restrict__ flag) {
+  __shared__ uint8_t lut_s[256];
+  if (CHARS) {
+    if (threadIdx.x < 256) lut_s[threadIdx.x] = lut.t[threadIdx.x];
+    __syncthreads();
+  }
+  const long long total = rows_padded * words;
+  const bool vec16 = (ld % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+  const bool vec4 = (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0);
+  bool bad = false;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / words;
+    const int w = static_cast<int>(i - row * words);
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 0u;
+    const int have = row < N ? min(32, L - w * 32) : 0;      // tokens of this word that exist
+    if (have > 0) {
+      const uint8_t* at = src + static_cast<size_t>(row) * ld + w * 32;
+      if (have == 32 && vec16) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(at));
+        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(at) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+        x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int left = have - 4 * k;
+          if (left >= 4 && vec4) {
+            x[k] = __ldcs(reinterpret_cast<const uint32_t*>(at) + k);
+          } else if (left > 0) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4 && b < left; ++b) v |= static_cast<uint32_t>(at[4 * k + b]) << (8 * b);
+            x[k] = v;
+          }
+        }
+      }
+      if (CHARS) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t v = x[k];
+          x[k] = static_cast<uint32_t>(lut_s[v & 0xffu]) | (static_cast<uint32_t>(lut_s[(v >> 8) & 0xffu]) << 8) |
+                 (static_cast<uint32_t>(lut_s[(v >> 16) & 0xffu]) << 16) | (static_cast<uint32_t>(lut_s[v >> 24]) << 24);
+        }
+        // bytes past the end of a short last word were loaded as 0 and must stay 0 whatever lut[0] is
+        if (have < 32) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int left = have - 4 * k;
+            if (left <= 0) x[k] = 0u;
+            else if (left < 4) x[k] &= (1u << (8 * left)) - 1u;
+          }
+        }
+      } else if (PLANES < 8) {
+        const uint32_t over = ~(((1u << PLANES) - 1u) * 0x01010101u);
+        const uint32_t any = (x[0] | x[1] | x[2]) | (x[3] | x[4] | x[5]) | (x[6] | x[7]);
+        if (any & over) {           // a token does not fit the planes: flag it and pack it as 0
+          bad = true;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t keep = 0;
+            for (int b = 0; b < 4; ++b)
+              if ((((x[k] >> (8 * b)) & 0xffu) >> PLANES) == 0u) keep |= 0xffu << (8 * b);
+            x[k] &= keep;
+          }
+        }
+      }
+    }
+    uint32_t out[PLANES];
+    planes_of_32_tokens<PLANES>(x, out);
+    uint32_t* dst = packed + static_cast<size_t>(row) * PLANES * words + w;
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) dst[p * words] = out[p];
+  }
+  if (bad && flag != nullptr) atomicExch(flag, 1);
 }
 
 // ---- integer pipe peak probe ------------------------------------------------------------
@@ -229,6 +311,20 @@ int pg_pack_tokens(const void* tokens, int dtype, int64_t N, int L, int64_t ld, 
   const long long cap = static_cast<long long>(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == PG_U8 && (planes == 5 || planes == 8)) {
+    // the format tokens have on the device: vectorised kernel, one thread per (row, word)
+    long long vb = ceil_div(rows_padded * words, threads);
+    if (vb > cap) vb = cap;
+    const CharLut none = {};
+    if (planes == 5)
+      pack_bytes_kernel<5, false><<<static_cast<unsigned>(vb), threads, 0, s>>>(
+          static_cast<const uint8_t*>(tokens), N, L, ld, none, packed, rows_padded, words, flag);
+    else
+      pack_bytes_kernel<8, false><<<static_cast<unsigned>(vb), threads, 0, s>>>(
+          static_cast<const uint8_t*>(tokens), N, L, ld, none, packed, rows_padded, words, flag);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+  }
 #define PG_PACK(T)                                                                                         \
   pack_kernel<T><<<static_cast<unsigned>(blocks), threads, 0, s>>>(static_cast<const T*>(tokens), N, L, ld, packed, \
                                                                     rows_padded, planes, words, flag)
@@ -251,7 +347,7 @@ int pg_pack_chars(const uint8_t* chars, int64_t N, int L, int64_t ld, const uint
                   int planes, int words, void* stream) {
   PG_CHECK_ARG(chars && lut256_host && packed, "null pointer");
   PG_CHECK_ARG(N > 0 && L > 0 && ld >= L, "bad shape N=%lld L=%d ld=%lld", (long long)N, L, (long long)ld);
-  PG_CHECK_ARG(planes >= 1 && planes <= 8 && words * 32 >= L, "bad planes / words");
+  PG_CHECK_ARG((planes == 5 || planes == 8) && words * 32 >= L, "bad planes / words");
   CharLut lut;
   for (int i = 0; i < 256; ++i) {
     PG_CHECK_ARG(lut256_host[i] < (1u << planes), "token %d of letter %d does not fit %d planes", lut256_host[i], i, planes);
@@ -259,11 +355,20 @@ int pg_pack_chars(const uint8_t* chars, int64_t N, int L, int64_t ld, const uint
   }
   const long long rows_padded = pg_packed_rows(N);
   const int threads = 256;
-  long long blocks = ceil_div(rows_padded * 32, threads);
+  long long blocks = ceil_div(rows_padded * words, threads);
   const long long cap = static_cast<long long>(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
-  pack_chars_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      chars, N, L, ld, lut, packed, rows_padded, planes, words);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (planes == 5)
+    pack_bytes_kernel<5, true><<<static_cast<unsigned>(blocks), threads, 0, s>>>(chars, N, L, ld, lut, packed, rows_padded,
+                                                                                words, nullptr);
+  else if (planes == 8)
+    pack_bytes_kernel<8, true><<<static_cast<unsigned>(blocks), threads, 0, s>>>(chars, N, L, ld, lut, packed, rows_padded,
+                                                                                words, nullptr);
+  else {
+    set_error("pg_pack_chars supports 5 or 8 planes, got %d", planes);
+    return PG_ERR_UNSUPPORTED;
+  }
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -14,6 +14,7 @@ namespace pg {
 constexpr int kMaxMaskWords = 64;  // sequences up to 2048 residues for the selection kernels
 
 struct WordVec { uint32_t w[kMaxMaskWords]; };
+struct LutVec { uint32_t w[kMaxMaskWords + 1]; };     // truth table over d = 0 .. 32*words: one word more
 
 __global__ void mutant_bits_kernel(const uint32_t* __restrict__ table, long long N, int planes, int words,
                                    const uint32_t* __restrict__ ref, uint32_t* __restrict__ mut) {
@@ -29,19 +30,33 @@ __global__ void mutant_bits_kernel(const uint32_t* __restrict__ table, long long
   }
 }
 
-__global__ void mutant_bool_kernel(const uint32_t* __restrict__ table, long long N, int planes, int words, int L,
-                                   const uint32_t* __restrict__ ref, uint8_t* __restrict__ out) {
-  // one thread per (row, residue): byte stores are coalesced along the residue index
-  const long long total = N * L;
+// One thread per (row, word): the 32 mask bits become 32 bytes; a nibble expands to four 0/1 bytes
+// with one multiply ((n * 0x00204081) & 0x01010101), rows whose pitch allows it are written with two
+// 128-bit stores.  HBM-bound: reads planes * words * 4 bytes, writes L bytes per row.
+__global__ void __launch_bounds__(256) mutant_bool_kernel(const uint32_t* __restrict__ table, long long N, int planes,
+                                                          int words, int L, const uint32_t* __restrict__ ref,
+                                                          uint8_t* __restrict__ out) {
+  const long long total = N * words;
+  const bool vec16 = (L % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / L;
-    const int l = static_cast<int>(i - n * L);
-    const int w = l >> 5, b = l & 31;
-    const uint32_t* row = table + static_cast<size_t>(n) * planes * words;
+    const long long n = i / words;
+    const int w = static_cast<int>(i - n * words);
+    const int have = min(32, L - w * 32);
+    if (have <= 0) continue;
+    const uint32_t* row = table + static_cast<size_t>(n) * planes * words + w;
     uint32_t m = 0;
-    for (int p = 0; p < planes; ++p) m |= row[p * words + w] ^ __ldg(ref + p * words + w);
-    out[i] = (m >> b) & 1u;
+    for (int p = 0; p < planes; ++p) m |= __ldcs(row + p * words) ^ __ldg(ref + p * words + w);
+    uint32_t b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = (((m >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
+    uint8_t* dst = out + static_cast<size_t>(n) * L + w * 32;
+    if (have == 32 && vec16) {
+      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(b[0], b[1], b[2], b[3]));
+      __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(b[4], b[5], b[6], b[7]));
+    } else {
+      for (int l = 0; l < have; ++l) dst[l] = static_cast<uint8_t>((b[l >> 2] >> (8 * (l & 3))) & 1u);
+    }
   }
 }
 
@@ -58,7 +73,7 @@ __global__ void mutant_any_kernel(const uint32_t* __restrict__ mut, long long N,
   }
 }
 
-__global__ void select_rows_kernel(const uint32_t* __restrict__ mut, long long N, int words, WordVec dist_lut,
+__global__ void select_rows_kernel(const uint32_t* __restrict__ mut, long long N, int words, LutVec dist_lut,
                                    int use_lut, WordVec inside, WordVec outside, int pos_mode,
                                    uint8_t* __restrict__ flag) {
   for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < N;
@@ -98,6 +113,19 @@ __global__ void distance_hist_kernel(const uint32_t* __restrict__ mut, long long
     if (sh[i]) atomicAdd(reinterpret_cast<unsigned long long*>(hist + i), static_cast<unsigned long long>(sh[i]));
 }
 
+struct AcceptVec { uint8_t a[1024]; };
+
+__global__ void flags_or_rows_kernel(const uint8_t* __restrict__ flags, int rows, long long N, long long ld, AcceptVec acc,
+                                     uint8_t* __restrict__ covered) {
+  for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < N;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint8_t c = covered[n];
+    for (int r = 0; r < rows; ++r)
+      if (acc.a[r]) c |= flags[static_cast<size_t>(r) * ld + n];
+    covered[n] = c;
+  }
+}
+
 static unsigned grid_for(long long work, int threads) {
   long long b = ceil_div(work, threads);
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -124,8 +152,21 @@ int pg_mutant_bits(const uint32_t* table, int64_t N, int planes, int words, cons
 int pg_mutant_bool(const uint32_t* table, int64_t N, int planes, int words, int L, const uint32_t* ref, uint8_t* out,
                    void* stream) {
   PG_CHECK_ARG(table && ref && out && N > 0 && planes > 0 && words > 0 && L > 0 && L <= words * 32, "bad arguments");
-  mutant_bool_kernel<<<grid_for(N * L, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes, words, L,
-                                                                                         ref, out);
+  mutant_bool_kernel<<<grid_for(N * words, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes, words,
+                                                                                             L, ref, out);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_flags_or_rows(const uint8_t* flags, int64_t rows, int64_t N, int64_t ld, const uint8_t* accept_host,
+                     uint8_t* covered, void* stream) {
+  PG_CHECK_ARG(flags && accept_host && covered && N > 0 && ld >= N, "bad arguments");
+  PG_CHECK_ARG(rows >= 1 && rows <= 1024, "at most 1024 flag rows per call");
+  AcceptVec acc;
+  memset(&acc, 0, sizeof(acc));
+  memcpy(acc.a, accept_host, static_cast<size_t>(rows));
+  flags_or_rows_kernel<<<grid_for(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(flags, static_cast<int>(rows), N, ld,
+                                                                                        acc, covered);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -146,10 +187,11 @@ int pg_select_rows(const uint32_t* mut, int64_t N, int words, const uint32_t* di
   PG_CHECK_ARG(words > 0 && words <= kMaxMaskWords, "selection kernels support up to %d words", kMaxMaskWords);
   PG_CHECK_ARG(pos_mode >= 0 && pos_mode <= 3, "bad pos_mode %d", pos_mode);
   PG_CHECK_ARG(pos_mode == 0 || inside_host, "positions mask missing");
-  PG_CHECK_ARG(!dist_lut_host || (lut_words >= 1 && lut_words <= kMaxMaskWords && lut_words * 32 > words * 32),
+  PG_CHECK_ARG(!dist_lut_host || (lut_words >= 1 && lut_words <= kMaxMaskWords + 1 && lut_words * 32 > words * 32),
                "distance lut must cover 0..%d", words * 32);
   PG_CHECK_ARG(!(pos_mode == 1 || pos_mode == 2) || outside_host, "unchanged-positions mask missing");
-  WordVec lut, inside, outside;
+  LutVec lut;
+  WordVec inside, outside;
   memset(&lut, 0, sizeof(lut));
   memset(&inside, 0, sizeof(inside));
   memset(&outside, 0, sizeof(outside));

@@ -823,6 +823,29 @@ int pg_hamming_tile(const uint32_t* data, int64_t data_rows, const uint32_t* que
   return dispatch(planes, words, prm, l);
 }
 
+int pg_hamming_flags_tile(const uint32_t* data, int64_t data_rows, const uint32_t* queries, int64_t query_rows, int64_t q0,
+                          int64_t qrows, int planes, int words, int d_lo, int d_hi, uint8_t* out, int64_t ld,
+                          void* stream) {
+  PG_CHECK_ARG(q0 >= 0 && qrows > 0 && q0 + qrows <= query_rows, "query range outside table");
+  PG_CHECK_ARG(q0 % kStreamRowPad == 0, "q0 must be a multiple of %d", kStreamRowPad);
+  int rc = check_common(data, data_rows, 0, data_rows, queries, qrows, planes, words);
+  if (rc != PG_OK) return rc;
+  PG_CHECK_ARG(out && ld >= data_rows, "bad output / leading dimension");
+  Geometry g = make_geometry(data_rows, qrows, words, kConsumers, 0);
+  g.n_splits = 1;
+  g.tiles_per_split = g.n_tiles;
+  SweepParams prm;
+  fill_common(prm, g, data, 0, data_rows, queries + static_cast<size_t>(q0) * planes * words, qrows);
+  prm.out = out;
+  prm.ld = ld;
+  prm.lo = d_lo;
+  prm.span = d_hi >= d_lo ? static_cast<unsigned>(d_hi - d_lo) : 0u;
+  if (d_hi < d_lo) prm.lo = 0x7fffffff;               // empty range: nothing passes
+  SweepLaunch l{MODE_TILE, 0, PG_W_FLAG_U8, 0, 0, static_cast<cudaStream_t>(stream)};
+  SweepTimer t(l.stream);
+  return dispatch(planes, words, prm, l);
+}
+
 size_t pg_knn_sym_workspace_bytes(int64_t rows, int words) {
   if (rows <= 0 || words <= 0) return 0;
   return sym_layout(rows, words).total;

@@ -147,6 +147,13 @@ __device__ __forceinline__ void write_weight(void* out_w, long long at, int d, i
   else reinterpret_cast<int*>(out_w)[at] = d;
 }
 
+// tile epilogue: the distance (or the range flag lo <= d <= lo + span) of one (stream, own) pair
+template <int WEIGHT>
+__device__ __forceinline__ void write_tile(void* out, long long at, int d, int lo, unsigned span) {
+  if constexpr (WEIGHT == PG_W_FLAG_U8) reinterpret_cast<uint8_t*>(out)[at] = static_cast<unsigned>(d - lo) <= span ? 1 : 0;
+  else write_weight(out, at, d, WEIGHT);
+}
+
 constexpr int kMaxListRounds = 3;  // sorted lists of up to 96 entries, one entry per lane and round
 
 // Warp-cooperative sorted insertion: the whole warp inserts `key` into the ascending list of
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
               ++cnt[i];
             }
           } else {  // MODE_TILE: out[stream * ld + own]
-            if (valid[i]) write_weight(prm.out, (col0 + c) * prm.ld + r[i], d[i], WEIGHT);
+            if (valid[i]) write_tile<WEIGHT>(prm.out, (col0 + c) * prm.ld + r[i], d[i], lo, span);
           }
         }
       }
@@ -448,6 +455,7 @@ int launch_sweep(const SweepParams& prm, const SweepLaunch& l) {
     case MODE_TILE:
       if (l.weight == PG_W_I64) return launch_one<P, W, 1, MODE_TILE, false, PG_W_I64>(prm, l);
       if (l.weight == PG_W_SIM_F32) return launch_one<P, W, 1, MODE_TILE, false, PG_W_SIM_F32>(prm, l);
+      if (l.weight == PG_W_FLAG_U8) return launch_one<P, W, 1, MODE_TILE, false, PG_W_FLAG_U8>(prm, l);
       return launch_one<P, W, 1, MODE_TILE, false, PG_W_I32>(prm, l);
   }
   set_error("bad sweep mode %d", l.mode);

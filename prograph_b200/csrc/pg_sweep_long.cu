@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_long_kernel(const __gr
         for (int j = 0; j < LBN; ++j) {
           const int d = acc[j];
           if constexpr (MODE == MODE_TILE) {
-            if (valid && j < ncols) write_weight(prm.out, (col0 + j) * prm.ld + r, d, WEIGHT);
+            if (valid && j < ncols) write_tile<WEIGHT>(prm.out, (col0 + j) * prm.ld + r, d, prm.lo, prm.span);
           } else {
             bool hit;
             if constexpr (LUT) hit = d < kMaxLutWords * 32 && ((lut_s[d >> 5] >> (d & 31)) & 1u);
@@ -258,6 +258,7 @@ int sweep_long_p5(const SweepParams& prm, const SweepLaunch& l, int words) {
     case MODE_TILE:
       if (l.weight == PG_W_I64) return launch_long_one<P, MODE_TILE, false, PG_W_I64>(prm, l, words);
       if (l.weight == PG_W_SIM_F32) return launch_long_one<P, MODE_TILE, false, PG_W_SIM_F32>(prm, l, words);
+      if (l.weight == PG_W_FLAG_U8) return launch_long_one<P, MODE_TILE, false, PG_W_FLAG_U8>(prm, l, words);
       return launch_long_one<P, MODE_TILE, false, PG_W_I32>(prm, l, words);
   }
   set_error("bad sweep mode %d", l.mode);

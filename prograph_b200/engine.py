@@ -318,6 +318,35 @@ class CudaEngine:
                                          self._stream()))
         return out
 
+    def hamming_flags(self, data, queries, qrows, d_lo, d_hi):
+        """(qrows, N) uint8 flags d_lo <= d(query, row) <= d_hi of the first `qrows` rows of the packed
+        `queries` table against every row of `data` (pg_hamming_flags_tile): a batch of neighbourhood
+        queries (prograph.py:571-588) in one fused sweep."""
+        self._check_pair(data, queries)
+        out = self.empty((qrows, data.rows), torch.uint8)
+        L.check(self.lib.pg_hamming_flags_tile(_ptr(data.data), data.rows, _ptr(queries.data), queries.rows, 0, int(qrows),
+                                               data.planes, data.words, int(d_lo), int(d_hi), _ptr(out), data.rows,
+                                               self._stream()))
+        return out
+
+    def gather_packed(self, table, rows):
+        """The packed rows `rows` (host index array) of `table` as a small PackedTable of its own."""
+        idx = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=self.device)
+        pad = int(self.lib.pg_packed_rows(len(rows)))
+        data = torch.zeros((pad, table.planes, table.words), dtype=torch.int32, device=self.device)
+        data[: len(rows)] = table.data[idx]
+        return PackedTable(data, len(rows), table.L, table.planes, table.words)
+
+    def flags_or_rows(self, flags, accept, covered):
+        """covered |= OR of the rows of `flags` selected by the host mask `accept` (pg_flags_or_rows)."""
+        acc = np.ascontiguousarray(accept, dtype=np.uint8)
+        rows, n = flags.shape
+        for r0 in range(0, rows, 1024):
+            part = acc[r0:r0 + 1024]
+            L.check(self.lib.pg_flags_or_rows(_ptr(flags[r0:]), len(part), n, int(flags.stride(0)),
+                                              part.ctypes.data_as(C.c_void_p), _ptr(covered), self._stream()))
+        return covered
+
     def check_edge_budget(self, nnz):
         """An epsilon graph can be dense (the reference would run out of host memory the same way):
         refuse before allocating instead of taking the GPU down."""
@@ -431,6 +460,14 @@ class CudaEngine:
         L.check(self.lib.pg_tile_topk(_ptr(tile), _PG_DTYPE[tile.dtype], rows, N, int(tile.stride(0)), int(k), int(drop),
                                       1 if descending else 0, _ptr(idx), _ptr(val), self._stream()))
         return idx, val
+
+    def tile_threshold_counts(self, tile, cmp, eps, swap=False, guard=0):
+        """Per-row number of tile entries passing the threshold test (pg_tile_threshold_count)."""
+        rows, N = tile.shape
+        counts = self.empty((rows,), torch.int64)
+        L.check(self.lib.pg_tile_threshold_count(_ptr(tile), _PG_DTYPE[tile.dtype], rows, N, int(tile.stride(0)), int(cmp),
+                                                 float(eps), 1 if swap else 0, int(guard), _ptr(counts), self._stream()))
+        return counts
 
     def tile_threshold(self, tile, cmp, eps, swap=False, guard=0, values=True):
         """CSR of the tile entries passing the threshold test (see pg_tile_threshold_count)."""

@@ -93,6 +93,23 @@ class KnnTable:
         return NeighbourTable(np.arange(0, (n + 1) * k, k, dtype=np.int64), self.idx.reshape(-1), self.w.reshape(-1))
 
 
+def row_sums_f32(indptr, w):
+    """float32 sum of every CSR row's weights, bit for bit what the reference's per-row
+    ``np.sum(weights.astype(np.float32))`` returns (prograph.py:819-821) without a Python loop over
+    the rows: rows of equal length are summed as one 2-D array, whose contiguous-axis reduction is
+    numpy's same pairwise routine."""
+    indptr = np.asarray(indptr)
+    w32 = np.asarray(w).astype(np.float32)
+    deg = np.diff(indptr)
+    out = np.zeros(len(deg), dtype=np.float32)
+    for d in np.unique(deg):
+        if d == 0:
+            continue
+        rows = np.nonzero(deg == d)[0]
+        out[rows] = w32[indptr[rows][:, None] + np.arange(d)].sum(axis=1, dtype=np.float32)
+    return out
+
+
 # ---------------------------------------------------------------------------------
 # helpers
 # ---------------------------------------------------------------------------------
@@ -112,6 +129,9 @@ def as_matrix(rep):
     return out
 
 
+MAX_TILE_K = 4095     # pg_tile_topk sorts k + 1 candidates of a row in shared memory
+
+
 def validate(eps, k):
     """Argument checks of prograph.py:714-718 (truthiness: eps=0 and k=0 are rejected)."""
     if operator.xor(bool(eps), bool(k)) is False:
@@ -119,6 +139,14 @@ def validate(eps, k):
                          "methods of graph construction.")
     if k is not None and not isinstance(k, int):
         raise TypeError("K must be provided as an integer.")
+
+
+def _check_tile_k(k, n):
+    """The reference sorts whole rows and accepts any k; the device top-k of the non-fused metrics
+    keeps k + 1 <= 4096 candidates per row.  Say so up front instead of failing inside a launch."""
+    if min(k, n - 1) > MAX_TILE_K:
+        raise ValueError(f"k={k}: the device top-k of this metric supports k <= {MAX_TILE_K} "
+                         "(Hamming on tokens: k <= 95 fused, above that through the same top-k)")
 
 
 def distance_lut(max_d, comp, eps, similarity, guard=True):
@@ -325,6 +353,7 @@ def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
     for the in-shared-memory lists of the fused sweep.  Ascending distance with index ties is
     the same order as descending similarity, so the sort always runs on the distances."""
     kk = min(k, stream.rows - 1)
+    _check_tile_k(k, stream.rows)
     step = max(512, (TILE_BUDGET_BYTES // (8 * stream.rows)) // 512 * 512)
     idxs, ws = [], []
     a0 = row0 // 512 * 512
@@ -487,6 +516,7 @@ def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows, gemm=N
 
 def _tile_knn(eng, tiles, k, similarity, n):
     kk = min(k, n - 1)
+    _check_tile_k(k, n)
     idxs, ws = [], []
     for _, tile in tiles:
         if kk <= 0:

@@ -177,8 +177,11 @@ class Prograph:
         return "This feature is not ready yet"
 
     def _letter_table(self):
+        """Byte -> token table of the tokeniser kernels: one byte per letter, tokens below 256."""
+        assert len(self.amino_acids) < 256, "alphabets of 256 or more letters do not fit one-byte tokens"
         table = np.zeros(256, dtype=np.uint8)
         for ch, tok in self.tokens.items():
+            assert len(ch) == 1, f"letter {ch!r} is not a single byte: the device tokeniser works on bytes"
             table[ch[0]] = tok
         return table
 
@@ -363,18 +366,45 @@ class Prograph:
         flag = self._hamming_flag(self.query(seq), operator.le, eps)
         return self[flag.cpu().numpy().view(np.bool_)]
 
-    def neighbourhood_clustering(self, eps, distance=hamming):
-        """Greedy cover: walk the sequences in order, every uncovered one seeds the cluster
-        of its eps-neighbourhood (prograph.py:590-615)."""
+    def neighbourhood_clustering(self, eps, distance=hamming, batch=128):
+        """Greedy cover: walk the sequences in order, every uncovered one seeds the cluster of its
+        eps-neighbourhood (prograph.py:590-615; clusters may overlap, as in the reference).
+
+        The reference asks for one neighbourhood per seed.  Here the next `batch` uncovered rows form
+        a frontier whose neighbourhood flags come out of ONE fused sweep (pg_hamming_flags_tile); the
+        greedy order inside the frontier is then resolved on its batch x batch corner -- a frontier row
+        that an earlier seed of the same batch covers is no seed -- and the member lists of the seeds are
+        compacted in one pass."""
+        eng = get_engine()
+        table = self._device_tokens()
+        n = len(self)
+        hi = int(np.floor(eps)) if eps >= 0 else -1                 # integer distances: d <= eps
+        covered_dev = torch.zeros(n, dtype=torch.uint8, device=eng.device)
+        covered = np.zeros(n, dtype=bool)
         clusters = {}
-        covered = np.zeros(len(self), dtype=bool)
-        for i in range(len(self)):
-            if covered[i]:
-                continue
-            flag = self._hamming_flag(i, operator.le, eps).cpu().numpy().view(np.bool_)
-            members = self.graph.iloc[flag]
-            clusters[i] = members
-            covered[np.asarray(members.index)] = True
+        start = 0
+        while start < n:
+            rest = np.nonzero(~covered[start:])[0]
+            if len(rest) == 0:
+                break
+            front = rest[:batch] + start
+            flags = eng.hamming_flags(table, eng.gather_packed(table, front), len(front), 0, hi)
+            corner = flags[:, torch.as_tensor(front, device=eng.device)].cpu().numpy().astype(bool)   # [seed, frontier row]
+            accept = np.zeros(len(front), dtype=np.uint8)
+            taken = np.zeros(len(front), dtype=bool)                 # frontier rows covered inside this batch
+            for b in range(len(front)):
+                if not taken[b]:
+                    accept[b] = 1
+                    taken |= corner[b]
+            seeds = np.nonzero(accept)[0]
+            flat = eng.flag_indices(flags[torch.as_tensor(seeds, device=eng.device)].reshape(-1)).cpu().numpy()
+            which, members = np.divmod(flat, n)
+            bounds = np.searchsorted(which, np.arange(len(seeds) + 1))
+            for s_i, b in enumerate(seeds):
+                clusters[int(front[b])] = self.graph.iloc[members[bounds[s_i]:bounds[s_i + 1]]]
+            eng.flags_or_rows(flags, accept, covered_dev)
+            covered = covered_dev.cpu().numpy().astype(bool)
+            start = int(front[-1]) + 1
         return clusters
 
     @staticmethod
@@ -439,15 +469,7 @@ class Prograph:
         t = self._table_for(graph)
         if boolean_weights:
             return t.degrees().astype(np.float32)
-        out = np.zeros(t.n_rows, dtype=np.float32)
-        w32 = t.w.astype(np.float32)
-        if w32.size and t.w.dtype.kind in "iu":
-            nz = t.indptr[:-1] < t.indptr[1:]
-            out[nz] = np.add.reduceat(w32.astype(np.float64), t.indptr[:-1][nz]).astype(np.float32)
-        else:
-            for r in range(t.n_rows):           # float weights: keep numpy's per-row summation order
-                out[r] = np.sum(w32[t.indptr[r]:t.indptr[r + 1]])
-        return out
+        return _graph.row_sums_f32(t.indptr, t.w)
 
     def get_neighbour_coords(self, graph="Neighbours", boolean_weights=False):
         """COO coordinates (I, J, weights) of the adjacency (prograph.py:823-853)."""

@@ -1,0 +1,210 @@
+"""Round-2 additions on the GPU: vectorised pack / mask kernels against the ballot kernels and the
+oracle, batched neighbourhood queries and clustering, the query module at BASELINE.json configs[4]
+scale (100 000 queries x 1 000 000 library rows, L=256, every metric of prograph/distance), and the
+error word of the symmetric sweep.  Reference lines: hamming.py:34-38, minkowski.py:36-40,
+prograph.py:488-492, 526-615."""
+import functools
+import operator
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prograph_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from prograph_b200.engine import get_engine
+    return get_engine()
+
+
+def np_(t):
+    return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+# ------------------------------------------------------------------ pack / masks
+@pytest.mark.parametrize("L", [1, 31, 32, 33, 56, 100, 255, 256, 257, 600])
+@pytest.mark.parametrize("alphabet", [20, 200])
+def test_vectorised_pack_equals_ballot_pack(eng, L, alphabet):
+    """uint8 tokens take pack_bytes_kernel (128-bit / 32-bit / byte loads depending on the row pitch,
+    one multiply per 4 tokens and plane); int64 tokens take the ballot kernel.  Same planes, for
+    5 planes (alphabet 20) and 8 planes (alphabet 200), ragged widths and short last words."""
+    rng = np.random.default_rng(L * 7 + alphabet)
+    n = 777
+    X = rng.integers(0, alphabet + 1, size=(n, L))
+    a = eng.pack(X.astype(np.uint8))
+    b = eng.pack(X.astype(np.int64))
+    assert (a.planes, a.words) == (b.planes, b.words) and a.planes == (5 if alphabet < 32 else 8)
+    assert torch.equal(a.data, b.data)
+    # rows of the padding (and words past L) are zero
+    assert int(a.data[n:].abs().sum().item()) == 0
+    D = O.hamming(X, X[:5])
+    np.testing.assert_array_equal(np_(eng.hamming_tile(a, a, 0, 512))[:5], D)
+
+
+def test_vectorised_pack_flags_tokens_that_do_not_fit(eng):
+    X = np.full((40, 64), 7, dtype=np.uint8)
+    X[17, 33] = 40                                       # does not fit 5 planes
+    flag = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    from prograph_b200 import _lib as L
+    from prograph_b200.engine import _ptr
+    t = eng.to_device(X)
+    out = eng.empty((512, 5, 2), torch.int32)
+    L.check(eng.lib.pg_pack_tokens(_ptr(t), L.U8, 40, 64, 64, _ptr(out), 5, 2, _ptr(flag), eng._stream()))
+    assert int(flag.item()) == 1
+    tab = eng.pack(X)                                    # the engine retries with 8 planes
+    assert tab.planes == 8
+    with pytest.raises(OverflowError):
+        eng.pack(X, planes=5)
+
+
+@pytest.mark.parametrize("L", [3, 33, 56, 100, 256])
+def test_pack_chars_and_mutant_bool(eng, L):
+    """Letters -> planes in one pass equals tokenise -> pack; the (N, L) boolean mutant array equals
+    prograph.py:488-492 for row pitches with and without 128-bit stores."""
+    rng = np.random.default_rng(L)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    n = 1500
+    chars = letters[rng.integers(0, 20, size=(n, L))]
+    short = rng.random(n) < 0.2                           # ragged library: zero bytes pad shorter strings
+    for r in np.nonzero(short)[0]:
+        chars[r, rng.integers(1, L + 1):] = 0
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[letters] = np.arange(1, 21)
+    tok = lut[chars].astype(np.int64)
+    a = eng.pack_chars(chars, lut)
+    b = eng.pack(tok, planes=5)
+    assert torch.equal(a.data, b.data)
+    for ref in (0, 7):
+        want = O.boolean_mutant_array(tok, ref)
+        got = np_(eng.mutant_bool(a, a.row(ref))).view(np.bool_)
+        np.testing.assert_array_equal(got, want)
+
+
+# ------------------------------------------------------------------ batched neighbourhoods
+def test_flags_tile_and_clustering_batches(eng, tmp_path):
+    from prograph_b200 import Prograph
+    rng = np.random.default_rng(4)
+    n, L = 3000, 40
+    wt = rng.integers(0, 20, size=L)
+    X = np.tile(wt, (n, 1))
+    for i in range(1, n):
+        pos = rng.choice(L, size=rng.integers(1, 6), replace=False)
+        X[i, pos] = (X[i, pos] + rng.integers(1, 20, size=len(pos))) % 20
+    alphabet = "ACDEFGHIKLMNPQRSTVWY"
+    seqs = ["".join(alphabet[t] for t in row) for row in X]
+    seqs = list(dict.fromkeys(seqs))                       # the frame's sequence -> row map wants unique rows
+    import pandas as pd
+    path = tmp_path / "lib.csv"
+    pd.DataFrame({"Sequence": seqs, "Fitness": np.arange(len(seqs), dtype=float)}).to_csv(path)
+    pg = Prograph(str(path))
+    tok = pg.tokenized
+    table = pg._device_tokens()
+    front = np.array([0, 5, 17, len(seqs) - 1])
+    flags = np_(eng.hamming_flags(table, eng.gather_packed(table, front), len(front), 0, 3))
+    np.testing.assert_array_equal(flags.astype(bool), O.hamming(tok, tok[front]) <= 3)
+    assert eng.hamming_flags(table, eng.gather_packed(table, front), len(front), 2, 1).sum().item() == 0
+    ref = None
+    for batch in (1, 7, 128):
+        clusters = pg.neighbourhood_clustering(3, batch=batch)
+        covered = np.zeros(len(pg), dtype=bool)
+        for seed, members in clusters.items():             # insertion order = the reference's greedy order
+            assert not covered[seed]
+            np.testing.assert_array_equal(np.asarray(members.index), np.where(O.neighbourhood_mask(tok, seed, 3))[0])
+            covered[np.asarray(members.index)] = True
+        assert covered.all()
+        keys = list(clusters)
+        assert keys == sorted(keys)
+        assert ref is None or keys == ref
+        ref = keys
+
+
+# ------------------------------------------------------------------ configs[4]: 100k queries x 1M library
+def _mutational(n, L, seed):
+    from bench import make_tokens
+    return make_tokens(n, L, "mutational", seed=seed)
+
+
+def test_config5_queries_every_metric(eng):
+    """BASELINE.json configs[4] / SURVEY.md §8(d) C5: library = C4-M (1M x 256), 100 000 queries from
+    the same wild type (default_rng(1)).  Every consumer of the query module against sampled oracle
+    rows: Hamming argmin/min, Hamming similarity tile, `<= eps` counts, materialised (1024, N) tiles,
+    Minkowski p=2 (int64 in -> float32 out, +- similarity) argmin and tiles, p in {1, 3} on a
+    subsample (the no-abs quirk: signed sums, NaN for negative cubes)."""
+    from oracle import c_oracle as CO
+    from prograph_b200 import hamming, minkowski, query
+    n, m, L = 1_000_000, 100_000, 256
+    X = _mutational(n, L, 0)
+    Q = _mutational(m, L, 1)
+    assert np.array_equal(X[0][X[0] == Q[0]], Q[0][X[0] == Q[0]])
+    lib = query.Library(X)
+    rng = np.random.default_rng(2)
+    sample = np.sort(rng.choice(m, size=24, replace=False))
+    sample[0], sample[-1] = 0, m - 1
+    planes = CO.pack(np.concatenate([X, Q[sample]]))
+    D = CO.hamming_rows(planes, L, n + np.arange(len(sample)), threads=16)[:, :n].astype(np.int64)   # (24, n)
+    del planes
+    # Hamming: argmin / min for all 100k queries
+    idx, d = query.nearest(lib, Q)
+    assert idx.shape == (m,) and d.dtype == torch.int64
+    np.testing.assert_array_equal(np_(idx)[sample], D.argmin(axis=1))
+    np.testing.assert_array_equal(np_(d)[sample], D.min(axis=1))
+    # <= eps counts (calc_neighbours semantics: no d > 0 filter), two predicates
+    for eps, comp in ((3, operator.le), (4, operator.eq)):
+        cnt = query.count_within(lib, Q, eps, comp)
+        np.testing.assert_array_equal(np_(cnt)[sample], comp(D, eps).sum(axis=1))
+    # materialised (1024, N) tiles: the public distance functions on the first 1024 queries
+    first = np.arange(0, 1024, 128)
+    D1 = CO.hamming_rows(CO.pack(np.concatenate([X, Q[first]])), L, n + np.arange(len(first)), threads=16)[:, :n]
+    T = query.tile(lib, Q, 0, 1024)
+    assert T.shape == (1024, n) and T.dtype == torch.int64
+    np.testing.assert_array_equal(np_(T[torch.as_tensor(first, device=T.device)]), D1)
+    S = query.tile(lib, Q, 0, 1024, similarity=True)
+    assert S.dtype == torch.float32
+    np.testing.assert_array_equal(np_(S[torch.as_tensor(first, device=S.device)]),
+                                  (np.float32(1) / (1 + D1).astype(np.float32)).astype(np.float32))
+    del T, S
+    # the drop-in distance function itself on a few queries against the whole library
+    D8 = CO.hamming_rows(CO.pack(np.concatenate([X, Q[:8]])), L, n + np.arange(8), threads=16)[:, :n]
+    np.testing.assert_array_equal(np_(hamming(X, Q[:8])), D8)
+    # Minkowski p=2 on int64 tokens: exact integer sum, float32 root (minkowski.py:36-40)
+    X64 = X.astype(np.int64)
+    few = sample[:6]
+    S2 = np.stack([((X.astype(np.int32) - Q[q].astype(np.int32)) ** 2).sum(axis=1, dtype=np.int64) for q in few])
+    root = np.sqrt(S2.astype(np.float32)).astype(np.float32)            # IEEE-rounded, as torch's CUDA sqrt
+    lib64 = query.Library(X64)
+    mi, mv = query.nearest(lib64, Q.astype(np.int64), distance=minkowski)
+    assert mv.dtype == torch.float32
+    np.testing.assert_array_equal(np_(mi)[few], np.argmin(S2, axis=1))
+    np.testing.assert_array_equal(np_(mv)[few], root.min(axis=1))
+    fewq = Q[few].astype(np.int64)
+    T2 = query.tile(lib64, fewq, distance=minkowski)
+    np.testing.assert_array_equal(np_(T2), root)
+    T2s = query.tile(lib64, fewq, distance=minkowski, similarity=True)
+    np.testing.assert_array_equal(np_(T2s), (np.float32(1) / (np.float32(1) + root)).astype(np.float32))
+    # p = 1 and p = 3 (no abs): signed sums; cube roots of negative sums are NaN -- subsample of the library
+    sub = X64[:20_000]
+    for p in (1, 3):
+        want = np_(O.minkowski(sub, fewq, p=p))
+        got = np_(query.tile(query.Library(sub), fewq, distance=functools.partial(minkowski, p=p)))
+        assert got.dtype == np.float32
+        if p == 1:
+            np.testing.assert_array_equal(got, (sub[None, :, :] - fewq[:, None, :]).sum(axis=2).astype(np.float32))
+        else:
+            s3 = ((sub[None, :, :] - fewq[:, None, :]) ** 3).sum(axis=2)
+            assert np.array_equal(np.isnan(got), s3 < 0)
+            ok = s3 >= 0
+            np.testing.assert_allclose(got[ok], np.cbrt(s3[ok].astype(np.float64)), rtol=4e-7)
+        np.testing.assert_allclose(got, want, rtol=4e-7, equal_nan=True)
+
+
+def test_sym_status_reports_ok_and_knows_its_workspace(eng):
+    rng = np.random.default_rng(3)
+    X = rng.integers(1, 21, size=(5000, 64)).astype(np.uint8)
+    tab = eng.pack(X)
+    eng.hamming_knn_sym(tab, 17)
+    eng.sym_check()                 # no lock was given up
+    eng.sym_check()                 # nothing pending: a no-op

@@ -303,3 +303,134 @@ def test_symmetric_build_policies():
         os.environ.pop("PG_KNN_SYM", None)
         if old is not None:
             os.environ["PG_KNN_SYM"] = old
+
+
+def test_symmetric_planner_covers_the_triangle_once_in_l2_bands():
+    """pg_knn_sym_plan (host-only): over all ranks the work items cover every (row block, stream tile)
+    of the triangle exactly once; every CTA walks its items band by band (so that co-resident CTAs
+    stream the same L2-sized part of the table); the CTAs' loads are balanced to a fraction of a percent."""
+    from prograph_b200.engine import sym_plan
+    for n, planes, words, boot, world in ((300_000, 5, 8, 8192, 1), (300_000, 5, 8, 8192, 3), (160_000, 5, 2, 8192, 2),
+                                          (70_000, 8, 4, 0, 1), (5_000, 5, 1, 512, 2)):
+        tile = 512 // words
+        n_tiles, n_blocks = -(-n // tile), -(-n // 256)
+        seen = np.zeros((n_blocks, n_tiles), dtype=np.int32)
+        for rank in range(world):
+            it = sym_plan(n, planes, words, boot, rank, world, 1 if world > 1 else 0, grid=296)
+            assert np.all(it[:, 2] > it[:, 1])
+            for rb, t0, t1, bt, cta in it:
+                seen[rb, t0:t1] += 1
+                assert bt == (1 if rb * 256 < boot else 0)
+            # per-CTA order: first tiles never go back by more than one band
+            load = np.bincount(it[:, 4], weights=(it[:, 2] - it[:, 1]).astype(np.float64))
+            if n >= 160_000:
+                assert load.max() / load.mean() < 1.02, (n, world, rank, load.max() / load.mean())
+            band_tiles = max(64, int(24 * 2**20 / (tile * planes * words * 4)))
+            for cta in np.unique(it[:, 4])[:8]:
+                mine = it[it[:, 4] == cta]
+                starts = mine[:, 1] // band_tiles
+                assert np.all(np.diff(starts) >= -1), (n, world, cta)
+        # the triangle: block rb sweeps the tiles from its own diagonal tile on (boot blocks: from `boot` on)
+        want = np.zeros_like(seen)
+        for rb in range(n_blocks):
+            first = (boot if rb * 256 < boot else rb * 256) // tile
+            want[rb, first:] = 1
+        np.testing.assert_array_equal(seen, want)
+
+
+def test_row_sums_match_the_reference_per_row_sum_bit_for_bit():
+    """graph.row_sums_f32 (degree of a weighted graph, prograph.py:819-821) equals a Python loop of
+    np.sum over the rows' float32 weights, for ragged rows, fp16 / float32 / integer weights."""
+    from prograph_b200.graph import row_sums_f32
+    rng = np.random.default_rng(0)
+    deg = rng.integers(0, 300, size=1500)
+    deg[5], deg[7] = 0, 1000
+    indptr = np.concatenate([[0], np.cumsum(deg)])
+    for w in (rng.random(indptr[-1]).astype(np.float16), (rng.random(indptr[-1]) * 1000).astype(np.float32),
+              rng.integers(0, 50, indptr[-1])):
+        ref = np.array([np.sum(w[indptr[r]:indptr[r + 1]].astype(np.float32)) for r in range(len(deg))], dtype=np.float32)
+        got = row_sums_f32(indptr, w)
+        assert got.dtype == np.float32
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_sidecar_fingerprint_rejects_a_rewritten_pickle(tmp_path):
+    """io.attach_sidecar only registers <name>.graph.npz when its fingerprint matches the pickled
+    Neighbours column (a pickle rewritten by another writer must not pick up stale CSR arrays)."""
+    import pandas as pd
+    from prograph_b200 import io as pio
+    from prograph_b200.graph import NeighbourTable
+
+    class Holder:
+        def __init__(self, frame):
+            self.graph, self.file, self.remembered = frame, str(tmp_path / "lib.csv"), None
+
+        def _table_for(self, name):
+            col = list(self.graph[name])
+            indptr = np.concatenate([[0], np.cumsum([len(x[0]) for x in col])])
+            return NeighbourTable(indptr, np.concatenate([x[0] for x in col]), np.concatenate([x[1] for x in col]))
+
+        def _remember(self, table, lists):
+            self.remembered = table
+
+    nb = [(np.array([1, 2]), np.array([1, 1])), (np.array([0]), np.array([1])), (np.array([0]), np.array([1]))]
+    h = Holder(pd.DataFrame({"Sequence": ["AA", "AC", "CA"], "Neighbours": nb, "Tokenized": [0, 1, 2]}))
+    pio.save(h, name="lib_pgraph", directory=str(tmp_path) + "/")
+    pkl = str(tmp_path / "lib_pgraph.pkl")
+    loaded = Holder(pd.read_pickle(pkl))
+    assert pio.attach_sidecar(loaded, pkl) and loaded.remembered.n_rows == 3
+    # same row count and same first row, but another graph: the round-1 check accepted this
+    frame = pd.read_pickle(pkl)
+    frame.at[2, "Neighbours"] = (np.array([0, 1]), np.array([1, 2]))
+    stale = Holder(frame)
+    assert not pio.attach_sidecar(stale, pkl) and stale.remembered is None
+
+
+def _gloo_output_worker(rank, world, port, n, tmpdir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _cpu_engine import CheckerEngine
+    from prograph_b200 import graph, shard
+    graph.SYM_MIN_ROWS = graph.SYM_EPS_MIN_ROWS = 0
+    rng = np.random.default_rng(8)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    eng = CheckerEngine()
+    knn = graph.build_neighbours(X, k=4, engine=eng, output="sharded")
+    eps = graph.build_neighbours(X, eps=2, engine=eng, output="sharded")
+    code = shard.agree(shard.NO_MEMORY if rank == 1 else shard.OK, world, None, torch.device("cpu"))
+    np.savez(os.path.join(tmpdir, f"o{rank}.npz"), idx=knn.idx, w=knn.w, row0=knn.row0, indptr=eps.indptr, eidx=eps.idx,
+             ew=eps.w, erow0=eps.row0, code=code, checks=eng.sym_checks)
+    dist.destroy_process_group()
+
+
+def test_sharded_output_and_collective_agreement_over_gloo(tmp_path):
+    """output="sharded": every rank returns its own row block (symmetric path: all-to-all of the lists,
+    merge, no final all-gather) and the blocks tile the oracle's graph; shard.agree hands every rank
+    the worst status any rank reported, so that all of them leave a failing build together."""
+    import torch.multiprocessing as mp
+    from oracle import prograph_oracle as O
+    from prograph_b200 import shard
+    n, world = 1301, 2
+    port = 29870 + os.getpid() % 50
+    mp.spawn(_gloo_output_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(8)
+    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    ri, rw = O.knn_from_distances(O.hamming(X, X), 4)
+    indptr, eidx, ew = O.to_csr(O.build_graph(X, eps=2))
+    rows_seen = 0
+    for r in range(world):
+        z = np.load(tmp_path / f"o{r}.npz")
+        r0, rows = shard.row_range(n, r, world)
+        assert int(z["row0"]) == r0 == int(z["erow0"]) and z["idx"].shape[0] == rows
+        np.testing.assert_array_equal(z["idx"], ri[r0:r0 + rows])
+        np.testing.assert_array_equal(z["w"], rw[r0:r0 + rows])
+        a, b = indptr[r0], indptr[r0 + rows]
+        np.testing.assert_array_equal(z["indptr"], indptr[r0:r0 + rows + 1] - a)
+        np.testing.assert_array_equal(z["eidx"], eidx[a:b])
+        np.testing.assert_array_equal(z["ew"], ew[a:b])
+        assert int(z["code"]) == shard.NO_MEMORY and int(z["checks"]) >= 1
+        rows_seen += rows
+    assert rows_seen == n
