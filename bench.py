@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eps", action="store_true", help="skip the threshold-graph block")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity checks")
+    ap.add_argument("--no-queries", action="store_true", help="skip the distance-to-dataset query block (C5)")
     ap.add_argument("--one-sided", action="store_true",
                     help="evaluate all N^2 ordered pairs with the one-sided sweep (no symmetry)")
     return ap.parse_args()
@@ -454,6 +455,14 @@ def run_b200(args):
             parity["eps_ok"] = bool(all(c.get("parity", {}).get("ok", True) for c in eps_block["cases"]))
             parity["ok"] = bool(parity["ok"] and parity["eps_ok"])
 
+    # ---- distance-to-dataset queries (BASELINE.json configs[4]) -----------------------------------
+    query_block = None
+    if not args.no_queries and not args.one_sided:
+        query_block = run_query_block(args, eng, rank, world, timed, cores)
+        if parity is not None and query_block is not None:
+            parity["queries_ok"] = bool(query_block.get("parity_ok", True))
+            parity["ok"] = bool(parity["ok"] and parity["queries_ok"])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -561,7 +570,8 @@ def run_b200(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8 tokens -> 5 bit planes, int32 popcount distances", "data": "synthetic",
         "config": config_of(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "phases_ms": phases, "parity": parity, "roofline": roofline, "eps": eps_block, "cpu_baseline": cpu,
+        "phases_ms": phases, "parity": parity, "roofline": roofline, "eps": eps_block, "queries": query_block,
+        "cpu_baseline": cpu,
     }
     emit(line)
     if world > 1:
@@ -724,6 +734,77 @@ def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
         dist.barrier()
     return {"metric": "threshold (epsilon) Hamming graphs, N^2 ordered pairs counted per build", "unit": "Gpairs/s",
             "steps": steps, "int_peak_tlops": int_peak / 1e12, "hbm_peak_gbs": hbm_peak, "cases": cases}
+
+
+# ----------------------------------------------------------------------------------------
+# distance-to-dataset queries: 100k queries x 1M library, every metric of prograph/distance (C5)
+# ----------------------------------------------------------------------------------------
+def run_query_block(args, eng, rank, world, timed, cores):
+    import functools
+    import operator
+    import torch
+    from prograph_b200 import minkowski, query
+    n, L = args.n, args.length
+    m = max(1024, n // 10)
+    X = make_tokens(n, L, "mutational")
+    Q = make_tokens(m, L, "mutational", seed=1)
+    lib = query.Library(X)
+    lib.packed()
+    lib.gemm(255)
+    torch.cuda.synchronize()
+    out = {}
+    cases = []
+
+    def run(name, fn, pairs, reps=2):
+        fn()
+        ms = timed(fn, reps) / reps
+        cases.append({"name": name, "ms": ms, "gpairs_per_s": pairs / (ms * 1e-3) / 1e9})
+
+    def hn():
+        out["hn"] = query.nearest(lib, Q)
+
+    def hc():
+        out["hc"] = query.count_within(lib, Q, 3)
+
+    def mn():
+        out["mn"] = query.nearest(lib, Q, distance=minkowski)
+
+    run(f"hamming argmin/min, {m} queries x {n}", hn, float(m) * n)
+    run(f"hamming count(d <= 3), {m} queries x {n}", hc, float(m) * n)
+    run(f"minkowski p=2 argmin/min (integer tokens -> float32), {m} queries x {n}", mn, float(m) * n)
+    run(f"hamming (1024, {n}) int64 tile", lambda: query.tile(lib, Q, 0, 1024), 1024.0 * n)
+    run(f"hamming similarity (1024, {n}) float32 tile", lambda: query.tile(lib, Q, 0, 1024, similarity=True), 1024.0 * n)
+    run(f"minkowski p=2 (1024, {n}) float32 tile", lambda: query.tile(lib, Q, 0, 1024, distance=minkowski), 1024.0 * n)
+    run(f"minkowski p=2 similarity (1024, {n}) float32 tile",
+        lambda: query.tile(lib, Q, 0, 1024, distance=minkowski, similarity=True), 1024.0 * n)
+    sub = min(1000, m)
+    for p in (1, 3):
+        run(f"minkowski p={p} ({sub}, {n}) float32 tile (element-wise kernel, no-abs quirk)",
+            lambda p=p: query.tile(lib, Q, 0, sub, distance=functools.partial(minkowski, p=p)), float(sub) * n, reps=1)
+    block = {"workload": f"C5: {m} queries (mutational, default_rng(1)) x {n}-row mutational library, L={L}; query rows "
+                         f"sharded over {world} GPU(s), library layouts resident", "cases": cases}
+    if not args.no_parity:
+        ok = True
+        if rank == 0:
+            from oracle import c_oracle as CO
+            sample = np.sort(np.random.default_rng(2).choice(m, size=16, replace=False))
+            D = CO.hamming_rows(CO.pack(np.concatenate([X, Q[sample]])), L, n + np.arange(len(sample)), threads=cores)[:, :n]
+            D = D.astype(np.int64)
+            sel = torch.from_numpy(sample).to(eng.device)
+            ok &= bool(np.array_equal(out["hn"][0][sel].cpu().numpy(), D.argmin(axis=1))
+                       and np.array_equal(out["hn"][1][sel].cpu().numpy(), D.min(axis=1))
+                       and np.array_equal(out["hc"][sel].cpu().numpy(), (D <= 3).sum(axis=1)))
+            few = sample[:4]
+            S2 = np.stack([((X.astype(np.int32) - Q[q].astype(np.int32)) ** 2).sum(axis=1, dtype=np.int64) for q in few])
+            fsel = torch.from_numpy(few).to(eng.device)
+            ok &= bool(np.array_equal(out["mn"][0][fsel].cpu().numpy(), S2.argmin(axis=1))
+                       and np.array_equal(out["mn"][1][fsel].cpu().numpy(),
+                                          np.sqrt(S2.min(axis=1).astype(np.float32)).astype(np.float32)))
+        block["parity_ok"] = all_true(ok, world, eng.device)
+        block["parity_how"] = "16 sampled queries: argmin / min / count against oracle/hamming_knn_cpu.c distance rows; 4 sampled " \
+                              "queries: Minkowski argmin / float32 root against exact integer sums (numpy)"
+    out.clear()
+    return block
 
 
 def main():

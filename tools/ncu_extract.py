@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Condense `ncu -i X.ncu-rep --page raw --csv` (stdin) into the metric,unit,value extract kept
-under profiles/ (first profiled launch; the metrics DESIGN.md / bench.py quote)."""
+under profiles/ (first profiled launch; the metrics DESIGN.md / bench.py quote).  `--all` prints one
+block per profiled launch (helper-kernel captures hold several kernels)."""
 import csv
 import sys
 
@@ -29,15 +30,16 @@ def main():
     rows = list(csv.reader(line for line in sys.stdin if line.startswith('"')))
     if len(rows) < 3:
         sys.exit("no raw page on stdin")
-    names, units, first = rows[0], rows[1], rows[2]
+    names, units = rows[0], rows[1]
     print("metric,unit,value")
-    for i, name in enumerate(names):
-        if name == "Kernel Name":
-            print(f'Kernel Name,,"{first[i]}"')
-    for want in KEEP:
-        if want in names:
-            i = names.index(want)
-            print(f"{want},{units[i]},{first[i].replace(',', '')}")
+    for first in (rows[2:] if "--all" in sys.argv else rows[2:3]):
+        for i, name in enumerate(names):
+            if name == "Kernel Name":
+                print(f'Kernel Name,,"{first[i]}"')
+        for want in KEEP:
+            if want in names:
+                i = names.index(want)
+                print(f"{want},{units[i]},{first[i].replace(',', '')}")
 
 
 if __name__ == "__main__":
