@@ -343,6 +343,11 @@ int pg_distance_hist(const uint32_t* mut, int64_t N, int words, int64_t* hist, v
  * 5 LOP3 : 1 POPC : 1 IADD mix as the Hamming inner loop (mix 0), LOP3 only (1) or
  * POPC only (2) and returns lane-ops per second (synchronous). */
 int pg_measure_int_peak(int mix, int iters, double* lane_ops_per_s, double* ms);
+/* int8 tensor-pipe peak: back-to-back tcgen05.mma kind::i8 (M=128, N=256, K=32) on operands resident
+ * in shared memory, 148 CTAs; returns int8 operations (2 per multiply-add) per second
+ * (synchronous).  The upper bound of a one-hot int8 GEMM formulation of Hamming (2*21*L operations
+ * per pair) that DESIGN.md compares the popcount sweep with.  */
+int pg_measure_i8_mma_peak(int batches, double* int8_ops_per_s, double* ms);
 /* number of kernel launches issued by this library since the last reset */
 int64_t pg_launch_count(int reset);
 /* average device time (CUDA events on the launch stream) of the fused sweep kernel since

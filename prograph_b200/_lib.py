@@ -77,6 +77,7 @@ SIGNATURES = {
     "pg_flag_indices": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "pg_distance_hist": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pg_measure_int_peak": (_i, [_i, _i, _pdbl, _pdbl]),
+    "pg_measure_i8_mma_peak": (_i, [_i, _pdbl, _pdbl]),
     "pg_launch_count": (_i64, [_i]),
     "pg_time_sweeps": (_i, [_i]),
     "pg_sweep_time": (_i, [_pdbl, _pi64, _i]),

@@ -106,6 +106,28 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 // ---- small device utilities ---------------------------------------------------
+// i -> (i / d, i % d) without the ~100-instruction 64-bit division of the generic path: d is a
+// power of two (shift >= 0) for every packed width up to 512 residues, and small indices divide in 32 bits.
+__device__ __forceinline__ void split_index(long long i, int d, int shift, long long* q, int* r) {
+  if (shift >= 0) {
+    *q = i >> shift;
+    *r = static_cast<int>(i & (d - 1));
+  } else if (i < (1ll << 32)) {
+    const unsigned u = static_cast<unsigned>(i);
+    *q = u / static_cast<unsigned>(d);
+    *r = static_cast<int>(u - static_cast<unsigned>(*q) * static_cast<unsigned>(d));
+  } else {
+    *q = i / d;
+    *r = static_cast<int>(i - *q * d);
+  }
+}
+__host__ __device__ inline int pow2_shift(int d) {
+  if (d <= 0 || (d & (d - 1)) != 0) return -1;
+  int s = 0;
+  while ((1 << s) < d) ++s;
+  return s;
+}
+
 __device__ __forceinline__ float sim_f32(int d) { return __fdiv_rn(1.0f, (float)(1 + d)); }
 
 template <typename T>

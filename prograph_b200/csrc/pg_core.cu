@@ -137,10 +137,12 @@ __global__ void __launch_bounds__(256) pack_bytes_kernel(const uint8_t* __restri
   const bool vec16 = (ld % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
   const bool vec4 = (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0);
   bool bad = false;
+  const int wshift = pow2_shift(words);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / words;
-    const int w = static_cast<int>(i - row * words);
+    long long row;
+    int w;
+    split_index(i, words, wshift, &row, &w);
     uint32_t x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = 0u;

@@ -11,14 +11,16 @@
 //   * operands are stored in HBM already in the K-major, no-swizzle core-matrix layout the
 //     MMA reads from shared memory (8 rows x 16 bytes per core matrix), so tiles are moved
 //     with 1-D bulk async copies (cp.async.bulk + mbarrier), no tensor map needed;
-//   * one CTA = 128 query rows (A tile, resident) against the whole dataset streamed in
-//     128-row B tiles through a 4-stage ring; M=128, N=128, K=32 per instruction;
-//   * four 128-column TMEM accumulators (all of TMEM), two per epilogue group: the MMAs run up
-//     to two tiles ahead of each group's epilogue;
-//   * warp roles: 8 epilogue warps in two groups that alternate tiles (thread = TMEM lane =
-//     query row, each group keeps its own lists, merged at the end), 1 producer lane,
-//     1 MMA-issuing lane (which also owns the TMEM allocation); the dataset norms ride along
-//     with the B tiles into a small shared-memory ring;
+//   * one CTA = 256 query rows = TWO resident A tiles against the whole dataset streamed in
+//     128-row B tiles through a ring; every B tile is multiplied with both A tiles (M=128, N=128,
+//     K=32 per instruction), which halves the bytes streamed out of L2 per pair: with one A tile
+//     the MMA issuer waited for B tiles 37 % of the time (every SM pulled 20 B/clk, 5.8 TB/s in
+//     aggregate, profiles/r1_ncu_notes.md);
+//   * four 128-column TMEM accumulators (all of TMEM): two per A tile, so the MMAs of tile t+1 run
+//     while the epilogues of tile t drain;
+//   * warp roles: 8 epilogue warps in two groups, group g owns A tile g (thread = TMEM lane =
+//     query row, one sorted list per row), 1 producer lane, 1 MMA-issuing lane (which also owns the
+//     TMEM allocation); the dataset norms ride along with the B tiles into a small shared-memory ring;
 //   * epilogues: materialised tile (minkowski.py:36-40) or fused kNN: a candidate test in
 //     S-space against a per-row integer threshold (min + one vote per 32 columns), rare
 //     warp-cooperative insertion into a sorted (value, index) list in shared memory; the
@@ -27,14 +29,16 @@
 
 namespace pg {
 
-constexpr int GM = 128;         // query rows per CTA (MMA M)
+constexpr int GM = 128;         // query rows per A tile (MMA M)
+constexpr int GA = 2;           // A tiles per CTA: every B tile is multiplied with both
+constexpr int GROWS = GM * GA;  // query rows per CTA
 constexpr int GN = 128;         // dataset rows per B tile (MMA N)
-constexpr int GSTAGES = 4;
+constexpr int GSTAGES = 4;      // deepest B ring (fewer stages when the lists need the room)
 constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp + MMA warp
 constexpr int GPROD_WARP = 8;
 constexpr int GMMA_WARP = 9;
 constexpr int GPROD_LANES = 8;  // lanes of the producer warp that each copy a slice of a B tile
-constexpr int GACC = 4;         // TMEM accumulators (4 x 128 columns = all 512): two per epilogue group
+constexpr int GACC = 4;         // TMEM accumulators (4 x 128 columns = all 512): two per A tile
 constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
 constexpr int PAD_NORM = 0x3fffffff;
 
@@ -192,31 +196,15 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
-__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// Epsilon modes walk the tiles as 0, h, 1, h+1, ... (h = half the tiles) so that each epilogue group
-// (even / odd positions) owns one contiguous half of the dataset: its hits of a row are then a
-// contiguous, ascending part of that row's edge list.
-template <int MODE>
-__device__ __forceinline__ int tile_at(int pos, int n_tiles) {
-  if (MODE == GM_COUNT || MODE == GM_FILL) {
-    const int half = (n_tiles + 1) >> 1;
-    return (pos & 1) ? half + (pos >> 1) : (pos >> 1);
-  }
-  return pos;
-}
-
 template <int VK, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int K = prm.K;
   const uint32_t tile_bytes = GM * K;                     // A and B tiles have the same shape
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + tile_bytes;
+  uint8_t* sA = smem;                                     // [GA] tiles
+  uint8_t* sB = smem + GA * tile_bytes;
   const int n_stages = prm.stages;
-  int* sNorm = reinterpret_cast<int*>(smem + tile_bytes * (1 + n_stages));        // [GNORM_SLOTS][GN]
+  int* sNorm = reinterpret_cast<int*>(smem + tile_bytes * (GA + n_stages));       // [GNORM_SLOTS][GN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + GNORM_SLOTS * GN);
   uint64_t* full = bars;                  // [GSTAGES] B tile (+ its norms) landed
   uint64_t* empty = bars + GSTAGES;       // [GSTAGES] MMAs reading the stage have completed
@@ -224,8 +212,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   uint64_t* acc_empty = acc_full + GACC;      // [GACC] epilogue has drained the accumulator
   uint64_t* a_full = acc_empty + GACC;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
-  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [2][GM][k1]
-  int* slists = reinterpret_cast<int*>(lists + 2 * GM * prm.k1);                        // [2][GM][k1] exact sums
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [GROWS][k1]
+  int* slists = reinterpret_cast<int*>(lists + GROWS * prm.k1);                         // [GROWS][k1] exact sums
   // tile mode (no lists): per-warp 32 x 36-word transpose buffers, 16-byte aligned
   uint32_t* tile_stage = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_holder + 2) + 15) & ~uintptr_t(15));
   const bool tile_fast = MODE == GM_TILE && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0 &&
@@ -234,7 +222,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const long long row0 = static_cast<long long>(blockIdx.x) * GM;
+  const long long row0 = static_cast<long long>(blockIdx.x) * GROWS;
   // blockIdx.y splits the dataset (tile mode with few query rows): this CTA sweeps tiles
   // [t_begin, t_begin + n_tiles); `t` below counts tiles within that range
   const int all_tiles = static_cast<int>((prm.N + GN - 1) / GN);
@@ -260,9 +248,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
     // GPROD_LANES lanes each issue a slice of the tile so that several bulk requests are in flight
     // (measured neutral against one 32 KB request; the kernel is not copy-bound, see
     // profiles/r1_ncu_notes.md).
-    if (lane == 0) {
-      mbar_arrive_expect_tx(a_full, tile_bytes);
+    if (lane == 0) {        // both A tiles: 256 consecutive rows of the core-matrix table (padded to GROWS)
+      mbar_arrive_expect_tx(a_full, GA * tile_bytes);
       bulk_g2s(sA, prm.A + static_cast<size_t>(row0) * K, tile_bytes, a_full);
+      bulk_g2s(sA + tile_bytes, prm.A + static_cast<size_t>(row0 + GM) * K, tile_bytes, a_full);
     }
     const uint32_t slice = tile_bytes / GPROD_LANES;
     int stage = 0;
@@ -271,15 +260,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       if (lane == 0) {
         mbar_wait_poll(&empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&full[stage], tile_bytes + GN * 4);
-        // the norms of tile t live in slot t % GNORM_SLOTS until the epilogue of tile t is done;
-        // slot reuse (tile t + 8) is ordered behind MMA t+4, i.e. behind the epilogue of tile t+2
-        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN,
+        // the norms of tile t live in slot t % GNORM_SLOTS until both epilogues of tile t are done;
+        // slot reuse (tile t + 8) is ordered behind the MMAs of tile t + 8 - stages >= t + 4, which
+        // themselves wait for the epilogues of tile t + 2
+        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + t) * GN,
                  GN * 4, &full[stage]);
       }
       __syncwarp();
       if (lane < GPROD_LANES) {
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
-                 prm.B + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN * K + lane * slice, slice,
+                 prm.B + static_cast<size_t>(t_begin + t) * GN * K + lane * slice, slice,
                  &full[stage]);
       }
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -294,27 +284,30 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int acc = t & (GACC - 1);
-        mbar_wait_poll(&acc_empty[acc], ((t / GACC) & 1) ^ 1u);
         mbar_wait_poll(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA);
         const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(stage) * tile_bytes);
-        for (int j = 0; j < K / 32; ++j) {
-          umma_i8(tmem_base + acc * GN, umma_desc(a_addr + j * 256, 128, sbo), umma_desc(b_addr + j * 256, 128, sbo),
-                  idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int a = 0; a < GA; ++a) {
+          const int acc = a + GA * (t & 1);               // A tile a alternates between accumulators a and a + 2
+          mbar_wait_poll(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + static_cast<size_t>(a) * tile_bytes);
+          for (int j = 0; j < K / 32; ++j) {
+            umma_i8(tmem_base + acc * GN, umma_desc(a_addr + j * 256, 128, sbo), umma_desc(b_addr + j * 256, 128, sbo),
+                    idesc, j > 0 ? 1u : 0u);
+          }
+          umma_commit(&acc_full[acc]);    // this A tile's accumulator is complete
         }
-        umma_commit(&empty[stage]);       // the stage may be refilled once these MMAs have read it
-        umma_commit(&acc_full[acc]);      // ... and the accumulator is complete
+        umma_commit(&empty[stage]);       // the stage may be refilled once all MMAs reading it are done
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
-    // ---------------- epilogue: two warp groups alternate tiles; thread = TMEM lane = query row ---
-    const int group = warp >> 2;                 // 0: even tiles (accumulator 0), 1: odd tiles
-    const int r_loc = tid & (GM - 1);            // query row within the CTA
+    // ---------------- epilogue: warp group g owns A tile g; thread = TMEM lane = query row ---------
+    const int group = warp >> 2;                 // A tile of this group
+    const int r_loc = tid & (GM - 1);            // query row within the A tile = TMEM lane
     const int qwarp = warp & 3;                  // TMEM lane quarter this warp may read
-    const long long row = row0 + r_loc;
+    const long long row = row0 + group * GM + r_loc;
     const bool valid = row < prm.M;
     const int nq = valid ? prm.normA[row] : 0;
     unsigned long long* my_list = lists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
@@ -325,15 +318,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       __syncwarp();
     }
     long long ecur = 0;    // epsilon modes: hits counted / next edge slot of this (row, group)
-    if (MODE == GM_FILL && valid)
-      ecur = prm.indptr[row] + (group ? prm.group_counts[row] : 0);
+    if (MODE == GM_FILL && valid) ecur = prm.indptr[row];
     const int eoff = nq - prm.s_lo;    // in range iff (unsigned)(v + eoff) <= s_span
     const uint32_t lane_base = static_cast<uint32_t>(qwarp * 32) << 16;
-    for (int t = group; t < n_tiles; t += 2) {
-      const int acc = t & (GACC - 1);       // group g drains accumulators g and g+2 in turn
-      mbar_wait(&acc_full[acc], (t / GACC) & 1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = group + GA * (t & 1);    // group g drains accumulators g and g + 2 in turn
+      mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
-      const long long col_tile = static_cast<long long>(t_begin + tile_at<MODE>(t, n_tiles)) * GN;
+      const long long col_tile = static_cast<long long>(t_begin + t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
       uint32_t dotbuf[2][32];
       tmem_ld32_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
@@ -379,7 +371,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
             __syncwarp();
             constexpr int LPR = WPR / 4;                       // lanes per row segment
             constexpr int RPI = 32 / LPR;                      // rows per store instruction
-            const long long wrow0 = row0 + qwarp * 32;
+            const long long wrow0 = row0 + group * GM + qwarp * 32;
 #pragma unroll
             for (int it = 0; it < 32 / RPI; ++it) {
               const int rr = it * RPI + lane / LPR;
@@ -446,20 +438,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-    if (MODE == GM_COUNT && valid) prm.group_counts[static_cast<size_t>(group) * prm.M + row] = ecur;
+    if (MODE == GM_COUNT && valid) prm.group_counts[row] = ecur;      // second half of the scratch stays 0
     if (MODE == GM_KNN) {
-      // merge the two groups' lists of every row (both ascending, keys unique) and write out
-      named_barrier_sync(1, 8 * 32);
-      if (group == 0 && valid) {
-        const unsigned long long* la = lists + static_cast<size_t>(r_loc) * prm.k1;
-        const unsigned long long* lb = lists + (static_cast<size_t>(GM) + r_loc) * prm.k1;
-        int ia = 0, ib = 0;
-        for (int j = 0; j < prm.drop + prm.k; ++j) {
-          const unsigned long long ka = ia < prm.k1 ? la[ia] : ~0ull;
-          const unsigned long long kb = ib < prm.k1 ? lb[ib] : ~0ull;
-          const unsigned long long key = ka < kb ? ka : kb;
-          if (ka < kb) ++ia; else ++ib;
-          if (j < prm.drop) continue;
+      // every row has one list (ascending, keys unique): drop, widen, write out
+      __syncwarp();
+      if (valid) {
+        for (int j = prm.drop; j < prm.drop + prm.k; ++j) {
+          const unsigned long long key = j < prm.k1 ? my_list[j] : ~0ull;
           const size_t at = static_cast<size_t>(row) * prm.k + (j - prm.drop);
           if (key == ~0ull) {
             prm.out_idx[at] = -1;
@@ -547,22 +532,22 @@ __global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long
 }
 
 static size_t gemm_smem_bytes(int K, int k1, int stages, bool tile_mode = false) {
-  return static_cast<size_t>(GM) * K * (1 + stages) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 2 * GACC + 1) * sizeof(uint64_t) +
-         16 + 2 * static_cast<size_t>(GM) * k1 * 12 + (tile_mode ? 16 + 8 * 32 * 36 * 4 : 0);
+  return static_cast<size_t>(GM) * K * (GA + stages) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 2 * GACC + 1) * sizeof(uint64_t) +
+         16 + static_cast<size_t>(GROWS) * k1 * 12 + (tile_mode ? 16 + 8 * 32 * 36 * 4 : 0);
 }
 
 template <int VK, int MODE>
 static int launch_gemm(GemmParams prm, cudaStream_t s) {
   auto kern = mink_gemm_kernel<VK, MODE>;
-  prm.stages = GSTAGES;
-  size_t smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages, MODE == GM_TILE);
-  if (smem > 227 * 1024) {     // long lists: give up one ring stage before giving up the fused path
-    prm.stages = GSTAGES - 1;
+  // wide rows / long lists: give up ring stages (down to 2) before giving up the fused path
+  size_t smem = 0;
+  for (prm.stages = GSTAGES; prm.stages >= 2; --prm.stages) {
     smem = gemm_smem_bytes(prm.K, MODE == GM_KNN ? prm.k1 : 0, prm.stages, MODE == GM_TILE);
+    if (smem <= 227 * 1024) break;
   }
   if (smem > 227 * 1024) { set_error("minkowski GEMM: k or row width too large for shared memory (%zu bytes)", smem); return PG_ERR_UNSUPPORTED; }
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const unsigned gx = static_cast<unsigned>(ceil_div(prm.M, GM));
+  const unsigned gx = static_cast<unsigned>(ceil_div(prm.M, GROWS));
   unsigned gy = 1;
   if (MODE == GM_TILE) {   // few query rows: split the dataset so that every SM gets a CTA or two
     const long long tiles = ceil_div(prm.N, GN);
@@ -576,14 +561,91 @@ static int launch_gemm(GemmParams prm, cudaStream_t s) {
   return PG_OK;
 }
 
+// ---- int8 tensor-pipe peak probe -------------------------------------------------------------
+// Back-to-back  tcgen05.mma.cta_group::1.kind::i8  M=128, N=256, K=32  on operands that stay in shared
+// memory (pseudo-random bytes), accumulating into the two halves of TMEM in turn; one batch of MMAs
+// is always in flight behind the one being issued.  Nothing is loaded, expanded or read back, so the
+// rate is an upper bound for ANY formulation of the path on the int8 tensor pipe -- in particular for
+// the one-hot Hamming GEMM (2 * 21 * L int8 operations per pair), which would in
+// addition have to expand its operands and run an epilogue.
+constexpr int PROBE_K = 256;
+constexpr int PROBE_BATCH = 16;      // tiles (8 MMAs each) per commit
+
+__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int batches) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint8_t* sA = smem;                               // 128 x 256
+  uint8_t* sB = smem + GM * PROBE_K;                // 256 x 256
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * GM * PROBE_K);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2);
+  for (int i = threadIdx.x; i < 3 * GM * PROBE_K / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = (i * 2654435761u + blockIdx.x * 40503u) & 0x1f1f1f1fu;   // tokens 0..31
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core reads
+  if (threadIdx.x < 32) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) {
+    // D=S32, A=B=UINT8, K-major both, N=256, M=128
+    const uint32_t idesc = (2u << 4) | (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(GM >> 4) << 24);
+    const uint32_t sbo = static_cast<uint32_t>(PROBE_K / 16) * 128u;
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    for (int b = 0; b < batches; ++b) {
+      if (b >= 2) mbar_wait_poll(&bars[b & 1], ((b >> 1) - 1) & 1);     // batch b - 2 has completed
+      for (int t = 0; t < PROBE_BATCH; ++t) {
+        const uint32_t acc = tmem_base + ((t & 1) ? 256u : 0u);
+        for (int j = 0; j < PROBE_K / 32; ++j)
+          umma_i8(acc, umma_desc(a_addr + j * 256, 128, sbo), umma_desc(b_addr + j * 256, 128, sbo), idesc, j > 0 ? 1u : 0u);
+      }
+      umma_commit(&bars[b & 1]);
+    }
+    for (int b = batches > 2 ? batches - 2 : 0; b < batches; ++b) mbar_wait_poll(&bars[b & 1], (b >> 1) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace pg
 
 using namespace pg;
 
 extern "C" {
 
+int pg_measure_i8_mma_peak(int batches, double* int8_ops_per_s, double* ms_out) {
+  PG_CHECK_ARG(batches >= 1 && batches <= (1 << 20), "bad probe arguments");
+  const size_t smem = 3 * static_cast<size_t>(GM) * PROBE_K + 64;
+  PG_CUDA(cudaFuncSetAttribute(i8_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaEvent_t a, b;
+  PG_CUDA(cudaEventCreate(&a));
+  PG_CUDA(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    PG_CUDA(cudaEventRecord(a, 0));
+    i8_mma_peak_kernel<<<num_sms(), 128, smem>>>(batches);
+    PG_CUDA(cudaEventRecord(b, 0));
+    PG_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    PG_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  PG_CUDA(cudaGetLastError());
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  // per CTA: batches * PROBE_BATCH tiles of 128 x 256 x 256 multiply-adds
+  const double ops = 2.0 * GM * 256.0 * PROBE_K * PROBE_BATCH * static_cast<double>(batches) * num_sms();
+  if (int8_ops_per_s) *int8_ops_per_s = ops / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return PG_OK;
+}
+
 int pg_gemm_width(int L) { return L <= 0 ? 0 : (L + 31) / 32 * 32; }
-int64_t pg_gemm_rows(int64_t N) { return N <= 0 ? 0 : round_up(N, GM); }
+int64_t pg_gemm_rows(int64_t N) { return N <= 0 ? 0 : round_up(N, GROWS); }   // a CTA loads GROWS query rows
 
 int pg_gemm_pack(const void* tokens, int dtype, int64_t N, int L, int64_t ld, uint8_t* table, int32_t* norms, int K,
                  int max_token, int* flag, void* stream) {

@@ -19,13 +19,15 @@ struct LutVec { uint32_t w[kMaxMaskWords + 1]; };     // truth table over d = 0 
 __global__ void mutant_bits_kernel(const uint32_t* __restrict__ table, long long N, int planes, int words,
                                    const uint32_t* __restrict__ ref, uint32_t* __restrict__ mut) {
   const long long total = N * words;
+  const int wshift = pow2_shift(words);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / words;
-    const int w = static_cast<int>(i - n * words);
-    const uint32_t* row = table + static_cast<size_t>(n) * planes * words;
+    long long n;
+    int w;
+    split_index(i, words, wshift, &n, &w);
+    const uint32_t* row = table + static_cast<size_t>(n) * planes * words + w;
     uint32_t m = 0;
-    for (int p = 0; p < planes; ++p) m |= row[p * words + w] ^ __ldg(ref + p * words + w);
+    for (int p = 0; p < planes; ++p) m |= __ldcs(row + p * words) ^ __ldg(ref + p * words + w);
     mut[i] = m;
   }
 }
@@ -38,10 +40,12 @@ __global__ void __launch_bounds__(256) mutant_bool_kernel(const uint32_t* __rest
                                                           uint8_t* __restrict__ out) {
   const long long total = N * words;
   const bool vec16 = (L % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const int wshift = pow2_shift(words);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / words;
-    const int w = static_cast<int>(i - n * words);
+    long long n;
+    int w;
+    split_index(i, words, wshift, &n, &w);
     const int have = min(32, L - w * 32);
     if (have <= 0) continue;
     const uint32_t* row = table + static_cast<size_t>(n) * planes * words + w;

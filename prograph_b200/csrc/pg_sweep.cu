@@ -588,10 +588,13 @@ __global__ void knn_keys_widen_kernel(const unsigned long long* __restrict__ key
                                       int k1, int k, int drop, int weight, long long* __restrict__ out_idx,
                                       void* out_w) {
   const long long total = rows * k;
+  const int kshift = pow2_shift(k);
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = e / k;
-    const int j = static_cast<int>(e - r * k) + drop;
+    long long r;
+    int j;
+    split_index(e, k, kshift, &r, &j);
+    j += drop;
     const unsigned long long key = j < k1 ? __ldcs(keys + (row0 + r) * k1 + j) : ~0ull;
     emit_key(key, e, weight, false, nullptr, out_idx, out_w);
   }

@@ -543,6 +543,12 @@ class CudaEngine:
         L.check(self.lib.pg_measure_int_peak(int(mix), int(iters), C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
 
+    def i8_mma_peak(self, batches=256):
+        """int8 operations per second of back-to-back tcgen05 MMAs on resident operands (pg_measure_i8_mma_peak)."""
+        ops, ms = C.c_double(0), C.c_double(0)
+        L.check(self.lib.pg_measure_i8_mma_peak(int(batches), C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
     def time_sweeps(self, enable=True):
         self.lib.pg_time_sweeps(1 if enable else 0)
 

@@ -553,7 +553,15 @@ def test_headline_config_one_million_uniform(eng):
     tab = eng.pack(X)
     from prograph_b200 import graph
     assert n >= graph.SYM_MIN_ROWS                                # i.e. the symmetric build, as in bench.py
-    idx, w = graph.hamming_knn_graph(eng, tab, k, False, 0, 1, None)
+    idx, w, row0 = graph.hamming_knn_graph(eng, tab, k, False, 0, 1, None)
+    assert row0 == 0
+    # every one of the 16 M entries against the one-sided sweep (10^12 pair evaluations, ~3 s): the lock
+    # regime of the full-size build (tens of millions of row-lock acquisitions) never occurs in the
+    # small-table tests
+    oi, ow = eng.hamming_knn(tab, 0, n, tab, k, drop=1)
+    assert torch.equal(idx, oi) and torch.equal(w, ow)
+    del oi, ow
+    eng.sym_check()
     idx, w = np_(idx), np_(w)
     rng = np.random.default_rng(123)
     # rows of the bootstrap block, of the first / last row blocks and random ones
