@@ -14,8 +14,11 @@ lists or mutation masks runs on the GPU through libprograph_b200.so:
     degree, get_neighbour_coords,     prograph.py:797-897   CSR-native (no per-row loops)
     adjacency, laplacian
 
-The ML adapters (sklearn / pytorch loaders, fit), networkx export and persistence of the
-reference are outside this path and are not re-implemented here.
+The ML adapters (sklearn / pytorch loaders, fit), networkx export, dirichlet / local_variance of
+the reference are outside this path and are not re-implemented: when the reference package is
+importable next to this one, those methods are the reference's own, bound to this object
+(``__getattr__``), so ``pg("sklearn")``, ``pg.fit(...)`` etc. keep working on the GPU-built graph;
+without it they raise with a message that says so.
 """
 import operator
 
@@ -31,6 +34,16 @@ from .engine import get_engine
 from .protein import Protein
 
 _MISSING = "This sequence is not in the dataset."
+
+
+def _reference_class():
+    """The reference's own ``Prograph`` class when acmater/prograph is installed beside this package
+    (everything outside the graph-construction path stays its code), else None."""
+    try:
+        import prograph as _ref
+        return getattr(_ref, "Prograph", None)
+    except Exception:           # not installed, or one of its optional imports is missing
+        return None
 
 
 class Prograph:
@@ -129,12 +142,28 @@ class Prograph:
         return self.label_iter(label, **kwargs)
 
     def label_iter(self, label, **kwargs):
-        """A copy of one frame column (or of the whole frame for ``None``), prograph.py:185-202."""
-        if label in ("pytorch", "sklearn"):
-            raise NotImplementedError("the ML data adapters are outside the graph-construction path")
+        """A copy of one frame column (or of the whole frame for ``None``); "pytorch" / "sklearn" hand
+        over to the reference's data adapters (prograph.py:185-202)."""
+        if label == "pytorch":
+            return self.pytorch_dataloaders(**kwargs)
+        if label == "sklearn":
+            return self.sklearn_data(**kwargs)
         if label is None:
             return self.graph.copy()
         return self.graph[label].copy()
+
+    def __getattr__(self, name):
+        """Methods outside the graph-construction path (sklearn_data, pytorch_dataloaders, fit,
+        graph_to_networkx, dirichlet, local_variance, ...) are the reference's own, bound to this
+        object, when the reference package is importable."""
+        if name.startswith("__") or name in ("graph", "tokenized"):
+            raise AttributeError(name)
+        ref = _reference_class()
+        if ref is not None and hasattr(ref, name):
+            attr = getattr(ref, name)
+            return attr.__get__(self, type(self)) if hasattr(attr, "__get__") else attr
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}: it is outside the graph-construction "
+                             "path of prograph_b200 and the reference package (acmater/prograph) is not importable")
 
     def query(self, sequence):
         """Row index (or indices) for an int, str, token tuple, list or array (prograph.py:204-240)."""

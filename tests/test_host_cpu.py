@@ -434,3 +434,26 @@ def test_sharded_output_and_collective_agreement_over_gloo(tmp_path):
         assert int(z["code"]) == shard.NO_MEMORY and int(z["checks"]) >= 1
         rows_seen += rows
     assert rows_seen == n
+
+
+def test_methods_outside_the_path_come_from_the_reference_when_it_is_installed(monkeypatch):
+    """Prograph.__call__("sklearn") / fit / graph_to_networkx are not part of the path: they are looked
+    up on the reference's class (bound to our object) when `prograph` is importable, and fail with a
+    clear message when it is not.  Checked with a stand-in module -- no GPU, no construction."""
+    import types
+    from prograph_b200.prograph import Prograph
+    pg = object.__new__(Prograph)                       # no __init__: nothing here touches the device
+    pg.__dict__["graph"] = {"Sequence": "frame"}
+    monkeypatch.setitem(sys.modules, "prograph", None)  # import prograph -> ImportError
+    with pytest.raises(AttributeError, match="outside the graph-construction path"):
+        pg.sklearn_data()
+    with pytest.raises(AttributeError):
+        pg("sklearn")
+
+    class RefPrograph:
+        def sklearn_data(self, split=0.8):
+            return ("reference adapter", self.graph, split)
+
+    monkeypatch.setitem(sys.modules, "prograph", types.SimpleNamespace(Prograph=RefPrograph))
+    assert pg("sklearn", split=0.5) == ("reference adapter", {"Sequence": "frame"}, 0.5)
+    assert pg.sklearn_data() == ("reference adapter", {"Sequence": "frame"}, 0.8)
