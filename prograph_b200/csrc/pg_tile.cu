@@ -84,6 +84,7 @@ struct ElemParams {
   int p_int;             // integer exponent for VK_I64
   int similarity;
   int weight;            // hamming-values output kind
+  const int* only_if;    // optional device flag: run only when *only_if != 0 (the p = 1 rank-1 path declined)
 };
 
 // METRIC 0: minkowski, 1: hamming on values
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
   const int mg = tid / ET_N;  // 0..3
   const long long n0 = static_cast<long long>(blockIdx.x) * ET_N;
   const long long m0 = static_cast<long long>(blockIdx.y) * ET_M;
+  if (prm.only_if != nullptr && *prm.only_if == 0) return;
 
   // accumulators: fp32 for f16/f32 sums, double for f64, int64 for integer inputs / counts
   float accf[ET_MPT];
@@ -189,6 +191,93 @@ static int launch_elem(const ElemParams& prm, int pk_in, int pk_root, cudaStream
     else PG_EL(PK_GENERAL, PK_GENERAL);
   }
 #undef PG_EL
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+// =============================================================================
+// Minkowski p = 1: a rank-1 difference
+// =============================================================================
+// The reference takes no absolute value (minkowski.py:36): for p = 1 the "distance" is
+//   pow(sum(x - y), 1) = sum(x) - sum(y).
+// In int64 arithmetic that identity always holds (wrap-around included); in fp16 / float32 it holds
+// bit for bit when every value is an integer of magnitude <= 255 and D * 510 < 2^24 (each difference,
+// and the fp32 running sum, are then exact).  So: one pass of row sums (+ a validity flag for the
+// float types) and an outer difference written at HBM speed instead of an O(N * M * D) kernel; when the
+// flag says the rows are not small integers, the element-wise kernel runs instead (both are
+// launched, each looks at the flag: no host round trip).
+template <typename T>
+__global__ void row_sums_kernel(const T* __restrict__ X, long long row0, long long rows, int D, long long* __restrict__ sums,
+                                int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const T* src = X + static_cast<size_t>(row0 + r) * D;
+    long long acc = 0;
+    bool bad = false;
+    for (int c = lane; c < D; c += 32) {
+      if constexpr (sizeof(T) == 8) {          // int64
+        acc += static_cast<long long>(src[c]);
+      } else {
+        const float v = static_cast<float>(load_val<T>(src + c));
+        bad |= !(v == truncf(v) && fabsf(v) <= 255.0f);
+        acc += static_cast<long long>(v);
+      }
+    }
+    acc = warp_sum(acc);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(flag, 1);
+    if (lane == 0) sums[r] = acc;
+  }
+}
+
+template <int VK>
+__global__ void __launch_bounds__(256) mink1_tile_kernel(const long long* __restrict__ sx, long long N,
+                                                         const long long* __restrict__ sy, long long qrows, int similarity,
+                                                         void* out, long long ld, const int* __restrict__ flag) {
+  if (*flag != 0) return;
+  const long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (n >= N) return;
+  const long long x = sx[n];
+  const long long m_end = min(qrows, (static_cast<long long>(blockIdx.y) + 1) * 8);
+  for (long long m = static_cast<long long>(blockIdx.y) * 8; m < m_end; ++m) {
+    const long long S = x - __ldg(sy + m);
+    const size_t at = static_cast<size_t>(m) * ld + n;
+    if (VK == VK_F16) {
+      float d = rh(static_cast<float>(S));
+      if (similarity) d = rh(__fdiv_rn(1.0f, rh(1.0f + d)));
+      static_cast<__half*>(out)[at] = __float2half_rn(d);
+    } else {
+      float d = static_cast<float>(S);
+      if (similarity) d = __fdiv_rn(1.0f, 1.0f + d);
+      static_cast<float*>(out)[at] = d;
+    }
+  }
+}
+
+// Row sums + the rank-1 tile; returns the scratch block (to be freed on the stream by the caller,
+// after the element-wise kernel that may follow) and the device flag that kernel has to look at.
+template <typename T, int VK>
+static int launch_mink1(const T* X, long long N, const T* Y, long long q0, long long qrows, int D, int similarity, void* out,
+                        long long ld, void** scratch, int** flag_dev, cudaStream_t s) {
+  void* tmp = nullptr;
+  PG_CUDA(temp_alloc(&tmp, static_cast<size_t>(N + qrows) * 8 + 16, s));
+  *scratch = tmp;
+  long long* sx = static_cast<long long*>(tmp);
+  long long* sy = sx + N;
+  int* flag = reinterpret_cast<int*>(sy + qrows);
+  *flag_dev = flag;
+  PG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  const int threads = 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  row_sums_kernel<T><<<static_cast<unsigned>(std::min<long long>(cap, ceil_div(N * 32, threads))), threads, 0, s>>>(
+      X, 0, N, D, sx, flag);
+  PG_LAUNCH_CHECK();
+  row_sums_kernel<T><<<static_cast<unsigned>(std::min<long long>(cap, ceil_div(qrows * 32, threads))), threads, 0, s>>>(
+      Y, q0, qrows, D, sy, flag);
+  PG_LAUNCH_CHECK();
+  dim3 grid(static_cast<unsigned>(ceil_div(N, threads)), static_cast<unsigned>(ceil_div(qrows, 8)));
+  mink1_tile_kernel<VK><<<grid, threads, 0, s>>>(sx, N, sy, qrows, similarity, out, ld, flag);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -475,6 +564,35 @@ int pg_minkowski_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_
   prm.out = out; prm.ld = ld; prm.similarity = similarity;
   const double root = 1.0 / p;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p == 1.0 && D <= 32768 && qrows <= 8ll * 65535 && (dtype == PG_F16 || dtype == PG_F32 || dtype == PG_I64)) {
+    // no abs in the reference: p = 1 is sum(x) - sum(y), a rank-1 tile; the element-wise kernel is
+    // launched behind it and only runs if the float rows turn out not to be small integers
+    void* scratch = nullptr;
+    int* flag = nullptr;
+    int rc;
+    if (dtype == PG_I64) {
+      rc = launch_mink1<long long, VK_I64>(static_cast<const long long*>(X), N, static_cast<const long long*>(Y), q0, qrows, D,
+                                           similarity, out, ld, &scratch, &flag, s);
+    } else if (dtype == PG_F32) {
+      rc = launch_mink1<float, VK_F32>(static_cast<const float*>(X), N, static_cast<const float*>(Y), q0, qrows, D, similarity,
+                                       out, ld, &scratch, &flag, s);
+      if (rc == PG_OK) {
+        prm.p_f = prm.root_f = 1.0f;
+        prm.only_if = flag;
+        rc = launch_elem<float, VK_F32, 0>(prm, PK_ONE, PK_ONE, s);
+      }
+    } else {
+      rc = launch_mink1<__half, VK_F16>(static_cast<const __half*>(X), N, static_cast<const __half*>(Y), q0, qrows, D,
+                                        similarity, out, ld, &scratch, &flag, s);
+      if (rc == PG_OK) {
+        prm.p_f = prm.root_f = 1.0f;
+        prm.only_if = flag;
+        rc = launch_elem<__half, VK_F16, 0>(prm, PK_ONE, PK_ONE, s);
+      }
+    }
+    if (scratch != nullptr) cudaFreeAsync(scratch, s);
+    return rc;
+  }
   if (dtype == PG_F16) {
     // exp_scalar.to<Half>(): both exponents are rounded to fp16 before use
     prm.p_f = __half2float(__float2half_rn(static_cast<float>(p)));
