@@ -750,7 +750,8 @@ def run_query_block(args, eng, rank, world, timed, cores):
     n, L = args.n, args.length
     m = max(1024, n // 10)
     X = make_tokens(n, L, "mutational")
-    Q = make_tokens(m, L, "mutational", seed=1)
+    Qh = make_tokens(m, L, "mutational", seed=1)
+    Q = torch.from_numpy(Qh).to(eng.device)          # queries resident in HBM, like the library
     lib = query.Library(X)
     lib.packed()
     lib.gemm(255)
@@ -791,14 +792,14 @@ def run_query_block(args, eng, rank, world, timed, cores):
         if rank == 0:
             from oracle import c_oracle as CO
             sample = np.sort(np.random.default_rng(2).choice(m, size=16, replace=False))
-            D = CO.hamming_rows(CO.pack(np.concatenate([X, Q[sample]])), L, n + np.arange(len(sample)), threads=cores)[:, :n]
+            D = CO.hamming_rows(CO.pack(np.concatenate([X, Qh[sample]])), L, n + np.arange(len(sample)), threads=cores)[:, :n]
             D = D.astype(np.int64)
             sel = torch.from_numpy(sample).to(eng.device)
             ok &= bool(np.array_equal(out["hn"][0][sel].cpu().numpy(), D.argmin(axis=1))
                        and np.array_equal(out["hn"][1][sel].cpu().numpy(), D.min(axis=1))
                        and np.array_equal(out["hc"][sel].cpu().numpy(), (D <= 3).sum(axis=1)))
             few = sample[:4]
-            S2 = np.stack([((X.astype(np.int32) - Q[q].astype(np.int32)) ** 2).sum(axis=1, dtype=np.int64) for q in few])
+            S2 = np.stack([((X.astype(np.int32) - Qh[q].astype(np.int32)) ** 2).sum(axis=1, dtype=np.int64) for q in few])
             fsel = torch.from_numpy(few).to(eng.device)
             ok &= bool(np.array_equal(out["mn"][0][fsel].cpu().numpy(), S2.argmin(axis=1))
                        and np.array_equal(out["mn"][1][fsel].cpu().numpy(),

@@ -63,6 +63,14 @@ class Library:
         return self._dev[dtype]
 
 
+def _probe(a):
+    """A zero-size CPU tensor with the dtype of `a` (numpy array or tensor on any device): what the
+    dtype-promotion helpers of the distance modules need to see."""
+    if isinstance(a, torch.Tensor):
+        return torch.empty(0, dtype=a.dtype)
+    return torch.as_tensor(a[:0])
+
+
 def _as_library(lib):
     return lib if isinstance(lib, Library) else Library(lib)
 
@@ -96,7 +104,7 @@ def nearest(lib, queries, distance=hamming, group=None):
         except (OverflowError, L.Unsupported):
             part = None
     elif kind == "minkowski" and float(p) == 2.0 and lib.L <= eng.GEMM_MAX_WIDTH:
-        vk, max_token = gemm_value_kind(staged_dtype(torch.as_tensor(lib.data[:1]), torch.as_tensor(Qr[:1]), p))
+        vk, max_token = gemm_value_kind(staged_dtype(_probe(lib.data), _probe(Qr), p))
         if vk is not None:
             try:
                 g = lib.gemm(max_token)
@@ -176,10 +184,10 @@ def _tiles(lib, Q, distance, kind, p, similarity, whole=False):
             except (OverflowError, L.Unsupported):
                 pass
             from .distance.hamming import value_dtype
-            dt = value_dtype(torch.result_type(torch.as_tensor(lib.data[:1]), torch.as_tensor(Qb[:1])))
+            dt = value_dtype(torch.result_type(_probe(lib.data), _probe(Qb)))
             yield b0, eng.hamming_values_tile(lib.device(dt), eng.to_device(Qb, dt), 0, Qb.shape[0], similarity=similarity)
         elif kind == "minkowski":
-            dt = staged_dtype(torch.as_tensor(lib.data[:1]), torch.as_tensor(Qb[:1]), p)
+            dt = staged_dtype(_probe(lib.data), _probe(Qb), p)
             vk, max_token = gemm_value_kind(dt)
             if float(p) == 2.0 and vk is not None and lib.L <= eng.GEMM_MAX_WIDTH:
                 try:

@@ -237,3 +237,34 @@ def test_integration_stub_as_documented(eng):
     np.testing.assert_array_equal(np_(w), rw)
     with pytest.raises(OverflowError):
         ns["pack"](torch.full((4, 8), 40, dtype=torch.int64, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype", ["int64", "float16", "float32"])
+def test_minkowski_p1_rank_one_tile_and_its_fallback(eng, dtype):
+    """p = 1 without abs is sum(x) - sum(y) (minkowski.py:36): integer-valued rows take the rank-1 tile
+    (row sums + outer difference), rows with fractional or large values are recognised on the device
+    and take the element-wise kernel; both must give the reference's rounding chain bit for bit."""
+    from prograph_b200 import minkowski
+    rng = np.random.default_rng(5)
+    X = rng.integers(0, 21, size=(900, 256))
+    Y = rng.integers(0, 21, size=(70, 256))
+    cast = {"int64": np.int64, "float16": np.float16, "float32": np.float32}[dtype]
+    for sim in (False, True):
+        got = np_(minkowski(X.astype(cast), Y.astype(cast), p=1, similarity=sim))
+        want = O.minkowski(X.astype(cast), Y.astype(cast), p=1, similarity=sim)
+        assert got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want)
+    if dtype != "int64":
+        Xf = (rng.integers(-40, 40, size=(300, 7)) / 8.0).astype(cast)          # fractional: not a rank-1 case
+        Yf = (rng.integers(-40, 40, size=(33, 7)) / 8.0).astype(cast)
+        np.testing.assert_array_equal(np_(minkowski(Xf, Yf, p=1)), O.minkowski(Xf, Yf, p=1))
+        Xb = X.astype(cast) * 20                                                  # integers, but beyond 255
+        got = np_(minkowski(Xb, Y.astype(cast), p=1))
+        want = O.minkowski(Xb, Y.astype(cast), p=1)
+        if dtype == "float32":
+            np.testing.assert_allclose(got, want, rtol=3e-7)                      # fp32 sum order (DESIGN.md §2)
+        else:
+            np.testing.assert_array_equal(got, want)
+    else:
+        big = rng.integers(-2**40, 2**40, size=(50, 9))
+        np.testing.assert_array_equal(np_(minkowski(big, big[:7], p=1)), O.minkowski(big, big[:7], p=1))
