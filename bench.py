@@ -783,7 +783,8 @@ def run_query_block(args, eng, rank, world, timed, cores):
         lambda: query.tile(lib, Q, 0, 1024, distance=minkowski, similarity=True), 1024.0 * n)
     sub = min(1000, m)
     for p in (1, 3):
-        run(f"minkowski p={p} ({sub}, {n}) float32 tile (element-wise kernel, no-abs quirk)",
+        how = "rank-1 tile: sum(x) - sum(y), no abs in the reference" if p == 1 else "element-wise kernel, no-abs quirk"
+        run(f"minkowski p={p} ({sub}, {n}) float32 tile ({how})",
             lambda p=p: query.tile(lib, Q, 0, sub, distance=functools.partial(minkowski, p=p)), float(sub) * n, reps=1)
     block = {"workload": f"C5: {m} queries (mutational, default_rng(1)) x {n}-row mutational library, L={L}; query rows "
                          f"sharded over {world} GPU(s), library layouts resident", "cases": cases}
