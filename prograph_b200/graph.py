@@ -409,10 +409,18 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     force = os.environ.get("PG_EPS_SYM")
     use_sym = n >= SYM_EPS_MIN_ROWS if force is None else force not in ("0", "")
     if use_sym:
-        # every rank samples the same rows -> the same degree, capacity and branch on all of them
+        # the ranks split the sample rows and add their counts up -> the same degree, capacity and
+        # branch on all of them
         parts = world if sharded else 1
         with phase("sample"):
-            degree = eng.hamming_eps_mean_degree(packed, *_eps_sample(n), packed, lut)
+            s0, srows = _eps_sample(n)
+            if sharded and srows >= 2 * world:
+                a, b = s0 + rank * srows // world, s0 + (rank + 1) * srows // world
+                total = eng.hamming_eps_degrees(packed, a, b - a, packed, lut).sum().reshape(1)
+                torch.distributed.all_reduce(total, group=group)
+                degree = float(total.item()) / srows
+            else:
+                degree = eng.hamming_eps_mean_degree(packed, s0, srows, packed, lut)
         capacity = int(1.5 * degree * n / parts) + (4 << 20)
         if (degree > SYM_EPS_MAX_DEGREE and force is None) or capacity * parts >= (1 << 31):
             use_sym = False        # dense graph, or more keys than one radix sort takes

@@ -126,9 +126,12 @@ class CheckerEngine:
             out[r, :len(u)] = u
         return torch.from_numpy(out)
 
-    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
+    def hamming_eps_degrees(self, own, row0, rows, stream, lut):
         indptr, _, _ = self.hamming_eps(own, row0, rows, stream, lut)
-        return float(indptr[-1]) / rows
+        return indptr[1:] - indptr[:-1]
+
+    def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
+        return float(self.hamming_eps_degrees(own, row0, rows, stream, lut).sum()) / rows
 
     # symmetric epsilon sweep: edge keys row << 40 | column << 12 | distance (the checker's own packing)
     def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):

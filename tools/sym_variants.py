@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--boot", default="8192")
     ap.add_argument("--eps", type=int, default=0)
     ap.add_argument("--world", type=int, default=1, help="emulate one rank of a `world`-GPU build")
-    ap.add_argument("--rank", type=int, default=0)
+    ap.add_argument("--rank", type=int, default=0, help="-1: every rank of `world` in turn")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--stats", action="store_true")
     args = ap.parse_args()
@@ -44,8 +44,10 @@ def main():
     lut = graph.distance_lut(tab.words * 32, operator.le, args.eps, False) if args.eps else None
     if args.stats:
         os.environ["PG_SYM_STATS"] = "1"
-    for pair, delay, band, boot in itertools.product(args.pair.split(","), args.delay.split(","), args.band.split(","),
-                                                     args.boot.split(",")):
+    ranks = list(range(args.world)) if args.rank < 0 else [args.rank]
+    for pair, delay, band, boot, rank in itertools.product(args.pair.split(","), args.delay.split(","), args.band.split(","),
+                                                           args.boot.split(","), ranks):
+        args.rank = rank
         os.environ["PG_SYM_PAIR"], os.environ["PG_SYM_BAND_MB"], os.environ["PG_SYM_BOOT"] = pair, band, boot
         os.environ["PG_SYM_DELAY"] = delay
         best = None
