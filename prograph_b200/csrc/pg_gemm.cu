@@ -16,15 +16,11 @@
 //     K=32 per instruction), which halves the bytes streamed out of L2 per pair: with one A tile
 //     the MMA issuer waited for B tiles 37 % of the time (every SM pulled 20 B/clk, 5.8 TB/s in
 //     aggregate, profiles/r1_ncu_notes.md);
-//   * four 128-column TMEM accumulators (all of TMEM): accumulator a + 2*(t & 1) holds A tile a x B
-//     tile t, so the MMAs of tile t+1 run while the epilogues of tile t drain;
-//   * warp roles: 16 epilogue warps in four groups -- group (a, par) drains the accumulator of A tile
-//     a for the B tiles of parity par (thread = TMEM lane = query row; the two groups of an A tile
-//     share one sorted list per row behind a shared-memory lock that only the rare insertion path
-//     takes), 1 producer lane, 1 MMA-issuing lane (which also owns the TMEM allocation); the dataset
-//     norms ride along with the B tiles into a small shared-memory ring.  Eight epilogue warps kept
-//     the tensor pipe 40 % busy: two warps per scheduler cannot hide the TMEM-load and barrier
-//     latencies of a 2-instructions-per-element epilogue (profiles/r2_notes.md);
+//   * four 128-column TMEM accumulators (all of TMEM): two per A tile, so the MMAs of tile t+1 run
+//     while the epilogues of tile t drain;
+//   * warp roles: 8 epilogue warps in two groups, group g owns A tile g (thread = TMEM lane =
+//     query row, one sorted list per row), 1 producer lane, 1 MMA-issuing lane (which also owns the
+//     TMEM allocation); the dataset norms ride along with the B tiles into a small shared-memory ring;
 //   * epilogues: materialised tile (minkowski.py:36-40) or fused kNN: a candidate test in
 //     S-space against a per-row integer threshold (min + one vote per 32 columns), rare
 //     warp-cooperative insertion into a sorted (value, index) list in shared memory; the
@@ -38,11 +34,9 @@ constexpr int GA = 2;           // A tiles per CTA: every B tile is multiplied w
 constexpr int GROWS = GM * GA;  // query rows per CTA
 constexpr int GN = 128;         // dataset rows per B tile (MMA N)
 constexpr int GSTAGES = 4;      // deepest B ring (fewer stages when the lists need the room)
-constexpr int GEPI_WARPS = 16;  // four epilogue groups of four warps: (A tile, parity of the B tile)
-constexpr int GTHREADS = (GEPI_WARPS + 2) * 32;   // + producer warp + MMA warp
-constexpr int GPROD_WARP = GEPI_WARPS;
-constexpr int GMMA_WARP = GEPI_WARPS + 1;
-constexpr int GCH = 16;         // accumulator columns per tcgen05.ld (keeps the epilogue under 112 registers)
+constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp + MMA warp
+constexpr int GPROD_WARP = 8;
+constexpr int GMMA_WARP = 9;
 constexpr int GPROD_LANES = 8;  // lanes of the producer warp that each copy a slice of a B tile
 constexpr int GACC = 4;         // TMEM accumulators (4 x 128 columns = all 512): two per A tile
 constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
@@ -88,16 +82,6 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -212,21 +196,6 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
-// Epsilon modes walk the tiles as 0, h, 1, h+1, ... (h = half the tiles) so that the two epilogue
-// groups of an A tile (even / odd positions) each own one contiguous half of the dataset: a group's
-// hits of a row are then a contiguous, ascending part of that row's edge list.
-template <int MODE>
-__device__ __forceinline__ int tile_at(int pos, int n_tiles) {
-  if (MODE == GM_COUNT || MODE == GM_FILL) {
-    const int half = (n_tiles + 1) >> 1;
-    return (pos & 1) ? half + (pos >> 1) : (pos >> 1);
-  }
-  return pos;
-}
-__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 template <int VK, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -243,11 +212,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   uint64_t* acc_empty = acc_full + GACC;      // [GACC] epilogue has drained the accumulator
   uint64_t* a_full = acc_empty + GACC;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
-  unsigned* klock = tmem_holder + 2;      // [8] list locks: (A tile, lane quarter), shared by the two parities
-  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2 + 8 + 2);   // [GROWS][k1], 8-byte aligned
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(tmem_holder + 2);   // [GROWS][k1]
   int* slists = reinterpret_cast<int*>(lists + GROWS * prm.k1);                         // [GROWS][k1] exact sums
-  // tile mode (no lists): per-warp 32 x 20-word transpose buffers, 16-byte aligned
-  uint32_t* tile_stage = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_holder + 12) + 15) & ~uintptr_t(15));
+  // tile mode (no lists): per-warp 32 x 36-word transpose buffers, 16-byte aligned
+  uint32_t* tile_stage = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_holder + 2) + 15) & ~uintptr_t(15));
   const bool tile_fast = MODE == GM_TILE && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0 &&
                          ((static_cast<size_t>(prm.ld) * (VK == GV_F16 ? 2 : 4)) & 15) == 0;
 
@@ -269,7 +237,6 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
     mbar_init(a_full, 1);
     fence_mbar_init();
   }
-  if (tid < 8) klock[tid] = 0u;
   if (warp == GMMA_WARP) tmem_alloc(tmem_holder, GACC * GN);  // all 512 columns: four int32 accumulators
   tc_fence_before();
   __syncthreads();
@@ -296,13 +263,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
         // the norms of tile t live in slot t % GNORM_SLOTS until both epilogues of tile t are done;
         // slot reuse (tile t + 8) is ordered behind the MMAs of tile t + 8 - stages >= t + 4, which
         // themselves wait for the epilogues of tile t + 2
-        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN,
+        bulk_g2s(sNorm + (t % GNORM_SLOTS) * GN, prm.normB + static_cast<size_t>(t_begin + t) * GN,
                  GN * 4, &full[stage]);
       }
       __syncwarp();
       if (lane < GPROD_LANES) {
         bulk_g2s(sB + static_cast<size_t>(stage) * tile_bytes + lane * slice,
-                 prm.B + static_cast<size_t>(t_begin + tile_at<MODE>(t, n_tiles)) * GN * K + lane * slice, slice,
+                 prm.B + static_cast<size_t>(t_begin + t) * GN * K + lane * slice, slice,
                  &full[stage]);
       }
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -336,45 +303,42 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       }
     }
   } else {
-    // ---------------- epilogue: group (a, par) = A tile a, B tiles of parity par -------------------
-    const int atile = (warp >> 2) & 1;           // A tile of this warp
-    const int par = warp >> 3;                   // it drains the tiles t with (t & 1) == par
-    const int acc = atile + GA * par;            // ... which the MMA issuer puts into this accumulator
+    // ---------------- epilogue: warp group g owns A tile g; thread = TMEM lane = query row ---------
+    const int group = warp >> 2;                 // A tile of this group
+    const int r_loc = tid & (GM - 1);            // query row within the A tile = TMEM lane
     const int qwarp = warp & 3;                  // TMEM lane quarter this warp may read
-    const int r_loc = qwarp * 32 + lane;         // query row within the A tile = TMEM lane
-    const long long row = row0 + atile * GM + r_loc;
+    const long long row = row0 + group * GM + r_loc;
     const bool valid = row < prm.M;
     const int nq = valid ? prm.normA[row] : 0;
-    unsigned long long* my_list = lists + (static_cast<size_t>(atile) * GM + r_loc) * prm.k1;
-    int* my_slist = slists + (static_cast<size_t>(atile) * GM + r_loc) * prm.k1;
-    unsigned* my_lock = klock + atile * 4 + qwarp;
+    unsigned long long* my_list = lists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
     int tprime = valid ? 0x7fffffff : static_cast<int>(0x80000000);   // candidate iff (nx - 2 dot) < tprime
     if (MODE == GM_KNN) {
-      if (par == 0)
-        for (int j = 0; j < prm.k1; ++j) { my_list[j] = ~0ull; my_slist[j] = 0x7fffffff; }
-      named_barrier_sync(1 + atile * 4 + qwarp, 64);      // the partner warp sees the initialised lists
+      int* my_slist = slists + (static_cast<size_t>(group) * GM + r_loc) * prm.k1;
+      for (int j = 0; j < prm.k1; ++j) { my_list[j] = ~0ull; my_slist[j] = 0x7fffffff; }
+      __syncwarp();
     }
-    long long ecur = 0;    // epsilon modes: hits counted / next edge slot of this (row, half of the dataset)
-    if (MODE == GM_FILL && valid) ecur = prm.indptr[row] + (par ? prm.group_counts[row] : 0);
+    long long ecur = 0;    // epsilon modes: hits counted / next edge slot of this (row, group)
+    if (MODE == GM_FILL && valid) ecur = prm.indptr[row];
     const int eoff = nq - prm.s_lo;    // in range iff (unsigned)(v + eoff) <= s_span
     const uint32_t lane_base = static_cast<uint32_t>(qwarp * 32) << 16;
-    for (int t = par; t < n_tiles; t += 2) {
+    for (int t = 0; t < n_tiles; ++t) {
+      const int acc = group + GA * (t & 1);    // group g drains accumulators g and g + 2 in turn
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
-      const long long col_tile = static_cast<long long>(t_begin + tile_at<MODE>(t, n_tiles)) * GN;
+      const long long col_tile = static_cast<long long>(t_begin + t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
-      uint32_t dotbuf[2][GCH];
-      tmem_ld16_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
+      uint32_t dotbuf[2][32];
+      tmem_ld32_issue(tmem_base + lane_base + acc * GN, dotbuf[0]);
 #pragma unroll
-      for (int c = 0; c < GN / GCH; ++c) {
-        uint32_t (&dot)[GCH] = dotbuf[c & 1];
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t (&dot)[32] = dotbuf[c & 1];
         tmem_ld_wait();
-        if (c + 1 < GN / GCH) tmem_ld16_issue(tmem_base + lane_base + acc * GN + (c + 1) * GCH, dotbuf[(c + 1) & 1]);
-        const long long col0 = col_tile + c * GCH;
-        int v[GCH];   // nx - 2 dot  (S = nq + v)
-        const int4* np = reinterpret_cast<const int4*>(nrm + c * GCH);
+        if (c + 1 < GN / 32) tmem_ld32_issue(tmem_base + lane_base + acc * GN + (c + 1) * 32, dotbuf[(c + 1) & 1]);
+        const long long col0 = col_tile + c * 32;
+        int v[32];   // nx - 2 dot  (S = nq + v)
+        const int4* np = reinterpret_cast<const int4*>(nrm + c * 32);
 #pragma unroll
-        for (int g = 0; g < GCH / 4; ++g) {
+        for (int g = 0; g < 8; ++g) {
           const int4 nx = np[g];
           v[4 * g + 0] = nx.x - 2 * static_cast<int>(dot[4 * g + 0]);
           v[4 * g + 1] = nx.y - 2 * static_cast<int>(dot[4 * g + 1]);
@@ -382,14 +346,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
           v[4 * g + 3] = nx.w - 2 * static_cast<int>(dot[4 * g + 3]);
         }
         if (MODE == GM_TILE) {
-          // Thread = query row holds GCH consecutive columns.  Storing them directly makes every
-          // store instruction touch 32 rows; instead the warp transposes its 32 x GCH block through
-          // shared memory and writes whole 64-byte (fp16: 32-byte) row segments, eight (sixteen)
-          // rows per instruction.
-          constexpr int WPR = VK == GV_F16 ? GCH / 2 : GCH;    // 32-bit words per row segment
+          // Thread = query row holds 32 consecutive columns.  Storing them directly makes every
+          // store instruction touch 32 rows (32 half-used sectors); instead the warp transposes the
+          // 32 x 32 block through shared memory and writes whole 128-byte (fp16: 64-byte) row
+          // segments, four (eight) rows per instruction.
+          constexpr int WPR = VK == GV_F16 ? 16 : 32;          // 32-bit words per row segment
           constexpr int STRIDE = WPR + 4;                      // conflict-free for 16-byte accesses
-          uint32_t* stg = tile_stage + static_cast<size_t>(warp) * 32 * (GCH + 4);
-          const bool fast = tile_fast && col0 + GCH <= prm.N;  // warp-uniform
+          uint32_t* stg = tile_stage + static_cast<size_t>(warp) * 32 * 36;
+          const bool fast = tile_fast && col0 + 32 <= prm.N;   // warp-uniform
           if (fast) {
             uint32_t* mine = stg + lane * STRIDE;
 #pragma unroll
@@ -407,7 +371,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
             __syncwarp();
             constexpr int LPR = WPR / 4;                       // lanes per row segment
             constexpr int RPI = 32 / LPR;                      // rows per store instruction
-            const long long wrow0 = row0 + atile * GM + qwarp * 32;
+            const long long wrow0 = row0 + group * GM + qwarp * 32;
 #pragma unroll
             for (int it = 0; it < 32 / RPI; ++it) {
               const int rr = it * RPI + lane / LPR;
@@ -424,24 +388,24 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
             if (VK == GV_F16) {
               unsigned short* o = static_cast<unsigned short*>(prm.out) + at;
 #pragma unroll
-              for (int j = 0; j < GCH; ++j)
+              for (int j = 0; j < 32; ++j)
                 if (col0 + j < prm.N) o[j] = static_cast<unsigned short>(value_bits<VK>(nq + v[j], sim));
             } else {
               uint32_t* o = static_cast<uint32_t*>(prm.out) + at;
 #pragma unroll
-              for (int j = 0; j < GCH; ++j)
+              for (int j = 0; j < 32; ++j)
                 if (col0 + j < prm.N) o[j] = value_bits<VK>(nq + v[j], sim);
             }
           }
         } else if (MODE == GM_COUNT) {
-          int cnt = 0;
+          int c32 = 0;
 #pragma unroll
-          for (int j = 0; j < GCH; ++j) cnt += (static_cast<unsigned>(v[j] + eoff) <= prm.s_span) ? 1 : 0;
-          ecur += valid ? cnt : 0;
+          for (int j = 0; j < 32; ++j) c32 += (static_cast<unsigned>(v[j] + eoff) <= prm.s_span) ? 1 : 0;
+          ecur += valid ? c32 : 0;
         } else if (MODE == GM_FILL) {
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < GCH; ++j) {
+            for (int j = 0; j < 32; ++j) {
               if (static_cast<unsigned>(v[j] + eoff) <= prm.s_span) {
                 prm.out_idx[ecur] = col0 + j;
                 const uint32_t bits = value_bits<VK>(nq + v[j], sim);
@@ -452,32 +416,21 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
             }
           }
         } else {
-          // tree minimum of the GCH values (a linear chain would serialise the dependent mins)
-          int m4[GCH / 4];
+          // tree minimum of the 32 values (a linear chain would serialise 31 dependent mins)
+          int m8[8];
 #pragma unroll
-          for (int g = 0; g < GCH / 4; ++g) m4[g] = min(min(v[4 * g], v[4 * g + 1]), min(v[4 * g + 2], v[4 * g + 3]));
-          const int best = min(min(m4[0], m4[1]), min(m4[2], m4[3]));
+          for (int g = 0; g < 8; ++g) m8[g] = min(min(v[4 * g], v[4 * g + 1]), min(v[4 * g + 2], v[4 * g + 3]));
+          const int best = min(min(min(m8[0], m8[1]), min(m8[2], m8[3])), min(min(m8[4], m8[5]), min(m8[6], m8[7])));
           if (__any_sync(0xffffffffu, best < tprime)) {
-            // rare: the rows' lists are shared with the warp of the other tile parity -- take the
-            // (A tile, lane quarter) lock, refresh the threshold from the list, insert, release
-            if (lane == 0) {
-              while (atomicCAS(my_lock, 0u, 1u) != 0u) __nanosleep(20);
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (valid) tprime = min(tprime, my_slist[prm.k1 - 1] - nq);
-            unsigned long long* warp_lists = lists + (static_cast<size_t>(atile) * GM + qwarp * 32) * prm.k1;
-            int* warp_slists = slists + (static_cast<size_t>(atile) * GM + qwarp * 32) * prm.k1;
+            unsigned long long* warp_lists = lists + (static_cast<size_t>(group) * GM + qwarp * 32) * prm.k1;
+            int* warp_slists = slists + (static_cast<size_t>(group) * GM + qwarp * 32) * prm.k1;
 #pragma unroll
-            for (int j = 0; j < GCH; ++j) {
+            for (int j = 0; j < 32; ++j) {
               const unsigned cand = __ballot_sync(0xffffffffu, v[j] < tprime);
               if (cand)
                 tprime = gemm_knn_serve<VK>(cand, nq + v[j], static_cast<unsigned>(col0 + j), warp_lists, warp_slists,
                                             prm.k1, sim, lane, nq, tprime);
             }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) atomicExch(my_lock, 0u);
           }
         }
       }
@@ -485,12 +438,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
-    if (MODE == GM_COUNT && valid) prm.group_counts[static_cast<size_t>(par) * prm.M + row] = ecur;
+    if (MODE == GM_COUNT && valid) prm.group_counts[row] = ecur;      // second half of the scratch stays 0
     if (MODE == GM_KNN) {
-      // both parities are done with this quarter's rows: one list per row (ascending, keys unique)
-      __threadfence_block();
-      named_barrier_sync(1 + atile * 4 + qwarp, 64);
-      if (par == 0 && valid) {
+      // every row has one list (ascending, keys unique): drop, widen, write out
+      __syncwarp();
+      if (valid) {
         for (int j = prm.drop; j < prm.drop + prm.k; ++j) {
           const unsigned long long key = j < prm.k1 ? my_list[j] : ~0ull;
           const size_t at = static_cast<size_t>(row) * prm.k + (j - prm.drop);
@@ -581,7 +533,7 @@ __global__ void gemm_pack_kernel<__half>(const __half* __restrict__ tokens, long
 
 static size_t gemm_smem_bytes(int K, int k1, int stages, bool tile_mode = false) {
   return static_cast<size_t>(GM) * K * (GA + stages) + GNORM_SLOTS * GN * 4 + (2 * GSTAGES + 2 * GACC + 1) * sizeof(uint64_t) +
-         64 + static_cast<size_t>(GROWS) * k1 * 12 + (tile_mode ? 16 + GEPI_WARPS * 32 * (GCH + 4) * 4 : 0);
+         16 + static_cast<size_t>(GROWS) * k1 * 12 + (tile_mode ? 16 + 8 * 32 * 36 * 4 : 0);
 }
 
 template <int VK, int MODE>
