@@ -7,6 +7,8 @@
 //                            block prefix-sum compaction
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "pg_common.cuh"
 
 namespace pg {
@@ -69,10 +71,11 @@ template <> struct Compute<long long> { using type = long long; };
 template <typename T> __device__ __forceinline__ typename Compute<T>::type load_val(const T* p) { return *p; }
 template <> __device__ __forceinline__ float load_val<__half>(const __half* p) { return __half2float(*p); }
 
-constexpr int ET_N = 64;   // dataset rows per CTA
-constexpr int ET_M = 32;   // query rows per CTA
-constexpr int ET_D = 32;   // components per staging chunk
-constexpr int ET_MPT = 8;  // queries per thread
+constexpr int ET_N = 128;  // dataset rows per CTA
+constexpr int ET_M = 64;   // query rows per CTA
+constexpr int ET_D = 16;   // components per staging chunk
+constexpr int ET_NPT = 4;  // dataset rows per thread (consecutive: one 128-bit shared-memory load for 4-byte types)
+constexpr int ET_MPT = 8;  // queries per thread (the same for all lanes of a warp: broadcast loads)
 
 struct ElemParams {
   const void* X; long long N;
@@ -87,91 +90,122 @@ struct ElemParams {
   const int* only_if;    // optional device flag: run only when *only_if != 0 (the p = 1 rank-1 path declined)
 };
 
-// METRIC 0: minkowski, 1: hamming on values
+// One term of the sum for a (dataset value x, query value y) pair, in the accumulator's type.
+template <typename CT, int VK, int METRIC, int PKIN>
+__device__ __forceinline__ CT elem_term(CT x, CT y, const ElemParams& prm) {
+  if constexpr (METRIC == 1) {
+    return (x != y) ? CT(1) : CT(0);
+  } else if constexpr (VK == VK_F16) {
+    return pow_f16<PKIN>(rh(x - y), prm.p_f);
+  } else if constexpr (VK == VK_F32) {
+    return pow_f32<PKIN>(x - y, prm.p_f);
+  } else if constexpr (VK == VK_F64) {
+    return pow_f64<PKIN>(x - y, prm.p_d);
+  } else {
+    const long long d = x - y;
+    if constexpr (PKIN == PK_ONE) return d;
+    else if constexpr (PKIN == PK_TWO) return d * d;
+    else if constexpr (PKIN == PK_THREE) return (d * d) * d;
+    else return ipow(d, prm.p_int);
+  }
+}
+
+// METRIC 0: minkowski, 1: hamming on values.  A 256-thread CTA computes a 128 (dataset rows) x 64
+// (queries) block; a thread owns 4 consecutive dataset rows x 8 queries = 32 running sums in
+// registers.  The operands are staged through shared memory component-major (Xs[c][row]): per
+// component a thread reads its 4 dataset values with one vector load and the 8 query values with
+// broadcast loads -- 3 loads for 32 terms (the first version read 9 scalars for 8 terms).  Every pair
+// still adds its terms in ascending component order, so the rounding chain of minkowski.py:36-40 is
+// untouched.
 template <typename T, int VK, int METRIC, int PKIN, int PKROOT>
 __global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
   using CT = typename Compute<T>::type;
-  __shared__ CT Xs[ET_N][ET_D + 1];
-  __shared__ CT Ys[ET_M][ET_D];
+  // the accumulator type: fp32 for f16 / f32 sums, double for f64, int64 for integer inputs / counts
+  using AT = typename std::conditional<METRIC == 1, long long, CT>::type;
+  __shared__ __align__(16) CT Xs[ET_D][ET_N];
+  __shared__ __align__(16) CT Ys[ET_D][ET_M];
   const T* X = static_cast<const T*>(prm.X);
   const T* Y = static_cast<const T*>(prm.Y);
   const int tid = threadIdx.x;
-  const int nl = tid % ET_N;
-  const int mg = tid / ET_N;  // 0..3
+  const int tx = tid & 31;   // lanes: dataset rows 4*tx .. 4*tx+3
+  const int ty = tid >> 5;   // warps: queries 8*ty .. 8*ty+7
   const long long n0 = static_cast<long long>(blockIdx.x) * ET_N;
   const long long m0 = static_cast<long long>(blockIdx.y) * ET_M;
   if (prm.only_if != nullptr && *prm.only_if == 0) return;
 
-  // accumulators: fp32 for f16/f32 sums, double for f64, int64 for integer inputs / counts
-  float accf[ET_MPT];
-  double accd[ET_MPT];
-  long long acci[ET_MPT];
+  AT acc[ET_MPT][ET_NPT];
 #pragma unroll
-  for (int i = 0; i < ET_MPT; ++i) { accf[i] = 0.f; accd[i] = 0.0; acci[i] = 0; }
+  for (int i = 0; i < ET_MPT; ++i)
+#pragma unroll
+    for (int j = 0; j < ET_NPT; ++j) acc[i][j] = AT(0);
 
   for (int d0 = 0; d0 < prm.D; d0 += ET_D) {
-    for (int i = tid; i < ET_N * ET_D; i += 256) {
-      const int r = i / ET_D, c = i % ET_D;
+    // stage: thread (row = tid % 128, half = tid / 128) reads 8 consecutive components of one dataset
+    // row; thread (q = tid % 64, quarter = tid / 64) reads 4 consecutive components of one query row
+    {
+      const int r = tid & (ET_N - 1), c0 = (tid >> 7) * 8;
       const long long n = n0 + r;
-      CT v = CT(0);
-      if (n < prm.N && d0 + c < prm.D) v = load_val<T>(X + static_cast<size_t>(n) * prm.D + d0 + c);
-      Xs[r][c] = v;
-    }
-    for (int i = tid; i < ET_M * ET_D; i += 256) {
-      const int r = i / ET_D, c = i % ET_D;
-      const long long m = m0 + r;
-      CT v = CT(0);
-      if (m < prm.qrows && d0 + c < prm.D) v = load_val<T>(Y + static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c);
-      Ys[r][c] = v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        CT v = CT(0);
+        if (n < prm.N && d0 + c < prm.D) v = load_val<T>(X + static_cast<size_t>(n) * prm.D + d0 + c);
+        Xs[c][r] = v;
+      }
+      const int q = tid & (ET_M - 1), qc0 = (tid >> 6) * 4;
+      const long long m = m0 + q;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = qc0 + k;
+        CT v = CT(0);
+        if (m < prm.qrows && d0 + c < prm.D) v = load_val<T>(Y + static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c);
+        Ys[c][q] = v;
+      }
     }
     __syncthreads();
     const int dn = min(ET_D, prm.D - d0);
     for (int c = 0; c < dn; ++c) {
-      const CT x = Xs[nl][c];
+      CT x[ET_NPT], y[ET_MPT];
 #pragma unroll
-      for (int i = 0; i < ET_MPT; ++i) {
-        const CT y = Ys[mg * ET_MPT + i][c];
-        if (METRIC == 1) {
-          acci[i] += (x != y) ? 1 : 0;
-        } else if (VK == VK_F16) {
-          const float diff = rh(static_cast<float>(x) - static_cast<float>(y));
-          accf[i] += pow_f16<PKIN>(diff, prm.p_f);
-        } else if (VK == VK_F32) {
-          accf[i] += pow_f32<PKIN>(static_cast<float>(x) - static_cast<float>(y), prm.p_f);
-        } else if (VK == VK_F64) {
-          accd[i] += pow_f64<PKIN>(static_cast<double>(x) - static_cast<double>(y), prm.p_d);
-        } else {
-          acci[i] += ipow(static_cast<long long>(x) - static_cast<long long>(y), prm.p_int);
-        }
-      }
+      for (int j = 0; j < ET_NPT; ++j) x[j] = Xs[c][tx * ET_NPT + j];
+#pragma unroll
+      for (int i = 0; i < ET_MPT; ++i) y[i] = Ys[c][ty * ET_MPT + i];
+#pragma unroll
+      for (int i = 0; i < ET_MPT; ++i)
+#pragma unroll
+        for (int j = 0; j < ET_NPT; ++j)
+          acc[i][j] += static_cast<AT>(elem_term<CT, VK, METRIC, PKIN>(x[j], y[i], prm));
     }
     __syncthreads();
   }
 
-  const long long n = n0 + nl;
-  if (n >= prm.N) return;
 #pragma unroll
   for (int i = 0; i < ET_MPT; ++i) {
-    const long long m = m0 + mg * ET_MPT + i;
+    const long long m = m0 + ty * ET_MPT + i;
     if (m >= prm.qrows) continue;
-    const size_t at = static_cast<size_t>(m) * prm.ld + n;
-    if (METRIC == 1) {
-      if (prm.weight == PG_W_I64) static_cast<long long*>(prm.out)[at] = acci[i];
-      else if (prm.weight == PG_W_SIM_F32) static_cast<float*>(prm.out)[at] = sim_f32(static_cast<int>(acci[i]));
-      else static_cast<int*>(prm.out)[at] = static_cast<int>(acci[i]);
-    } else if (VK == VK_F16) {
-      float d = pow_f16<PKROOT>(rh(accf[i]), prm.root_f);
-      if (prm.similarity) d = rh(__fdiv_rn(1.0f, rh(1.0f + d)));
-      static_cast<__half*>(prm.out)[at] = __float2half_rn(d);
-    } else if (VK == VK_F32 || VK == VK_I64) {
-      const float s = VK == VK_I64 ? static_cast<float>(acci[i]) : accf[i];
-      float d = pow_f32<PKROOT>(s, prm.root_f);
-      if (prm.similarity) d = __fdiv_rn(1.0f, 1.0f + d);
-      static_cast<float*>(prm.out)[at] = d;
-    } else {
-      double d = pow_f64<PKROOT>(accd[i], prm.root_d);
-      if (prm.similarity) d = 1.0 / (1.0 + d);
-      static_cast<double*>(prm.out)[at] = d;
+#pragma unroll
+    for (int j = 0; j < ET_NPT; ++j) {
+      const long long n = n0 + tx * ET_NPT + j;
+      if (n >= prm.N) continue;
+      const size_t at = static_cast<size_t>(m) * prm.ld + n;
+      if constexpr (METRIC == 1) {
+        if (prm.weight == PG_W_I64) static_cast<long long*>(prm.out)[at] = acc[i][j];
+        else if (prm.weight == PG_W_SIM_F32) static_cast<float*>(prm.out)[at] = sim_f32(static_cast<int>(acc[i][j]));
+        else static_cast<int*>(prm.out)[at] = static_cast<int>(acc[i][j]);
+      } else if constexpr (VK == VK_F16) {
+        float d = pow_f16<PKROOT>(rh(acc[i][j]), prm.root_f);
+        if (prm.similarity) d = rh(__fdiv_rn(1.0f, rh(1.0f + d)));
+        static_cast<__half*>(prm.out)[at] = __float2half_rn(d);
+      } else if constexpr (VK == VK_F32 || VK == VK_I64) {
+        const float sum = static_cast<float>(acc[i][j]);
+        float d = pow_f32<PKROOT>(sum, prm.root_f);
+        if (prm.similarity) d = __fdiv_rn(1.0f, 1.0f + d);
+        static_cast<float*>(prm.out)[at] = d;
+      } else {
+        double d = pow_f64<PKROOT>(acc[i][j], prm.root_d);
+        if (prm.similarity) d = 1.0 / (1.0 + d);
+        static_cast<double*>(prm.out)[at] = d;
+      }
     }
   }
 }
@@ -618,6 +652,7 @@ int pg_minkowski_tile(const void* X, int64_t N, const void* Y, int64_t M, int64_
     const int pkr = pow_kind(prm.root_f);
     if (pkr == PK_SQRT) return launch_elem<long long, VK_I64, 0>(prm, PK_TWO, PK_SQRT, s);
     if (pkr == PK_ONE) return launch_elem<long long, VK_I64, 0>(prm, PK_ONE, PK_ONE, s);
+    if (prm.p_int == 3) return launch_elem<long long, VK_I64, 0>(prm, PK_THREE, PK_GENERAL, s);
     return launch_elem<long long, VK_I64, 0>(prm, PK_GENERAL, PK_GENERAL, s);
   }
   set_error("minkowski tile: unsupported dtype %d", dtype);
