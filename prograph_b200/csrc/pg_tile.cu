@@ -122,8 +122,14 @@ __global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
   using CT = typename Compute<T>::type;
   // the accumulator type: fp32 for f16 / f32 sums, double for f64, int64 for integer inputs / counts
   using AT = typename std::conditional<METRIC == 1, long long, CT>::type;
-  __shared__ __align__(16) CT Xs[ET_D][ET_N];
-  __shared__ __align__(16) CT Ys[ET_D][ET_M];
+  // fp16 rows with one of the multiply-only exponents run their per-element chain in native half2
+  // arithmetic: fp16 subtract / multiply round exactly like "compute in fp32, round to fp16" (the
+  // reference's chain; double rounding through a format of >= 2p+2 bits is innocuous), two pairs per
+  // instruction, no conversion round trips.  The running sum stays fp32, as torch.sum keeps it.
+  constexpr bool HALF2 = VK == VK_F16 && METRIC == 0 && (PKIN == PK_ONE || PKIN == PK_TWO || PKIN == PK_THREE);
+  using ST = typename std::conditional<HALF2, __half, CT>::type;      // staging type in shared memory
+  __shared__ __align__(16) ST Xs[ET_D][ET_N];
+  __shared__ __align__(16) ST Ys[ET_D][ET_M];
   const T* X = static_cast<const T*>(prm.X);
   const T* Y = static_cast<const T*>(prm.Y);
   const int tid = threadIdx.x;
@@ -148,8 +154,11 @@ __global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = c0 + k;
-        CT v = CT(0);
-        if (n < prm.N && d0 + c < prm.D) v = load_val<T>(X + static_cast<size_t>(n) * prm.D + d0 + c);
+        ST v = ST(0);
+        if (n < prm.N && d0 + c < prm.D) {
+          if constexpr (HALF2) v = X[static_cast<size_t>(n) * prm.D + d0 + c];
+          else v = load_val<T>(X + static_cast<size_t>(n) * prm.D + d0 + c);
+        }
         Xs[c][r] = v;
       }
       const int q = tid & (ET_M - 1), qc0 = (tid >> 6) * 4;
@@ -157,24 +166,41 @@ __global__ void __launch_bounds__(256) elem_tile_kernel(const ElemParams prm) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = qc0 + k;
-        CT v = CT(0);
-        if (m < prm.qrows && d0 + c < prm.D) v = load_val<T>(Y + static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c);
+        ST v = ST(0);
+        if (m < prm.qrows && d0 + c < prm.D) {
+          if constexpr (HALF2) v = Y[static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c];
+          else v = load_val<T>(Y + static_cast<size_t>(prm.q0 + m) * prm.D + d0 + c);
+        }
         Ys[c][q] = v;
       }
     }
     __syncthreads();
     const int dn = min(ET_D, prm.D - d0);
     for (int c = 0; c < dn; ++c) {
-      CT x[ET_NPT], y[ET_MPT];
+      if constexpr (HALF2) {
+        const __half2 x01 = *reinterpret_cast<const __half2*>(&Xs[c][tx * ET_NPT]);
+        const __half2 x23 = *reinterpret_cast<const __half2*>(&Xs[c][tx * ET_NPT + 2]);
 #pragma unroll
-      for (int j = 0; j < ET_NPT; ++j) x[j] = Xs[c][tx * ET_NPT + j];
+        for (int i = 0; i < ET_MPT; ++i) {
+          const __half2 yy = __half2half2(Ys[c][ty * ET_MPT + i]);
+          __half2 a = __hsub2(x01, yy), b = __hsub2(x23, yy);
+          if (PKIN == PK_TWO) { a = __hmul2(a, a); b = __hmul2(b, b); }
+          if (PKIN == PK_THREE) { a = __hmul2(__hmul2(a, a), a); b = __hmul2(__hmul2(b, b), b); }
+          const float2 fa = __half22float2(a), fb = __half22float2(b);
+          acc[i][0] += fa.x; acc[i][1] += fa.y; acc[i][2] += fb.x; acc[i][3] += fb.y;
+        }
+      } else {
+        CT x[ET_NPT], y[ET_MPT];
 #pragma unroll
-      for (int i = 0; i < ET_MPT; ++i) y[i] = Ys[c][ty * ET_MPT + i];
+        for (int j = 0; j < ET_NPT; ++j) x[j] = Xs[c][tx * ET_NPT + j];
 #pragma unroll
-      for (int i = 0; i < ET_MPT; ++i)
+        for (int i = 0; i < ET_MPT; ++i) y[i] = Ys[c][ty * ET_MPT + i];
 #pragma unroll
-        for (int j = 0; j < ET_NPT; ++j)
-          acc[i][j] += static_cast<AT>(elem_term<CT, VK, METRIC, PKIN>(x[j], y[i], prm));
+        for (int i = 0; i < ET_MPT; ++i)
+#pragma unroll
+          for (int j = 0; j < ET_NPT; ++j)
+            acc[i][j] += static_cast<AT>(elem_term<CT, VK, METRIC, PKIN>(x[j], y[i], prm));
+      }
     }
     __syncthreads();
   }

@@ -457,3 +457,32 @@ def test_methods_outside_the_path_come_from_the_reference_when_it_is_installed(m
     monkeypatch.setitem(sys.modules, "prograph", types.SimpleNamespace(Prograph=RefPrograph))
     assert pg("sklearn", split=0.5) == ("reference adapter", {"Sequence": "frame"}, 0.5)
     assert pg.sklearn_data() == ("reference adapter", {"Sequence": "frame"}, 0.8)
+
+
+def test_bench_workload_helpers():
+    """bench.py's synthetic inputs and its accounting of evaluated pairs (host-only): the GB1-style
+    library has the known epsilon-graph answers of SURVEY.md 8c, the query set shares the library's
+    wild type, and the pair count of the symmetric sweep equals what the library's planner hands out."""
+    import bench
+    from prograph_b200.engine import sym_plan
+    G = bench.make_gb1_library()
+    assert G.shape == (160_000, 56) and G.dtype == np.uint8 and G.min() >= 1 and G.max() <= 20
+    assert len({row.tobytes() for row in G[::997]}) == len(G[::997])
+    d = (G[:4000] != G[0]).sum(1)
+    # rows 0..3999: site 0 fixed, site 1 over its first 10 residues, sites 2 and 3 over all 20
+    assert np.array_equal(np.bincount(d, minlength=4), [1, 9 + 19 + 19, 9 * 19 * 2 + 19 * 19, 9 * 19 * 19])
+    M = bench.make_tokens(5000, 64, "mutational")
+    Q = bench.make_tokens(300, 64, "mutational", seed=1)
+    wt = np.array([np.bincount(M[:, c]).argmax() for c in range(64)])
+    assert ((Q != wt).sum(1) <= 8).all() and ((M != wt).sum(1) <= 8).all() and not np.array_equal(M[:300], Q)
+    assert np.array_equal(bench.make_tokens(100, 8, "uniform"), np.random.default_rng(0).integers(1, 21, size=(100, 8), dtype=np.uint8))
+    n, boot, words = 300_000, 8192, 8
+    it = sym_plan(n, 5, words, boot, 0, 1, 0, grid=296)
+    tile = 512 // words
+    planned = 0
+    for rb, t0, t1, _, _ in it.astype(np.int64):
+        rows = min(n, rb * 256 + 256) - rb * 256
+        planned += int(rows * (min(n, t1 * tile) - t0 * tile))
+    exact = bench.triangle_pairs(n, boot, (0, n))
+    # the planner deals whole tiles: a block's first tile may start before its diagonal / the bootstrap edge
+    assert exact <= planned <= exact + (-(-n // 256)) * 256 * tile
