@@ -268,3 +268,32 @@ def test_minkowski_p1_rank_one_tile_and_its_fallback(eng, dtype):
     else:
         big = rng.integers(-2**40, 2**40, size=(50, 9))
         np.testing.assert_array_equal(np_(minkowski(big, big[:7], p=1)), O.minkowski(big, big[:7], p=1))
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_fp16_chain_in_native_half_arithmetic(eng, p):
+    """The element-wise fp16 path runs its per-element chain (x - y, powers) in native half2
+    arithmetic.  With two components per row the fp32 sum has no order to disagree on, so the result
+    must equal the reference's rounding chain bit for bit -- including overflow to inf, subnormal
+    differences, negative bases under the odd exponents (NaN roots), signed zeros."""
+    from prograph_b200 import minkowski
+    rng = np.random.default_rng(40 + p)
+    X = (rng.standard_normal((3000, 2)) * rng.choice([1e-4, 0.1, 1.0, 30.0, 300.0], size=(3000, 1))).astype(np.float16)
+    Y = (rng.standard_normal((257, 2)) * rng.choice([1e-4, 0.1, 1.0, 30.0, 300.0], size=(257, 1))).astype(np.float16)
+    X[:4] = np.array([[65504, 65504], [-65504, 1], [6e-8, -6e-8], [0.0, -0.0]], dtype=np.float16)
+    Y[:2] = np.array([[-65504, -65504], [6e-8, 6e-8]], dtype=np.float16)
+    for sim in (False, True):
+        with np.errstate(all="ignore"):
+            want = O.minkowski(X, Y, p=p, similarity=sim)
+        got = np_(minkowski(X, Y, p=p, similarity=sim))
+        assert got.dtype == np.float16
+        np.testing.assert_array_equal(got.view(np.uint16)[~np.isnan(want)], want.view(np.uint16)[~np.isnan(want)])
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+    # wide rows of small integers: every partial sum is exact, so the order cannot matter either
+    Xi = rng.integers(-6, 7, size=(700, 300)).astype(np.float16)
+    Yi = rng.integers(-6, 7, size=(65, 300)).astype(np.float16)
+    with np.errstate(all="ignore"):
+        want = O.minkowski(Xi, Yi, p=p)
+    got = np_(minkowski(Xi, Yi, p=p))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
