@@ -287,8 +287,12 @@ def test_fp16_chain_in_native_half_arithmetic(eng, p):
             want = O.minkowski(X, Y, p=p, similarity=sim)
         got = np_(minkowski(X, Y, p=p, similarity=sim))
         assert got.dtype == np.float16
-        np.testing.assert_array_equal(got.view(np.uint16)[~np.isnan(want)], want.view(np.uint16)[~np.isnan(want)])
+        ok = ~np.isnan(want)
         assert np.array_equal(np.isnan(got), np.isnan(want))
+        ulp = np.abs(got.view(np.int16)[ok].astype(np.int32) - want.view(np.int16)[ok].astype(np.int32))
+        # p = 1, 2: bit for bit.  p = 3: the cube root is powf(s, fp16(1/3)) on both sides, but torch's pow and
+        # CUDA's powf are different implementations: 1 fp16 ulp, as stated in DESIGN.md §2 (only the root).
+        assert ulp.max() <= (1 if p == 3 else 0), int(ulp.max())
     # wide rows of small integers: every partial sum is exact, so the order cannot matter either
     Xi = rng.integers(-6, 7, size=(700, 300)).astype(np.float16)
     Yi = rng.integers(-6, 7, size=(65, 300)).astype(np.float16)
@@ -296,4 +300,6 @@ def test_fp16_chain_in_native_half_arithmetic(eng, p):
         want = O.minkowski(Xi, Yi, p=p)
     got = np_(minkowski(Xi, Yi, p=p))
     assert np.array_equal(np.isnan(got), np.isnan(want))
-    np.testing.assert_array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+    ok = ~np.isnan(want)
+    ulp = np.abs(got.view(np.int16)[ok].astype(np.int32) - want.view(np.int16)[ok].astype(np.int32))
+    assert ulp.max() <= (1 if p == 3 else 0), int(ulp.max())
