@@ -155,19 +155,6 @@ static __device__ __noinline__ void sym_serve_col(const SymParams& prm, long lon
 
 constexpr int kMaxSymList = 32;   // longest list the symmetric sweep keeps (k + drop)
 
-// knn_insert_coop for lists of at most 32 entries (every list of the symmetric sweep): one entry
-// per lane, one ballot -- a third of the instructions of the three-round version.
-__device__ __forceinline__ unsigned knn_insert_coop32(unsigned long long* list, int k1, unsigned long long key, int lane) {
-  const bool in = lane < k1;
-  const unsigned long long cur = in ? list[lane] : ~0ull;
-  const unsigned long long prev = (in && lane > 0) ? list[lane - 1] : 0ull;
-  const int pos = __popc(__ballot_sync(0xffffffffu, in && cur < key));
-  __syncwarp();
-  if (in && lane >= pos) list[lane] = (lane == pos) ? key : prev;
-  __syncwarp();
-  return static_cast<unsigned>(list[k1 - 1] >> 32);
-}
-
 // Row side: the warp inserts the candidates of one stream row (column `col`) into the
 // shared-memory lists of its own rows; returns the lane's updated filter.
 static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists, int k1, unsigned cand, unsigned dv,
@@ -179,7 +166,7 @@ static __device__ __noinline__ int sym_serve_row(unsigned long long* warp_lists,
     cand &= cand - 1;
     const unsigned dd = __shfl_sync(0xffffffffu, dv, src);
     const unsigned long long key = (static_cast<unsigned long long>(dd) << 32) | col;
-    const unsigned t_new = knn_insert_coop32(warp_lists + static_cast<size_t>(src) * k1, k1, key, lane);
+    const unsigned t_new = knn_insert_coop(warp_lists + static_cast<size_t>(src) * k1, k1, key, lane);
     if (lane == src) tau = min(tau_seed, t_new == 0xffffffffu ? kTauInf : static_cast<int>(t_new));
   }
   return tau;
