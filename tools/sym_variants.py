@@ -1,10 +1,8 @@
 #!/usr/bin/env python3
 """A/B timing of the symmetric sweeps' schedule knobs in ONE process (the library reads its
-environment at every call): L2 band size, bootstrap columns, emulated ranks.  (--pair / --delay
-selected the paired-lane and delayed-vote instantiations measured in profiles/r2_notes.md; both lost
-and were removed, the flags are accepted and ignored.)
+environment at every call): L2 band size, bootstrap columns, emulated ranks.
 
-    python tools/sym_variants.py --n 1000000 --band 0,24,40 [--eps 1] [--world 8 --rank 0]
+    python tools/sym_variants.py --n 1000000 --band 0,24,40 [--eps 1] [--world 8 --rank -1] [--stats]
 """
 import argparse
 import itertools
@@ -24,8 +22,8 @@ def main():
     ap.add_argument("--length", type=int, default=256)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--dist", default="uniform")
-    ap.add_argument("--pair", default="0,1")
-    ap.add_argument("--delay", default="0")
+    ap.add_argument("--pair", default="0", help=argparse.SUPPRESS)      # instantiations measured in round 2 and removed
+    ap.add_argument("--delay", default="0", help=argparse.SUPPRESS)
     ap.add_argument("--band", default="0,24")
     ap.add_argument("--boot", default="8192")
     ap.add_argument("--eps", type=int, default=0)
