@@ -349,10 +349,20 @@ class CudaEngine:
 
     def check_edge_budget(self, nnz):
         """An epsilon graph can be dense (the reference would run out of host memory the same way):
-        refuse before allocating instead of taking the GPU down."""
-        free, _ = torch.cuda.mem_get_info(self.device)
+        refuse before allocating instead of taking the GPU down.  cudaMemGetInfo costs anything from
+        0.1 to several milliseconds (measured: tools/host_gaps.py), which is a third of a small graph's
+        build, so the driver is only asked when the request is a sizeable part of what was free at the
+        last look (refreshed at least every few seconds)."""
+        import time
         need = nnz * 16
-        if need > 0.9 * (free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)):
+        now = time.monotonic()
+        hint = getattr(self, "_free_hint", None)
+        if hint is not None and now - hint[1] < 5.0 and need < 0.2 * hint[0]:
+            return
+        free, _ = torch.cuda.mem_get_info(self.device)
+        avail = free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        self._free_hint = (avail, now)
+        if need > 0.9 * avail:
             raise MemoryError(f"the requested graph has {nnz} edges ({need / 2**30:.1f} GiB as int64 index/weight "
                               f"pairs) and does not fit in device memory; lower eps or build a kNN graph")
 
