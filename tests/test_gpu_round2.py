@@ -303,3 +303,13 @@ def test_fp16_chain_in_native_half_arithmetic(eng, p):
     ok = ~np.isnan(want)
     ulp = np.abs(got.view(np.int16)[ok].astype(np.int32) - want.view(np.int16)[ok].astype(np.int32))
     assert ulp.max() <= (1 if p == 3 else 0), int(ulp.max())
+
+
+def test_edge_budget_refuses_graphs_that_cannot_fit(eng):
+    """A graph whose CSR cannot fit in device memory is refused with MemoryError before anything is
+    allocated (the C4-M eps=2 graph of the bench: 1.6e10 edges = 257 GB); small requests pass, also
+    when the cached free-memory reading is used."""
+    eng.check_edge_budget(1000)
+    eng.check_edge_budget(1000)
+    with pytest.raises(MemoryError, match="does not fit in device memory"):
+        eng.check_edge_budget(16_071_968_078)
