@@ -19,12 +19,16 @@
 //   * four 128-column TMEM accumulators (all of TMEM): two per A tile, so the MMAs of tile t+1 run
 //     while the epilogues of tile t drain;
 //   * warp roles: 8 epilogue warps in two groups, group g owns A tile g (thread = TMEM lane =
-//     query row, one sorted list per row), 1 producer lane, 1 MMA-issuing lane (which also owns the
-//     TMEM allocation); the dataset norms ride along with the B tiles into a small shared-memory ring;
+//     query row, one sorted list per row), 1 producer lane, one MMA-issuing lane PER A TILE (a single
+//     thread issuing all sixteen MMAs of a B tile was the bottleneck: with descriptors rebuilt per
+//     instruction it needed ~130 clocks per MMA, the tensor pipe 64); the dataset norms ride along
+//     with the B tiles into a small shared-memory ring;
 //   * epilogues: materialised tile (minkowski.py:36-40) or fused kNN: a candidate test in
 //     S-space against a per-row integer threshold (min + one vote per 32 columns), rare
 //     warp-cooperative insertion into a sorted (value, index) list in shared memory; the
 //     N x N matrix never reaches HBM.
+#include <cstdlib>
+
 #include "pg_sweep.cuh"   // knn_insert_coop, kMaxListRounds
 
 namespace pg {
@@ -34,9 +38,9 @@ constexpr int GA = 2;           // A tiles per CTA: every B tile is multiplied w
 constexpr int GROWS = GM * GA;  // query rows per CTA
 constexpr int GN = 128;         // dataset rows per B tile (MMA N)
 constexpr int GSTAGES = 4;      // deepest B ring (fewer stages when the lists need the room)
-constexpr int GTHREADS = 320;   // 8 epilogue warps (two groups) + producer warp + MMA warp
+constexpr int GTHREADS = 352;   // 8 epilogue warps (two groups) + producer warp + one MMA warp per A tile
 constexpr int GPROD_WARP = 8;
-constexpr int GMMA_WARP = 9;
+constexpr int GMMA_WARP = 9;    // warps 9 and 10: the MMA issuers of A tile 0 and 1 (warp 9 owns the TMEM allocation)
 constexpr int GPROD_LANES = 8;  // lanes of the producer warp that each copy a slice of a B tile
 constexpr int GACC = 4;         // TMEM accumulators (4 x 128 columns = all 512): two per A tile
 constexpr int GNORM_SLOTS = 8;  // ring of per-tile dataset norms (512 B each)
@@ -121,6 +125,8 @@ struct GemmParams {
   const uint8_t* B; const int* normB; long long N;       // dataset (stream rows)
   int K;                                                 // padded width, multiple of 32
   int stages;                                            // depth of the B ring (3 or 4)
+  int debug;                                             // experiments (PG_GEMM_DEBUG): 1 = epilogues only hand the accumulator back
+  int issuers;                                           // MMA-issuing warps: 1 (both A tiles) or 2 (one per A tile)
   int similarity;
   // tile
   void* out; long long ld;
@@ -196,7 +202,7 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
-template <int VK, int MODE>
+template <int VK, int MODE, int ISSUERS>
 __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_constant__ GemmParams prm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int K = prm.K;
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
   const bool sim = prm.similarity != 0;
 
   if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ISSUERS); }   // one commit per issuer
     for (int a = 0; a < GACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
     mbar_init(a_full, 1);
     fence_mbar_init();
@@ -274,32 +280,62 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       }
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == GMMA_WARP) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+  } else if (warp >= GMMA_WARP) {
+    // ---------------- MMA issuers ----------------
+    // issuers == 2: warp GMMA_WARP + a multiplies A tile a with every B tile (short lists / queries: the
+    // MMA side alone reaches 71 % of the tensor peak instead of 58 %); issuers == 1: warp GMMA_WARP
+    // issues for both A tiles (long lists: measured 346 ms against 401 ms for the 1 M x 1 M k=16 graph).
+    const int a_first = warp - GMMA_WARP;
+    if (lane == 0 && a_first < ISSUERS) {
       // instruction descriptor: D=S32, A=B=UINT8, K-major both, N=128, M=128
       const uint32_t idesc = (2u << 4) | (static_cast<uint32_t>(GN >> 3) << 17) | (static_cast<uint32_t>(GM >> 4) << 24);
       const uint32_t sbo = static_cast<uint32_t>(K / 16) * 128u;
       mbar_wait_poll(a_full, 0);
+      // Descriptors are built ONCE: a k-step advances the start address by 256 bytes (16 descriptor
+      // units), a ring stage by tile_bytes.  Rebuilding them for every instruction (two 64-bit shift /
+      // or chains) cost the issuing thread more clocks per MMA than the tensor pipe needs to execute one.
+      const uint64_t adesc0 = umma_desc(smem_u32(sA), 128, sbo);
+      const uint64_t bdesc0 = umma_desc(smem_u32(sB), 128, sbo);
+      const uint32_t stage_units = tile_bytes >> 4;
+      const int ksteps = K / 32;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_poll(&full[stage], phase);
-        const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(stage) * tile_bytes);
+      if constexpr (ISSUERS == 1) {
+        const uint64_t adesc1 = adesc0 + stage_units;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait_poll(&full[stage], phase);
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage) * stage_units;
 #pragma unroll
-        for (int a = 0; a < GA; ++a) {
-          const int acc = a + GA * (t & 1);               // A tile a alternates between accumulators a and a + 2
+          for (int a = 0; a < GA; ++a) {
+            const int acc = a + GA * (t & 1);               // A tile a alternates between accumulators a and a + 2
+            mbar_wait_poll(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            const uint64_t adesc = a == 0 ? adesc0 : adesc1;
+            const uint32_t d_addr = tmem_base + acc * GN;
+            umma_i8(d_addr, adesc, bdesc, idesc, 0u);
+#pragma unroll 4
+            for (int j = 1; j < ksteps; ++j) umma_i8(d_addr, adesc + 16u * j, bdesc + 16u * j, idesc, 1u);
+            umma_commit(&acc_full[acc]);    // this A tile's accumulator is complete
+          }
+          umma_commit(&empty[stage]);       // the stage may be refilled once all MMAs reading it are done
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      } else {
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(a_first) * stage_units;
+        for (int t = 0; t < n_tiles; ++t) {
+          const int acc = a_first + GA * (t & 1);
+          mbar_wait_poll(&full[stage], phase);
           mbar_wait_poll(&acc_empty[acc], ((t >> 1) & 1) ^ 1u);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + static_cast<size_t>(a) * tile_bytes);
-          for (int j = 0; j < K / 32; ++j) {
-            umma_i8(tmem_base + acc * GN, umma_desc(a_addr + j * 256, 128, sbo), umma_desc(b_addr + j * 256, 128, sbo),
-                    idesc, j > 0 ? 1u : 0u);
-          }
-          umma_commit(&acc_full[acc]);    // this A tile's accumulator is complete
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage) * stage_units;
+          const uint32_t d_addr = tmem_base + acc * GN;
+          umma_i8(d_addr, adesc, bdesc, idesc, 0u);
+#pragma unroll 4
+          for (int j = 1; j < ksteps; ++j) umma_i8(d_addr, adesc + 16u * j, bdesc + 16u * j, idesc, 1u);
+          umma_commit(&acc_full[acc]);      // this A tile's accumulator is complete
+          umma_commit(&empty[stage]);       // the stage may be refilled once BOTH issuers' MMAs have read it
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&empty[stage]);       // the stage may be refilled once all MMAs reading it are done
-        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -325,6 +361,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) mink_gemm_kernel(const __grid_con
       const int acc = group + GA * (t & 1);    // group g drains accumulators g and g + 2 in turn
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
+      if (prm.debug & 1) {                    // timing experiment: how fast is the MMA side on its own?
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        continue;
+      }
       const long long col_tile = static_cast<long long>(t_begin + t) * GN;
       const int* nrm = sNorm + (t % GNORM_SLOTS) * GN;
       uint32_t dotbuf[2][32];
@@ -536,9 +578,25 @@ static size_t gemm_smem_bytes(int K, int k1, int stages, bool tile_mode = false)
          16 + static_cast<size_t>(GROWS) * k1 * 12 + (tile_mode ? 16 + 8 * 32 * 36 * 4 : 0);
 }
 
+template <int VK, int MODE, int ISSUERS>
+static int launch_gemm_issuers(GemmParams prm, cudaStream_t s);
+
+// One MMA-issuing warp (both A tiles, 320 threads) or two (one per A tile, 352 threads).  Two issuers
+// lift the MMA side from 58 % to 71 % of the tensor peak and win where the epilogue is light (k = 1
+// queries: 1 M x 1 M in 207 ms instead of 227 ms); with long lists the extra warp costs more than it
+// gives (k = 16: 346 ms with one issuer, 397-401 ms with two).  PG_GEMM_ISSUERS overrides.
 template <int VK, int MODE>
 static int launch_gemm(GemmParams prm, cudaStream_t s) {
-  auto kern = mink_gemm_kernel<VK, MODE>;
+  int issuers = (MODE == GM_KNN && prm.k1 <= 4) ? 2 : 1;
+  if (const char* ev = std::getenv("PG_GEMM_ISSUERS")) issuers = std::atoi(ev) == 2 ? 2 : 1;
+  return issuers == 2 ? launch_gemm_issuers<VK, MODE, 2>(prm, s) : launch_gemm_issuers<VK, MODE, 1>(prm, s);
+}
+
+template <int VK, int MODE, int ISSUERS>
+static int launch_gemm_issuers(GemmParams prm, cudaStream_t s) {
+  auto kern = mink_gemm_kernel<VK, MODE, ISSUERS>;
+  if (const char* ev = std::getenv("PG_GEMM_DEBUG")) prm.debug = std::atoi(ev);
+  prm.issuers = ISSUERS;
   // wide rows / long lists: give up ring stages (down to 2) before giving up the fused path
   size_t smem = 0;
   for (prm.stages = GSTAGES; prm.stages >= 2; --prm.stages) {
@@ -556,7 +614,7 @@ static int launch_gemm(GemmParams prm, cudaStream_t s) {
     if (want > 65535) want = 65535;
     gy = static_cast<unsigned>(want < 1 ? 1 : want);
   }
-  kern<<<dim3(gx, gy), GTHREADS, smem, s>>>(prm);
+  kern<<<dim3(gx, gy), ISSUERS == 2 ? GTHREADS : GTHREADS - 32, smem, s>>>(prm);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
