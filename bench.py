@@ -609,6 +609,11 @@ def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
         dev = host.to(eng.device)
         row0, rows = shard.row_range(n, rank, world)
         lut = graph.distance_lut(words * 32, operator.le, eps, False)
+        # what the build sweeps: the residue positions that are not constant over the library
+        # (graph.informative_table); the rooflines below count the lane-ops of THAT width
+        swept = graph.informative_table(eng, eng.pack(dev))
+        words_swept, cols_swept = swept.words, swept.L
+        del swept
         res = {}
 
         def step():
@@ -637,7 +642,7 @@ def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
         # sweep launches per step: [degree sample, symmetric sweep] or [sample, count(, fill)] or [count]
         per = max(1, len(sw) // reps)
         main_ms = max(sum(sw[i::per]) / reps for i in range(per)) if sw else None
-        case = {"name": name, "n": n, "L": L, "eps": eps, "mode": mode, "ms_per_build": ms,
+        case = {"name": name, "n": n, "L": L, "columns_swept": cols_swept, "eps": eps, "mode": mode, "ms_per_build": ms,
                 "gpairs_per_s": float(n) * n / (ms * 1e-3) / 1e9, "phases_ms": ph}
         if mode == "csr":
             indptr, idx, w = res["csr"]
@@ -645,16 +650,16 @@ def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
             deg = indptr[1:] - indptr[:-1]
             symmetric = "csr" in ph                       # the key-sort phase only exists on the symmetric path
             if symmetric:
-                band = (0, n) if world == 1 else eng.sym_band(n, words, 0, 0, world)
+                band = (0, n) if world == 1 else eng.sym_band(n, words_swept, 0, 0, world)
                 evaluated = triangle_pairs(n, 0, band)
             else:
                 evaluated = float(shard.row_range(n, 0, world)[1]) * n          # per launch (count, and fill if it ran)
             csr_bytes = nnz * 16.0 + (n + 1) * 8.0
             csr_ms = ph.get("csr") if symmetric else None
             case.update({"nnz": nnz, "path": "symmetric sweep + key sort" if symmetric else "one-sided count / fill",
-                         "roofline_sweep": ({"bound": "int-alu", "achieved": 7.0 * words * evaluated / (main_ms * 1e-3) / 1e12,
+                         "roofline_sweep": ({"bound": "int-alu", "achieved": 7.0 * words_swept * evaluated / (main_ms * 1e-3) / 1e12,
                                              "peak": int_peak / 1e12, "unit": "Tlane-op/s",
-                                             "frac": 7.0 * words * evaluated / (main_ms * 1e-3) / int_peak,
+                                             "frac": 7.0 * words_swept * evaluated / (main_ms * 1e-3) / int_peak,
                                              "kernel_ms": main_ms, "pairs_evaluated_per_launch": evaluated}
                                             if main_ms else None),
                          "roofline_csr": ({"bound": "hbm", "achieved": csr_bytes / (csr_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -696,7 +701,7 @@ def run_eps_block(args, eng, rank, world, timed, max_over_ranks, cores):
             n_rows = 0
             if rank == 0:
                 from oracle import c_oracle as CO
-                srows = sample_rows(n, world, eng, words, 0, count=oracle_rows, seed=11)
+                srows = sample_rows(n, world, eng, words_swept, 0, count=oracle_rows, seed=11)
                 D = CO.hamming_rows(CO.pack(tokens), L, srows, threads=cores)
                 keep = (D <= eps) & (D > 0)                          # prograph.py:736
                 if mode == "csr":

@@ -313,6 +313,17 @@ int pg_mutant_bool(const uint32_t* table, int64_t N, int planes, int words, int 
                    const uint32_t* ref, uint8_t* out, void* stream);
 /* any_bits[w] = OR_n mut[n][w]  (calc_mutated_positions, :494-505) */
 int pg_mutant_any(const uint32_t* mut, int64_t N, int words, uint32_t* any_bits, void* stream);
+/* Informative columns of a table swept against itself (build_graph, prograph.py:726-765):
+ * a residue position at which every row carries the same token adds 0 to every pairwise
+ * Hamming distance (hamming.py:34), so the sweeps may run on the other positions only.
+ * varying[p*words + w] = OR_n (table[n][p][w] ^ table[0][p][w])  (device, planes*words words;
+ * OR over p = bit l set <=> position l is not constant). */
+int pg_varying_columns(const uint32_t* table, int64_t N, int planes, int words,
+                       uint32_t* varying, void* stream);
+/* out[n][p][w2] bit b = table[n][p][.] bit cols[32*w2 + b] (cols: device int32[out_words*32],
+ * -1 = padding -> 0); out has pg_packed_rows(N) rows, pad rows are zeroed. */
+int pg_compact_columns(const uint32_t* table, int64_t N, int planes, int words,
+                       const int32_t* cols, uint32_t* out, int out_words, void* stream);
 /* row selection: flag[n] = dist_ok & pos_ok with
  *   dist_ok = dist_lut == NULL or bit popc(mut[n]) of dist_lut set       (:300-308)
  *   pos_ok  = pos_mode 0: true

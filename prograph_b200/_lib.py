@@ -73,6 +73,8 @@ SIGNATURES = {
     "pg_mutant_bits": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "pg_mutant_bool": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "pg_mutant_any": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "pg_varying_columns": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    "pg_compact_columns": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp]),
     "pg_select_rows": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pg_flag_indices": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "pg_distance_hist": (_i, [_vp, _i64, _i, _vp, _vp]),

@@ -122,6 +122,85 @@ __global__ void distance_hist_kernel(const uint32_t* __restrict__ mut, long long
     if (sh[i]) atomicAdd(reinterpret_cast<unsigned long long*>(hist + i), static_cast<unsigned long long>(sh[i]));
 }
 
+// Informative columns.  A thread walks the table with a stride that is a multiple of the row length,
+// so it always meets the same (plane, word) position: one register accumulator of x ^ row 0, OR-ed
+// per block in shared memory, then one global atomic per position and block (skipped when the bits
+// are already there).  HBM-bound: reads the table once.
+template <typename V>
+__device__ __forceinline__ void or_into(uint32_t* dst, const V& v);
+template <>
+__device__ __forceinline__ void or_into<uint32_t>(uint32_t* dst, const uint32_t& v) {
+  if (v) atomicOr(dst, v);
+}
+template <>
+__device__ __forceinline__ void or_into<uint4>(uint32_t* dst, const uint4& v) {
+  if (v.x) atomicOr(dst + 0, v.x);
+  if (v.y) atomicOr(dst + 1, v.y);
+  if (v.z) atomicOr(dst + 2, v.z);
+  if (v.w) atomicOr(dst + 3, v.w);
+}
+__device__ __forceinline__ uint32_t xor_or(uint32_t acc, uint32_t a, uint32_t b) { return acc | (a ^ b); }
+__device__ __forceinline__ uint4 xor_or(uint4 acc, uint4 a, uint4 b) {
+  return make_uint4(acc.x | (a.x ^ b.x), acc.y | (a.y ^ b.y), acc.z | (a.z ^ b.z), acc.w | (a.w ^ b.w));
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) varying_columns_kernel(const V* __restrict__ table, long long total, int row_elems,
+                                                              long long stride, uint32_t* __restrict__ varying) {
+  extern __shared__ uint32_t sh_var[];                       // [row_elems * words per V]
+  constexpr int VW = sizeof(V) / 4;
+  for (int i = threadIdx.x; i < row_elems * VW; i += blockDim.x) sh_var[i] = 0;
+  __syncthreads();
+  const long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (g < stride) {
+    const int pos = static_cast<int>(g % row_elems);
+    const V ref = __ldg(table + pos);
+    V acc = {};
+    for (long long e = g; e < total; e += stride) acc = xor_or(acc, __ldcs(table + e), ref);
+    or_into<V>(sh_var + pos * VW, acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < row_elems * VW; i += blockDim.x) {
+    const uint32_t v = sh_var[i];
+    if (v && (__ldcg(varying + i) & v) != v) atomicOr(varying + i, v);
+  }
+}
+
+// One thread per (row, output word): bit b of every plane comes from source column cols[32*w2 + b].
+template <int P>
+__global__ void __launch_bounds__(256) compact_columns_kernel(const uint32_t* __restrict__ table, long long N,
+                                                              long long rows_padded, int words,
+                                                              const int* __restrict__ cols, uint32_t* __restrict__ out,
+                                                              int out_words) {
+  extern __shared__ int sh_cols[];                           // [out_words * 32]
+  for (int i = threadIdx.x; i < out_words * 32; i += blockDim.x) sh_cols[i] = __ldg(cols + i);
+  __syncthreads();
+  const long long total = rows_padded * out_words;
+  const int wshift = pow2_shift(out_words);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long n;
+    int w2;
+    split_index(i, out_words, wshift, &n, &w2);
+    uint32_t acc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[p] = 0;
+    if (n < N) {
+      const uint32_t* row = table + static_cast<size_t>(n) * P * words;
+      for (int b = 0; b < 32; ++b) {
+        const int c = sh_cols[w2 * 32 + b];
+        if (c < 0) continue;
+        const int sw = c >> 5, sb = c & 31;
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] |= ((__ldg(row + p * words + sw) >> sb) & 1u) << b;
+      }
+    }
+    uint32_t* dst = out + static_cast<size_t>(n) * P * out_words + w2;
+#pragma unroll
+    for (int p = 0; p < P; ++p) dst[p * out_words] = acc[p];
+  }
+}
+
 struct AcceptVec { uint8_t a[1024]; };
 
 __global__ void flags_or_rows_kernel(const uint8_t* __restrict__ flags, int rows, long long N, long long ld, AcceptVec acc,
@@ -185,6 +264,49 @@ int pg_mutant_any(const uint32_t* mut, int64_t N, int words, uint32_t* any_bits,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PG_CUDA(cudaMemsetAsync(any_bits, 0, sizeof(uint32_t) * words, s));
   mutant_any_kernel<<<grid_for(N, 256), 256, 0, s>>>(mut, N, words, any_bits);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_varying_columns(const uint32_t* table, int64_t N, int planes, int words, uint32_t* varying, void* stream) {
+  PG_CHECK_ARG(table && varying && N > 0 && planes > 0 && words > 0, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int row_words = planes * words;
+  PG_CUDA(cudaMemsetAsync(varying, 0, sizeof(uint32_t) * row_words, s));
+  const bool vec = row_words % 4 == 0 && reinterpret_cast<uintptr_t>(table) % 16 == 0;
+  const int row_elems = vec ? row_words / 4 : row_words;
+  const long long total = static_cast<long long>(N) * row_elems;
+  long long threads = static_cast<long long>(num_sms()) * 8 * 256;
+  if (threads > total) threads = total;
+  const long long stride = max(1ll, threads / row_elems) * row_elems;      // a multiple of the row length
+  const unsigned grid = static_cast<unsigned>(ceil_div(stride, 256));
+  const size_t smem = sizeof(uint32_t) * row_words;
+  if (vec)
+    varying_columns_kernel<uint4><<<grid, 256, smem, s>>>(reinterpret_cast<const uint4*>(table), total, row_elems, stride,
+                                                         varying);
+  else
+    varying_columns_kernel<uint32_t><<<grid, 256, smem, s>>>(table, total, row_elems, stride, varying);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+int pg_compact_columns(const uint32_t* table, int64_t N, int planes, int words, const int32_t* cols, uint32_t* out,
+                       int out_words, void* stream) {
+  PG_CHECK_ARG(table && cols && out && N > 0 && words > 0, "bad arguments");
+  PG_CHECK_ARG(out_words > 0 && (out_words & (out_words - 1)) == 0 || out_words % 8 == 0, "out_words must come from pg_packed_words");
+  PG_CHECK_ARG(out_words <= 1024, "out_words too large");
+  const long long rows_padded = pg_packed_rows(N);
+  const size_t smem = sizeof(int) * out_words * 32;
+  const unsigned grid = grid_for(rows_padded * out_words, 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (planes == 5)
+    compact_columns_kernel<5><<<grid, 256, smem, s>>>(table, N, rows_padded, words, cols, out, out_words);
+  else if (planes == 8)
+    compact_columns_kernel<8><<<grid, 256, smem, s>>>(table, N, rows_padded, words, cols, out, out_words);
+  else {
+    set_error("pg_compact_columns supports 5 or 8 planes, got %d", planes);
+    return PG_ERR_UNSUPPORTED;
+  }
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -141,6 +141,57 @@ __device__ __forceinline__ void ham_rows(const uint32_t (&q)[TM][P * W], const u
   }
 }
 
+// Distances of TM own rows to FOUR consecutive stream rows (col: the first of them, 16-byte aligned:
+// every tile starts aligned and the callers step in groups of four).  Rows of a multiple of four
+// words are read with 128-bit loads by ham_rows already.  Narrow rows (W = 1, 2: 20 / 40 bytes at five
+// planes) are not 16-byte multiples on their own, so one row at a time means 32- or 64-bit loads --
+// five shared-memory instructions per pair, and the shared-memory pipe takes one per clock and SM:
+// the W = 1 sweep ran at 27 clocks per pair-warp on 20 clocks of LDS.  Four rows together ARE a
+// multiple of 16 bytes: P*W 128-bit loads per four pairs.
+template <int P, int W, int TM>
+__device__ __forceinline__ void ham_rows4(const uint32_t (&q)[TM][P * W], const uint32_t* __restrict__ col,
+                                          int (&d0)[TM], int (&d1)[TM], int (&d2)[TM], int (&d3)[TM], unsigned one) {
+  constexpr int COLW = P * W;
+  if constexpr (W % 4 == 0) {
+    ham_rows<P, W, TM>(q, col + 0 * COLW, d0, one);
+    ham_rows<P, W, TM>(q, col + 1 * COLW, d1, one);
+    ham_rows<P, W, TM>(q, col + 2 * COLW, d2, one);
+    ham_rows<P, W, TM>(q, col + 3 * COLW, d3, one);
+  } else {
+    uint32_t v[4 * COLW];
+    const uint4* c4 = reinterpret_cast<const uint4*>(col);
+#pragma unroll
+    for (int i = 0; i < COLW; ++i) {
+      const uint4 t = c4[i];
+      v[4 * i + 0] = t.x;
+      v[4 * i + 1] = t.y;
+      v[4 * i + 2] = t.z;
+      v[4 * i + 3] = t.w;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        uint32_t m[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          m[w] = q[i][w] ^ v[r * COLW + w];
+#pragma unroll
+          for (int p = 1; p < P; ++p) m[w] |= q[i][p * W + w] ^ v[r * COLW + p * W + w];
+        }
+        unsigned s = __popc(m[0]);
+#pragma unroll
+        for (int w = 1; w < W; ++w) s = mad_u32(__popc(m[w]), one, s);
+        const int dd = static_cast<int>(s);
+        if (r == 0) d0[i] = dd;
+        else if (r == 1) d1[i] = dd;
+        else if (r == 2) d2[i] = dd;
+        else d3[i] = dd;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void write_weight(void* out_w, long long at, int d, int weight) {
   if (weight == PG_W_I64) reinterpret_cast<long long*>(out_w)[at] = d;
   else if (weight == PG_W_SIM_F32) reinterpret_cast<float*>(out_w)[at] = sim_f32(d);
@@ -313,10 +364,7 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
 #pragma unroll 1
         for (; c + 4 <= ncols; c += 4) {
           int d0[TM], d1[TM], d2[TM], d3[TM];
-          ham_rows<P, W, TM>(q, tile + (c + 0) * COLW, d0, one);
-          ham_rows<P, W, TM>(q, tile + (c + 1) * COLW, d1, one);
-          ham_rows<P, W, TM>(q, tile + (c + 2) * COLW, d2, one);
-          ham_rows<P, W, TM>(q, tile + (c + 3) * COLW, d3, one);
+          ham_rows4<P, W, TM>(q, tile + c * COLW, d0, d1, d2, d3, one);
 #pragma unroll
           for (int i = 0; i < TM; ++i) {
             const unsigned best = min(min(static_cast<unsigned>(d0[i]), static_cast<unsigned>(d1[i])),
@@ -330,10 +378,8 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
           }
         }
       }
-#pragma unroll 2
-      for (; c < ncols; ++c) {
-        int d[TM];
-        ham_rows<P, W, TM>(q, tile + c * COLW, d, one);
+      // what a mode does with the distances of one stream row
+      auto consume = [&](int c, const int (&d)[TM]) {
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
           if constexpr (MODE == MODE_KNN) {
@@ -362,6 +408,24 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
             if (valid[i]) write_tile<WEIGHT>(prm.out, (col0 + c) * prm.ld + r[i], d[i], lo, span);
           }
         }
+      };
+      if constexpr (MODE != MODE_KNN && W % 4 != 0) {
+        // narrow rows: four stream rows per group of 128-bit loads (see ham_rows4)
+#pragma unroll 1
+        for (; c + 4 <= ncols; c += 4) {
+          int d0[TM], d1[TM], d2[TM], d3[TM];
+          ham_rows4<P, W, TM>(q, tile + c * COLW, d0, d1, d2, d3, one);
+          consume(c + 0, d0);
+          consume(c + 1, d1);
+          consume(c + 2, d2);
+          consume(c + 3, d3);
+        }
+      }
+#pragma unroll 2
+      for (; c < ncols; ++c) {
+        int d[TM];
+        ham_rows<P, W, TM>(q, tile + c * COLW, d, one);
+        consume(c, d);
       }
       // done with this stage: the last warp to get here refills it with the lookahead tile
       __syncwarp();

@@ -388,11 +388,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_sym_kernel(const __gri
 
 #pragma unroll 1
       for (; c + 4 <= ncols; c += 4) {
-        const int d0 = dist(tile + (c + 0) * COLW);
-        const int d1 = dist(tile + (c + 1) * COLW);
-        const int d2 = dist(tile + (c + 2) * COLW);
-        const int d3 = dist(tile + (c + 3) * COLW);
-        vote(c, d0, d1, d2, d3);
+        int d0[1], d1[1], d2[1], d3[1];
+        ham_rows4<P, W, 1>(qq, tile + c * COLW, d0, d1, d2, d3, one);
+        vote(c, d0[0], d1[0], d2[0], d3[0]);
       }
 #pragma unroll 1
       for (; c < ncols; ++c) {   // ragged end of the table (last tile only)

@@ -25,10 +25,11 @@ def _host_u32(a):
 
 class PackedTable:
     """Bit-plane token table on the device: int32 tensor [rows_padded, planes, words]."""
-    __slots__ = ("data", "rows", "L", "planes", "words")
+    __slots__ = ("data", "rows", "L", "planes", "words", "informative")
 
     def __init__(self, data, rows, L_, planes, words):
         self.data, self.rows, self.L, self.planes, self.words = data, rows, L_, planes, words
+        self.informative = None     # graph.informative_table: the table the self-sweeps of this one run on
 
     def row(self, i):
         """One packed row (planes*words words) as a device tensor."""
@@ -123,6 +124,28 @@ class CudaEngine:
         L.check(self.lib.pg_pack_chars(_ptr(c), N, L_, int(c.stride(0)), lut.ctypes.data_as(C.c_void_p), _ptr(out),
                                        int(planes), words, self._stream()))
         return PackedTable(out, N, L_, planes, words)
+
+    def varying_columns(self, table):
+        """Residue positions at which the rows of `table` do not all carry the same token
+        (pg_varying_columns), ascending, as an int32 array."""
+        var = self.empty((table.planes * table.words,), torch.int32)
+        L.check(self.lib.pg_varying_columns(_ptr(table.data), table.rows, table.planes, table.words, _ptr(var),
+                                            self._stream()))
+        bits = var.cpu().numpy().view(np.uint32).reshape(table.planes, table.words)
+        mask = np.bitwise_or.reduce(bits, axis=0)
+        return np.nonzero(np.unpackbits(mask.view(np.uint8), bitorder="little"))[0].astype(np.int32)
+
+    def compact_columns(self, table, cols):
+        """The packed table restricted to the residue positions `cols` (pg_compact_columns): the same
+        pairwise Hamming distances when every dropped position is constant over the rows."""
+        cols = np.asarray(cols, dtype=np.int32)
+        words = self.packed_words(max(1, len(cols)))
+        src = np.full(words * 32, -1, dtype=np.int32)
+        src[: len(cols)] = cols
+        out = self.empty((int(self.lib.pg_packed_rows(table.rows)), table.planes, words), torch.int32)
+        L.check(self.lib.pg_compact_columns(_ptr(table.data), table.rows, table.planes, table.words,
+                                            _ptr(self.to_device(src)), _ptr(out), words, self._stream()))
+        return PackedTable(out, table.rows, max(1, len(cols)), table.planes, words)
 
     # ---- fused Hamming sweeps -----------------------------------------------------------
     def _workspace(self, rows, stream_rows, words, k1):

@@ -249,6 +249,29 @@ def pack_table(eng, X, rank, world, group):
 
 
 
+COMPACT_MIN_ROWS = 4096     # smaller tables: the look at the columns costs more than it can save
+
+
+def informative_table(eng, packed):
+    """The table a graph build sweeps: `packed` itself, or its restriction to the residue positions
+    that are not constant over the rows when that is a narrower kernel instantiation.  A position
+    where every row carries the same token adds 0 to every pairwise Hamming distance
+    (hamming.py:34), so distances, neighbours and edges are bit for bit the same; libraries built
+    around one wild type (a 4-site combinatorial library of 56-residue sequences) are exactly the
+    tables prograph is used on.  Every rank holds the whole table and takes the same decision."""
+    done = getattr(packed, "informative", None)     # None: not looked at yet; False: nothing to drop
+    if done is not None:
+        return packed if done is False else done
+    out = False
+    if packed.rows >= COMPACT_MIN_ROWS:
+        cols = eng.varying_columns(packed)
+        if eng.packed_words(max(1, len(cols))) < packed.words:
+            out = eng.compact_columns(packed, cols)
+            out.informative = False
+    packed.informative = out        # looked at once per table (the Prograph mirror keeps its table)
+    return packed if out is False else out
+
+
 def hamming_knn_device(eng, own, stream, k, similarity, row0, rows):
     """kNN rows [row0,row0+rows) of `own` against `stream` (both PackedTable)."""
     kk = min(k, stream.rows - 1)          # [:, 1:k+1] of a row of N entries
@@ -295,6 +318,8 @@ def hamming_knn_graph(eng, packed, k, similarity, rank, world, group, output="re
     sweep on this rank's row block followed by the all-gather of the result rows."""
     n = packed.rows
     kk = min(k, n - 1)
+    with phase("columns"):
+        packed = informative_table(eng, packed)
     if kk > 0 and _sym_enabled(eng, packed, kk + 1, world):
         try:
             return _hamming_knn_sym(eng, packed, kk, similarity, rank, world, group, output)
@@ -406,6 +431,8 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     n = packed.rows
     dev = eng.device
     sharded = world > 1 and n >= world
+    with phase("columns"):
+        packed = informative_table(eng, packed)
     force = os.environ.get("PG_EPS_SYM")
     use_sym = n >= SYM_EPS_MIN_ROWS if force is None else force not in ("0", "")
     if use_sym:
@@ -603,6 +630,9 @@ def build_neighbours(rep, eps=None, k=None, similarity=False, distance=hamming, 
                 packed = pack_table(eng, X, rank, world, group)
         except OverflowError:
             packed = None
+    if packed is not None:
+        with phase("columns"):
+            packed = informative_table(eng, packed)     # may bring a wide table back into range
     if packed is not None and (packed.words > 56 or (packed.words > 8 and packed.planes != 5)):
         packed = None          # wider than the fused sweeps: element-wise tiles below
 

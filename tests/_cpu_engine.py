@@ -50,6 +50,17 @@ class CheckerEngine:
             raise OverflowError("not tokens")
         return _Packed(t.astype(np.int64))
 
+    def packed_words(self, L_):
+        from prograph_b200 import _lib
+        return int(_lib.load().pg_packed_words(int(L_)))
+
+    def varying_columns(self, table):
+        return np.nonzero((table.tokens != table.tokens[0]).any(axis=0))[0].astype(np.int32)
+
+    def compact_columns(self, table, cols):
+        self.compacted = getattr(self, "compacted", 0) + 1
+        return _Packed(table.tokens[:, cols] if len(cols) else np.zeros((table.rows, 1), dtype=np.int64))
+
     def hamming_knn(self, own, row0, rows, stream, k, drop=1, similarity=False):
         self.rows_seen = (row0, rows)
         D = O.hamming(stream.tokens, own.tokens[row0:row0 + rows], similarity=similarity)

@@ -25,6 +25,63 @@ def np_(t):
     return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
+# ------------------------------------------------------------------ informative columns
+@pytest.mark.parametrize("L,alphabet,n", [(56, 20, 3000), (256, 20, 5000), (300, 200, 1500), (33, 20, 7), (1000, 20, 900),
+                                          (2000, 20, 600)])
+def test_varying_and_compacted_columns(eng, L, alphabet, n):
+    """pg_varying_columns against numpy and pg_compact_columns against a pack of the selected token
+    columns, for 5 and 8 planes, vector and scalar row lengths, short last words."""
+    rng = np.random.default_rng(L + n)
+    wt = rng.integers(1, alphabet + 1, size=L)
+    X = np.tile(wt, (n, 1))
+    sites = np.sort(rng.choice(L, size=max(1, L // 7), replace=False))
+    X[:, sites] = rng.integers(1, alphabet + 1, size=(n, len(sites)))
+    X[0] = wt
+    X[n - 1, sites[-1]] = wt[sites[-1]] % alphabet + 1             # the last row alone makes a column vary
+    tab = eng.pack(X.astype(np.uint8))
+    cols = eng.varying_columns(tab)
+    want = np.nonzero((X != X[0]).any(axis=0))[0]
+    np.testing.assert_array_equal(cols, want)
+    small = eng.compact_columns(tab, cols)
+    ref = eng.pack(X[:, want].astype(np.uint8), planes=tab.planes)
+    assert (small.planes, small.words, small.rows) == (ref.planes, ref.words, n)
+    assert torch.equal(small.data, ref.data)
+    # identical rows: nothing varies
+    same = eng.pack(np.tile(wt, (50, 1)).astype(np.uint8))
+    assert len(eng.varying_columns(same)) == 0
+
+
+@pytest.mark.parametrize("n,L,sites", [(6000, 56, 4), (70000, 200, 30), (5000, 1900, 100)])
+def test_graph_builds_on_informative_columns_match_the_oracle(eng, n, L, sites):
+    """build_neighbours on libraries with few varying positions (graph.informative_table drops the
+    constant ones: W=2 -> 1, W=8 -> 1, and a 1900-residue table that no fused sweep covers comes back
+    into range): kNN and epsilon CSR against the C oracle on the FULL rows."""
+    from oracle import c_oracle as CO
+    from prograph_b200 import build_neighbours, graph
+    rng = np.random.default_rng(n + L)
+    wt = rng.integers(1, 21, size=L)
+    X = np.tile(wt, (n, 1)).astype(np.uint8)
+    pos = np.sort(rng.choice(L, size=sites, replace=False))
+    muts = rng.integers(0, 4, size=(n, sites)) == 0                # each site mutated with probability 1/4
+    X[:, pos] = np.where(muts, rng.integers(1, 21, size=(n, sites)), wt[pos]).astype(np.uint8)
+    tab = eng.pack(X)
+    small = graph.informative_table(eng, tab)
+    assert small.L <= sites and small.words == eng.packed_words(small.L) < tab.words
+    srows = np.unique(np.concatenate([[0, n - 1], rng.choice(n, size=40, replace=False)]))
+    D = CO.hamming_rows(CO.pack(X), L, srows)
+    knn = build_neighbours(X, k=8)
+    for i, r in enumerate(srows):
+        order = np.lexsort((np.arange(n), D[i]))[1:9]
+        np.testing.assert_array_equal(knn.idx[r], order)
+        np.testing.assert_array_equal(knn.w[r], D[i, order])
+    g = build_neighbours(X, eps=1)
+    for i, r in enumerate(srows):
+        cols = np.nonzero((D[i] <= 1) & (D[i] > 0))[0]
+        a, b = g.indptr[r], g.indptr[r + 1]
+        np.testing.assert_array_equal(g.idx[a:b], cols)
+        np.testing.assert_array_equal(g.w[a:b], D[i, cols])
+
+
 # ------------------------------------------------------------------ pack / masks
 @pytest.mark.parametrize("L", [1, 31, 32, 33, 56, 100, 255, 256, 257, 600])
 @pytest.mark.parametrize("alphabet", [20, 200])

@@ -305,6 +305,49 @@ def test_symmetric_build_policies():
             os.environ["PG_KNN_SYM"] = old
 
 
+def test_constant_columns_are_dropped_without_changing_the_graph(monkeypatch):
+    """graph.informative_table: a library built around one wild type (here 9 of 70 positions vary) is
+    swept on its varying positions only -- same kNN lists and the same epsilon CSR as the oracle
+    computes on the full rows (hamming.py:34, prograph.py:731-765); a table whose varying positions
+    do not fit a narrower kernel instantiation is left alone."""
+    from _cpu_engine import CheckerEngine
+    from oracle import prograph_oracle as O
+    from prograph_b200 import build_neighbours, graph
+    rng = np.random.default_rng(5)
+    n, L = 300, 70
+    wt = rng.integers(1, 21, size=L)
+    X = np.tile(wt, (n, 1))
+    sites = np.sort(rng.choice(L, size=9, replace=False))
+    X[:, sites] = rng.integers(1, 21, size=(n, 9))
+    X[0] = wt
+    monkeypatch.setattr(graph, "COMPACT_MIN_ROWS", 1)
+    eng = CheckerEngine()
+    tab = eng.pack(X)
+    small = graph.informative_table(eng, tab)
+    assert small.words == 1 and small.L == 9 and np.array_equal(small.tokens, X[:, sites])
+    D = O.hamming(X, X)
+    knn = build_neighbours(X, k=5, engine=eng)
+    ri, rw = O.knn_from_distances(D, 5)
+    assert np.array_equal(knn.idx, ri) and np.array_equal(knn.w, rw)
+    g = build_neighbours(X, eps=2, engine=eng)
+    keep = (D <= 2) & (D > 0)
+    rows, cols = np.nonzero(keep)
+    assert np.array_equal(g.indptr, np.concatenate([[0], np.cumsum(keep.sum(1))]))
+    assert np.array_equal(g.idx, cols) and np.array_equal(g.w, D[rows, cols])
+    assert eng.compacted == 3
+    # 40 varying positions still need two words: nothing to gain, the table stays as it is
+    Y = rng.integers(1, 21, size=(n, 40))
+    taby = eng.pack(Y)
+    assert graph.informative_table(eng, taby) is taby
+    # identical rows: one (empty) column is left and every distance is 0
+    Z = np.tile(wt, (n, 1))
+    z = graph.informative_table(eng, eng.pack(Z))
+    assert z.words == 1 and not z.tokens.any()
+    monkeypatch.setattr(graph, "COMPACT_MIN_ROWS", 10**9)
+    fresh = eng.pack(X)
+    assert graph.informative_table(eng, fresh) is fresh
+
+
 def test_symmetric_planner_covers_the_triangle_once_in_l2_bands():
     """pg_knn_sym_plan (host-only): over all ranks the work items cover every (row block, stream tile)
     of the triangle exactly once; every CTA walks its items band by band (so that co-resident CTAs
