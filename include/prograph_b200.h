@@ -283,7 +283,10 @@ int pg_minkowski2_gemm_eps_fill(const uint8_t* A, const int32_t* normA, int64_t 
  * ------------------------------------------------------------------------- */
 /* stable top-k of each tile row (prograph.py:757-762): positions [drop, drop+k) of the
  * row sorted by (value, index) ascending, or descending with NaN first when
- * `descending` (torch.sort semantics).  out_idx int64 [rows][k], out_val tile dtype. */
+ * `descending` (torch.sort semantics).  out_idx int64 [rows][k], out_val tile dtype.
+ * k + drop <= 4096: radix select + sort in shared memory, one CTA per row; above that the
+ * whole tile is sorted (two stable device-wide radix sorts: by value, then by row), as the
+ * reference sorts whole rows for any k (rows * N < 2^31 per call). */
 int pg_tile_topk(const void* tile, int dtype, int64_t rows, int64_t N, int64_t ld,
                  int k, int drop, int descending, int64_t* out_idx, void* out_val, void* stream);
 

@@ -11,7 +11,7 @@
 
 namespace pg {
 
-constexpr int kMaxMaskWords = 64;  // sequences up to 2048 residues for the selection kernels
+constexpr int kMaxMaskWords = 128;  // sequences up to 4096 residues for the selection kernels
 
 struct WordVec { uint32_t w[kMaxMaskWords]; };
 struct LutVec { uint32_t w[kMaxMaskWords + 1]; };     // truth table over d = 0 .. 32*words: one word more
@@ -38,6 +38,7 @@ __global__ void mutant_bits_kernel(const uint32_t* __restrict__ table, long long
 // expands to four 0/1 bytes with one multiply ((n * 0x00204081) & 0x01010101).  The two threads of a
 // word read the same plane words (one L1 line).  HBM-bound: reads planes * words * 4 bytes, writes L
 // bytes per row.
+template <int ILP>
 __global__ void __launch_bounds__(256) mutant_bool_kernel(const uint32_t* __restrict__ table, long long N, int planes,
                                                           int words, int L, const uint32_t* __restrict__ ref,
                                                           uint8_t* __restrict__ out) {
@@ -45,26 +46,41 @@ __global__ void __launch_bounds__(256) mutant_bool_kernel(const uint32_t* __rest
   const long long total = N * halves;
   const bool vec16 = (L % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   const int hshift = pow2_shift(halves);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long n;
-    int h;
-    split_index(i, halves, hshift, &n, &h);
-    const int w = h >> 1;
-    const int have = min(16, L - h * 16);
-    if (have <= 0) continue;
-    const uint32_t* row = table + static_cast<size_t>(n) * planes * words + w;
-    uint32_t m = 0;
-    for (int p = 0; p < planes; ++p) m |= __ldg(row + p * words) ^ __ldg(ref + p * words + w);
-    m = (h & 1) ? (m >> 16) : (m & 0xffffu);
-    uint32_t b[4];
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total; i0 += step * ILP) {
+    // ILP independent (row, half word) items per thread: all their plane words are requested before
+    // the first mask is formed (20 bytes of loads per item do not cover the HBM latency on their own)
+    uint32_t m[ILP];
+    long long n[ILP];
+    int h[ILP];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) b[k] = (((m >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
-    uint8_t* dst = out + static_cast<size_t>(n) * L + h * 16;
-    if (have == 16 && vec16) {
-      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(b[0], b[1], b[2], b[3]));
-    } else {
-      for (int l = 0; l < have; ++l) dst[l] = static_cast<uint8_t>((b[l >> 2] >> (8 * (l & 3))) & 1u);
+    for (int u = 0; u < ILP; ++u) {
+      const long long i = i0 + u * step;
+      m[u] = 0;
+      n[u] = -1;
+      h[u] = 0;
+      if (i < total) {
+        split_index(i, halves, hshift, &n[u], &h[u]);
+        const int w = h[u] >> 1;
+        const uint32_t* row = table + static_cast<size_t>(n[u]) * planes * words + w;
+        for (int p = 0; p < planes; ++p) m[u] |= __ldg(row + p * words) ^ __ldg(ref + p * words + w);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) {
+      if (n[u] < 0) continue;
+      const int have = min(16, L - h[u] * 16);
+      if (have <= 0) continue;
+      const uint32_t mm = (h[u] & 1) ? (m[u] >> 16) : (m[u] & 0xffffu);
+      uint32_t b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b[k] = (((mm >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u;
+      uint8_t* dst = out + static_cast<size_t>(n[u]) * L + h[u] * 16;
+      if (have == 16 && vec16) {
+        __stcs(reinterpret_cast<uint4*>(dst), make_uint4(b[0], b[1], b[2], b[3]));
+      } else {
+        for (int l = 0; l < have; ++l) dst[l] = static_cast<uint8_t>((b[l >> 2] >> (8 * (l & 3))) & 1u);
+      }
     }
   }
 }
@@ -240,8 +256,9 @@ int pg_mutant_bits(const uint32_t* table, int64_t N, int planes, int words, cons
 int pg_mutant_bool(const uint32_t* table, int64_t N, int planes, int words, int L, const uint32_t* ref, uint8_t* out,
                    void* stream) {
   PG_CHECK_ARG(table && ref && out && N > 0 && planes > 0 && words > 0 && L > 0 && L <= words * 32, "bad arguments");
-  mutant_bool_kernel<<<grid_for(N * words * 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes,
-                                                                                                 words, L, ref, out);
+  // two items per thread: 107.7 us at 1 M x 256 (3.86 TB/s); one: 112.1 us, four: 140.4 us (profiles/r4c_mb.log)
+  const unsigned grid = grid_for(ceil_div(N * words * 2, 2ll), 256);
+  mutant_bool_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, N, planes, words, L, ref, out);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

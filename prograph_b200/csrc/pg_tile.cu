@@ -6,6 +6,7 @@
 //   pg_tile_threshold_*      prograph.py:734-739 / :544 (where + gather) as ballot +
 //                            block prefix-sum compaction
 #include <math_constants.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <type_traits>
 
@@ -498,6 +499,101 @@ __global__ void __launch_bounds__(TK_THREADS) tile_topk_kernel(const T* __restri
 }
 
 // =============================================================================
+// Top-k of each row when k + drop exceeds the shared-memory sort: the reference sorts whole rows
+// (prograph.py:757-762, any k).  Two stable device-wide radix sorts: (1) all entries of the tile by
+// their order-preserving key, the value being the entry's position row*N + i -- equal keys keep
+// ascending positions; (2) by row.  What comes out is every row in (key, index) order.
+// =============================================================================
+template <typename T>
+__global__ void sort_keys_kernel(const T* __restrict__ tile, long long rows, long long N, long long ld, int descending,
+                                 typename KeyOf<T>::K* __restrict__ keys, uint32_t* __restrict__ pos) {
+  using K = typename KeyOf<T>::K;
+  const K flip = descending ? ~K(0) : K(0);
+  const long long total = rows * N;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / N, i = e - r * N;
+    keys[e] = KeyOf<T>::get(tile[static_cast<size_t>(r) * ld + i]) ^ flip;
+    pos[e] = static_cast<uint32_t>(e);
+  }
+}
+
+__global__ void sort_rows_of_kernel(const uint32_t* __restrict__ pos, long long total, unsigned N, uint32_t* __restrict__ row_of) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x)
+    row_of[e] = pos[e] / N;
+}
+
+template <typename T>
+__global__ void sort_take_kernel(const T* __restrict__ tile, const uint32_t* __restrict__ pos, long long rows, long long N,
+                                 long long ld, int k, int drop, long long* __restrict__ out_idx, T* __restrict__ out_val) {
+  const long long total = rows * k;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / k;
+    const int j = static_cast<int>(e - r * k);
+    if (drop + j < N) {
+      const long long i = static_cast<long long>(pos[r * N + drop + j]) - r * N;
+      out_idx[e] = i;
+      out_val[e] = tile[static_cast<size_t>(r) * ld + i];
+    } else {
+      out_idx[e] = -1;
+      out_val[e] = T(0);
+    }
+  }
+}
+
+template <typename T>
+static int tile_topk_by_sort(const T* tile, long long rows, long long N, long long ld, int k, int drop, int descending,
+                             long long* out_idx, T* out_val, cudaStream_t s) {
+  using K = typename KeyOf<T>::K;
+  const long long total = rows * N;
+  if (total >= (1ll << 31)) { set_error("tile too large for one key sort: split the rows"); return PG_ERR_UNSUPPORTED; }
+  const int n = static_cast<int>(total);
+  K* keys = nullptr;
+  uint32_t* pos = nullptr;
+  uint32_t* rowk = nullptr;
+  const size_t kbytes = round_up(sizeof(K) * static_cast<size_t>(n), size_t(256));
+  const size_t pbytes = round_up(sizeof(uint32_t) * static_cast<size_t>(n), size_t(256));
+  unsigned char* slab = nullptr;
+  PG_CUDA(temp_alloc(reinterpret_cast<void**>(&slab), 2 * kbytes + 4 * pbytes, s));
+  keys = reinterpret_cast<K*>(slab);
+  pos = reinterpret_cast<uint32_t*>(slab + 2 * kbytes);
+  rowk = reinterpret_cast<uint32_t*>(slab + 2 * kbytes + 2 * pbytes);
+  cub::DoubleBuffer<K> kb(keys, reinterpret_cast<K*>(slab + kbytes));
+  cub::DoubleBuffer<uint32_t> pb(pos, reinterpret_cast<uint32_t*>(slab + 2 * kbytes + pbytes));
+  cub::DoubleBuffer<uint32_t> rb(rowk, reinterpret_cast<uint32_t*>(slab + 2 * kbytes + 3 * pbytes));
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(ceil_div(total, 256), static_cast<long long>(num_sms()) * 16));
+  sort_keys_kernel<T><<<grid, 256, 0, s>>>(tile, rows, N, ld, descending, kb.Current(), pb.Current());
+  count_launch();
+  int row_bits = 1;
+  while ((1ll << row_bits) < rows) ++row_bits;
+  size_t t1 = 0, t2 = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, t1, kb, pb, n, 0, static_cast<int>(sizeof(K) * 8), s);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, t2, rb, pb, n, 0, row_bits, s);
+  void* tmp = nullptr;
+  if (e == cudaSuccess) e = temp_alloc(&tmp, std::max(t1, t2), s);
+  size_t tb = std::max(t1, t2);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb, kb, pb, n, 0, static_cast<int>(sizeof(K) * 8), s);
+  if (e == cudaSuccess) {
+    sort_rows_of_kernel<<<grid, 256, 0, s>>>(pb.Current(), total, static_cast<unsigned>(N), rb.Current());
+    e = cub::DeviceRadixSort::SortPairs(tmp, tb, rb, pb, n, 0, row_bits, s);
+    count_launch();
+  }
+  if (e == cudaSuccess) {
+    const long long out_total = rows * k;
+    sort_take_kernel<T><<<static_cast<unsigned>(std::min<long long>(ceil_div(out_total, 256), 1 << 20)), 256, 0, s>>>(
+        tile, pb.Current(), rows, N, ld, k, drop, out_idx, out_val);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  if (tmp) cudaFreeAsync(tmp, s);
+  cudaFreeAsync(slab, s);
+  if (e != cudaSuccess) { set_error("tile top-k by sort failed: %s", cudaGetErrorString(e)); return PG_ERR_CUDA; }
+  return PG_OK;
+}
+
+// =============================================================================
 // Threshold -> CSR compaction
 // =============================================================================
 struct ThreshParams {
@@ -716,8 +812,18 @@ int pg_tile_topk(const void* tile, int dtype, int64_t rows, int64_t N, int64_t l
   if (k1 > N) k1 = N;
   int cap = 2;
   while (cap < k1) cap <<= 1;
-  if (cap > 4096) { set_error("k=%d too large for the shared-memory sort (max 4096 incl. drop)", k); return PG_ERR_UNSUPPORTED; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cap > 4096) {      // longer than the shared-memory sort holds: sort the whole rows, like the reference
+    long long* oi = reinterpret_cast<long long*>(out_idx);
+    switch (dtype) {
+      case PG_F16: return tile_topk_by_sort(static_cast<const __half*>(tile), rows, N, ld, k, drop, descending, oi, static_cast<__half*>(out_val), s);
+      case PG_F32: return tile_topk_by_sort(static_cast<const float*>(tile), rows, N, ld, k, drop, descending, oi, static_cast<float*>(out_val), s);
+      case PG_F64: return tile_topk_by_sort(static_cast<const double*>(tile), rows, N, ld, k, drop, descending, oi, static_cast<double*>(out_val), s);
+      case PG_I32: return tile_topk_by_sort(static_cast<const int*>(tile), rows, N, ld, k, drop, descending, oi, static_cast<int*>(out_val), s);
+      case PG_I64: return tile_topk_by_sort(static_cast<const long long*>(tile), rows, N, ld, k, drop, descending, oi, static_cast<long long*>(out_val), s);
+      default: set_error("tile top-k: unsupported dtype %d", dtype); return PG_ERR_INVALID;
+    }
+  }
 #define PG_TK(T)                                                                                              \
   do {                                                                                                        \
     const size_t smem = (sizeof(KeyOf<T>::K) + 4) * static_cast<size_t>(cap);                                 \

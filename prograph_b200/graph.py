@@ -129,9 +129,6 @@ def as_matrix(rep):
     return out
 
 
-MAX_TILE_K = 4095     # pg_tile_topk sorts k + 1 candidates of a row in shared memory
-
-
 def validate(eps, k):
     """Argument checks of prograph.py:714-718 (truthiness: eps=0 and k=0 are rejected)."""
     if operator.xor(bool(eps), bool(k)) is False:
@@ -139,14 +136,6 @@ def validate(eps, k):
                          "methods of graph construction.")
     if k is not None and not isinstance(k, int):
         raise TypeError("K must be provided as an integer.")
-
-
-def _check_tile_k(k, n):
-    """The reference sorts whole rows and accepts any k; the device top-k of the non-fused metrics
-    keeps k + 1 <= 4096 candidates per row.  Say so up front instead of failing inside a launch."""
-    if min(k, n - 1) > MAX_TILE_K:
-        raise ValueError(f"k={k}: the device top-k of this metric supports k <= {MAX_TILE_K} "
-                         "(Hamming on tokens: k <= 95 fused, above that through the same top-k)")
 
 
 def distance_lut(max_d, comp, eps, similarity, guard=True):
@@ -259,7 +248,7 @@ def informative_table(eng, packed):
     (hamming.py:34), so distances, neighbours and edges are bit for bit the same; libraries built
     around one wild type (a 4-site combinatorial library of 56-residue sequences) are exactly the
     tables prograph is used on.  Every rank holds the whole table and takes the same decision."""
-    done = getattr(packed, "informative", None)     # None: not looked at yet; False: nothing to drop
+    done = packed.informative     # None: not looked at yet; False: nothing to drop
     if done is not None:
         return packed if done is False else done
     out = False
@@ -378,7 +367,6 @@ def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
     for the in-shared-memory lists of the fused sweep.  Ascending distance with index ties is
     the same order as descending similarity, so the sort always runs on the distances."""
     kk = min(k, stream.rows - 1)
-    _check_tile_k(k, stream.rows)
     step = max(512, (TILE_BUDGET_BYTES // (8 * stream.rows)) // 512 * 512)
     idxs, ws = [], []
     a0 = row0 // 512 * 512
@@ -551,7 +539,6 @@ def _tiles(eng, X, kind, p, distance, similarity, batch_size, row0, rows, gemm=N
 
 def _tile_knn(eng, tiles, k, similarity, n):
     kk = min(k, n - 1)
-    _check_tile_k(k, n)
     idxs, ws = [], []
     for _, tile in tiles:
         if kk <= 0:

@@ -13,6 +13,7 @@ class _Packed:
         self.tokens = np.asarray(tokens)
         self.rows, self.L = self.tokens.shape
         self.planes, self.words = 5, max(1, -(-self.L // 32))
+        self.informative = None
 
 
 class CheckerEngine:

@@ -82,6 +82,42 @@ def test_graph_builds_on_informative_columns_match_the_oracle(eng, n, L, sites):
         np.testing.assert_array_equal(g.w[a:b], D[i, cols])
 
 
+# ------------------------------------------------------------------ any k, like the reference's whole-row sort
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64, torch.int32, torch.int64])
+@pytest.mark.parametrize("descending", [False, True])
+def test_tile_topk_beyond_the_shared_memory_sort(eng, dtype, descending):
+    """k + drop > 4096: pg_tile_topk sorts whole rows (two stable radix sorts); same (value, index)
+    order as torch.sort(stable=True) (prograph.py:757-762), heavy ties included."""
+    rng = np.random.default_rng(3)
+    rows, n, k, drop = 5, 9000, 5000, 1
+    vals = rng.integers(0, 40, size=(rows, n))                     # 40 distinct values: long runs of ties
+    tile = torch.from_numpy(vals).to(eng.device).to(dtype)
+    idx, val = eng.tile_topk(tile, k, drop=drop, descending=descending)
+    sv, si = torch.sort(tile.cpu().to(torch.float64), dim=1, stable=True, descending=descending)
+    assert torch.equal(idx.cpu(), si[:, drop:drop + k])
+    assert torch.equal(val.cpu().to(torch.float64), sv[:, drop:drop + k])
+    # k beyond the row: the reference's slice simply ends; missing slots are marked -1
+    idx, _ = eng.tile_topk(tile[:2, :4500].contiguous(), 4499, drop=1, descending=descending)
+    assert idx.shape == (2, 4499) and int((idx < 0).sum()) == 0
+
+
+def test_build_graph_accepts_any_k(eng):
+    """build_neighbours(k=4200) on 4 300 rows: Hamming on tokens (k beyond the fused lists -> int64 tiles
+    -> whole-row sort) and Minkowski, against the oracle's stable sort."""
+    from prograph_b200 import build_neighbours, minkowski
+    rng = np.random.default_rng(8)
+    n, L, k = 4300, 40, 4200
+    X = rng.integers(1, 21, size=(n, L))
+    D = O.hamming(X, X)
+    got = build_neighbours(X, k=k)
+    ri, rw = O.knn_from_distances(D, k)
+    assert np.array_equal(got.idx, ri) and np.array_equal(got.w, rw)
+    Dm = O.minkowski(X.astype(np.float16), X.astype(np.float16))
+    gm = build_neighbours(X, k=k, distance=minkowski)
+    mi, mw = O.knn_from_distances(Dm, k)
+    assert np.array_equal(gm.idx, mi) and np.array_equal(gm.w, mw)
+
+
 # ------------------------------------------------------------------ pack / masks
 @pytest.mark.parametrize("L", [1, 31, 32, 33, 56, 100, 255, 256, 257, 600])
 @pytest.mark.parametrize("alphabet", [20, 200])

@@ -28,14 +28,33 @@ def main():
     G = make_gb1_library()
     n = len(G)
     dev = torch.from_numpy(G).to(eng.device)
+    from prograph_b200 import trace
+
+    def phases_of(fn):
+        """Per-phase and per-sweep-launch milliseconds of one more call."""
+        eng.time_sweeps(True)
+        eng.sweep_times(reset=True)
+        trace.enable_timing(True)
+        trace.phases()
+        fn()
+        ph = trace.phases()
+        trace.enable_timing(False)
+        sw = eng.sweep_times(reset=True)
+        eng.time_sweeps(False)
+        return {k: round(v, 3) for k, v in ph.items()}, [round(v, 3) for v in sw]
+
     for min_rows, label in ((10**9, "full rows"), (4096, "informative columns")):
         graph.COMPACT_MIN_ROWS = min_rows
         for eps in (1, 2):
             lut = graph.distance_lut(64, operator.le, eps, False)
-            ms, (ip, _, _) = timed(lambda: graph.hamming_eps_graph(eng, eng.pack(dev), lut, False, 0, 1, None), reps=3)
+            fn = lambda: graph.hamming_eps_graph(eng, eng.pack(dev), lut, False, 0, 1, None)
+            ms, (ip, _, _) = timed(fn, reps=3)
             print(f"C3 eps={eps} [{label}]: {ms:.3f} ms  nnz={int(ip[-1])}  {n * n / ms / 1e6:.1f} Gpairs/s", flush=True)
-        ms, _ = timed(lambda: graph.hamming_knn_graph(eng, eng.pack(dev), 16, False, 0, 1, None), reps=3)
+            print("   phases", *phases_of(fn), flush=True)
+        fn = lambda: graph.hamming_knn_graph(eng, eng.pack(dev), 16, False, 0, 1, None)
+        ms, _ = timed(fn, reps=3)
         print(f"C3 kNN k=16 [{label}]: {ms:.3f} ms  {n * n / ms / 1e6:.1f} Gpairs/s", flush=True)
+        print("   phases", *phases_of(fn), flush=True)
     U = torch.from_numpy(make_tokens(args.n, 256, "uniform")).to(eng.device)
     tab = eng.pack(U)
     ms, cols = timed(lambda: eng.varying_columns(tab), reps=5)
