@@ -173,6 +173,16 @@ def test_sharded_build_over_gloo(tmp_path, n):
     assert seen[0][0] == 0 and seen[0][0] + seen[0][1] == seen[1][0] and seen[1][0] + seen[1][1] == n
 
 
+def _sym_table(n):
+    """12 varying sites (3 letters each) inside 70-residue copies of one wild type: the sharded builds
+    below also go through graph.informative_table (70 residues = 4 words -> 12 positions = 1 word)."""
+    rng = np.random.default_rng(5)
+    sites = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    X = np.tile(np.arange(70, dtype=np.int64) % 20 + 1, (n, 1))
+    X[:, 3:63:5] = sites
+    return X
+
+
 def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -182,8 +192,8 @@ def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
     from _cpu_engine import CheckerEngine
     from prograph_b200 import graph
     graph.SYM_MIN_ROWS, graph.SYM_BOOT_DIV = 0, boot_div      # route this small table through the symmetric build
-    rng = np.random.default_rng(5)
-    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    graph.COMPACT_MIN_ROWS = 1                                # ... on its informative columns
+    X = _sym_table(n)
     eng = CheckerEngine()
     graph.SYM_EPS_MIN_ROWS = 0
     knn = graph.build_neighbours(X, k=k, engine=eng)
@@ -194,7 +204,7 @@ def _gloo_sym_worker(rank, world, port, n, k, boot_div, tmpdir):
     np.savez(os.path.join(tmpdir, f"r{rank}.npz"), idx=knn.idx, w=knn.w, sidx=sim.idx, sw=sim.w,
              eindptr=eps.indptr, eidx=eps.idx, ew=eps.w, sindptr=esim.indptr, seidx=esim.idx, sew=esim.w,
              oindptr=odd.indptr, oidx=odd.idx, ow=odd.w,
-             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n), min(eng.sym_modes), eng.eps_sym_calls]))
+             calls=np.array([eng.sym_calls, graph.sym_boot_rows(n), min(eng.sym_modes), eng.eps_sym_calls, eng.compacted]))
     dist.destroy_process_group()
 
 
@@ -208,8 +218,7 @@ def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
     k, world = 5, 2
     port = 29950 + (os.getpid() + n) % 40
     mp.spawn(_gloo_sym_worker, args=(world, port, n, k, boot_div, str(tmp_path)), nprocs=world, join=True)
-    rng = np.random.default_rng(5)
-    X = rng.integers(1, 4, size=(n, 12)).astype(np.int64)
+    X = _sym_table(n)
     ri, rw = O.knn_from_distances(O.hamming(X, X), k)
     si, sw = O.knn_from_distances(O.hamming(X, X, similarity=True), k, descending=True)
     for r in range(world):
@@ -230,6 +239,7 @@ def test_symmetric_build_over_gloo(tmp_path, n, boot_div):
         # eps=2 and its similarity form took the symmetric sweep; `d != 2` keeps nearly every pair
         # (dense: above graph.SYM_EPS_MAX_DEGREE for n=1301, not a range for n=700) -> one-sided passes
         assert z["calls"][3] == 2
+        assert z["calls"][4] == 5                       # every build swept the 12 informative columns only
 
 
 def test_symmetric_band_planner_partitions_and_balances():
