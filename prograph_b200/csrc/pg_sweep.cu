@@ -379,7 +379,7 @@ struct SymPlan {
 };
 
 static SymPlan sym_plan(const SymLayout& s, long long rows, int part, int parts, int mode, int grid,
-                        long long boot_rows) {
+                        long long boot_rows, int chunk_floor = 32) {
   const int boot_blocks = static_cast<int>(boot_rows / kConsumers);
   int band0 = 0, band1 = s.n_tiles;
   if (mode == 1) sym_band(s, rows, boot_rows, part, parts, &band0, &band1);
@@ -394,7 +394,7 @@ static SymPlan sym_plan(const SymLayout& s, long long rows, int part, int parts,
   const int n_sub = std::max(1, static_cast<int>(ceil_div(span, s.band_tiles)));
   const int sub_w = std::max(1, static_cast<int>(ceil_div(span, n_sub)));
   if (n_sub > 1 && chunk > sub_w / 2) chunk = sub_w / 2;     // at least two phase-shifted chunks per band crossing
-  if (chunk < 32) chunk = 32;
+  if (chunk < chunk_floor) chunk = chunk_floor;
   std::vector<std::vector<SymItem>> per_cta(static_cast<size_t>(grid));
   std::vector<long long> load(static_cast<size_t>(grid), 0);
   // min-heap of (load, cta)
@@ -903,7 +903,7 @@ int pg_knn_sym_plan(int64_t rows, int planes, int words, int64_t boot_rows, int 
                    (mode == 0 || mode == 1) && boot_rows >= 0 && boot_rows % kStreamRowPad == 0,
                "bad plan arguments");
   const SymLayout lay = sym_layout(rows, words, planes);
-  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, grid, boot_rows);
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, grid, boot_rows, 32 * std::max(1, 8 / words));
   *n_items = static_cast<int64_t>(plan.items.size());
   PG_CHECK_ARG(sym_plan_bytes(plan) <= lay.item_bytes_max, "item table overflow (%zu items)", plan.items.size());
   if (items_host) {
@@ -974,7 +974,10 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   int resident = 0;
   int rc = dispatch_sym(planes, words, prm, l, &resident);   // grid 0: occupancy query only
   if (rc != PG_OK) return rc;
-  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, boot_rows);
+  // a kNN chunk starts with empty shared-memory lists and ends with a locked merge of 256 lists: on
+  // small tables of narrow rows (C3: 160 000 x 20 bytes) that is as long as sweeping 32 tiles, so the
+  // chunks are at least 32 * 8/W tiles there (C3 kNN 18.4 -> 16.5 ms, profiles/r4i_chunks.log)
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, boot_rows, 32 * std::max(1, 8 / words));
   sym_init_kernel<<<num_sms() * 4, 256, 0, cs>>>(prm.glist, static_cast<long long>(rows) * k1, prm.glast,
                                                  static_cast<long long>(lay.n_tiles) * lay.tile_cols, prm.glock, rows,
                                                  stats_dev, k1, boot_rows > 0 ? 1 : 0);

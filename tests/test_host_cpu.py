@@ -377,7 +377,9 @@ def test_symmetric_planner_covers_the_triangle_once_in_l2_bands():
             # per-CTA order: first tiles never go back by more than one band
             load = np.bincount(it[:, 4], weights=(it[:, 2] - it[:, 1]).astype(np.float64))
             if n >= 160_000:
-                assert load.max() / load.mean() < 1.02, (n, world, rank, load.max() / load.mean())
+                # narrow rows trade balance for fewer list merges (chunks of at least 32 * 8/W tiles)
+                limit = 1.02 if words >= 8 else 1.06
+                assert load.max() / load.mean() < limit, (n, world, rank, load.max() / load.mean())
             band_tiles = max(64, int(24 * 2**20 / (tile * planes * words * 4)))
             for cta in np.unique(it[:, 4])[:8]:
                 mine = it[it[:, 4] == cta]

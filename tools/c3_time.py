@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--quick", action="store_true", help="informative columns only, no 1 M-row column census")
     args = ap.parse_args()
     from bench import make_gb1_library, make_tokens
     from prograph_b200 import graph
@@ -44,6 +45,8 @@ def main():
         return {k: round(v, 3) for k, v in ph.items()}, [round(v, 3) for v in sw]
 
     for min_rows, label in ((10**9, "full rows"), (4096, "informative columns")):
+        if args.quick and min_rows != 4096:
+            continue
         graph.COMPACT_MIN_ROWS = min_rows
         for eps in (1, 2):
             lut = graph.distance_lut(64, operator.le, eps, False)
@@ -55,6 +58,8 @@ def main():
         ms, _ = timed(fn, reps=3)
         print(f"C3 kNN k=16 [{label}]: {ms:.3f} ms  {n * n / ms / 1e6:.1f} Gpairs/s", flush=True)
         print("   phases", *phases_of(fn), flush=True)
+    if args.quick:
+        return
     U = torch.from_numpy(make_tokens(args.n, 256, "uniform")).to(eng.device)
     tab = eng.pack(U)
     ms, cols = timed(lambda: eng.varying_columns(tab), reps=5)
