@@ -92,10 +92,17 @@ int pg_pack_chars(const uint8_t* chars, int64_t N, int L, int64_t ld, const uint
 size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words, int k1);
 
 /* workspace of the two epsilon passes: per-split row counts plus, when it fits, room for the
- * first 32 hits of every (split,row): sparse graphs (e.g. the default eps=1 graph of
+ * first 128 hits of every (split,row): sparse graphs (e.g. the default eps=1 graph of
  * Prograph.__init__, prograph.py:140-141) are then finished by a compaction kernel instead of
  * a second sweep */
 size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words);
+/* the same with room for `capture` hits per (split,row): a caller that knows the graph is dense
+ * -- a degree sample -- lets the count pass keep every hit (pg_hamming_eps_count_capture), and
+ * pg_hamming_eps_fill_capture becomes one coalesced copy instead of a second sweep.  The column
+ * range is then cut into no more splits than keep the captures within 8 GiB; if one split is
+ * already too much, the default geometry and captures are used.  Count, fill and this function
+ * must be given the same `capture`. */
+size_t pg_eps_workspace_bytes_capture(int64_t own_rows, int64_t stream_rows, int words, int capture);
 
 /* kNN (prograph.py:755-765: sort each row, keep sorted positions drop..drop+k-1).
  * For every own row r in [row0,row0+rows): the first (drop+k) stream rows in
@@ -212,6 +219,17 @@ int pg_hamming_eps_fill(const uint32_t* own, int64_t own_rows, int64_t row0, int
                         int planes, int words, const uint32_t* lut_host, int lut_words,
                         const int64_t* indptr, int weight, int64_t* out_idx, void* out_w,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* both passes for a workspace sized by pg_eps_workspace_bytes_capture(..., capture) */
+int pg_hamming_eps_count_capture(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                                 const uint32_t* stream_tab, int64_t stream_rows,
+                                 int planes, int words, const uint32_t* lut_host, int lut_words,
+                                 int capture, int64_t* counts,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int pg_hamming_eps_fill_capture(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                                const uint32_t* stream_tab, int64_t stream_rows,
+                                int planes, int words, const uint32_t* lut_host, int lut_words,
+                                int capture, const int64_t* indptr, int weight, int64_t* out_idx, void* out_w,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* materialised distance tile (hamming.py:34-38): out[m*ld + n] for query rows
  * m in [q0,q0+qrows) of `queries` against all `data_rows` rows of `data`;

@@ -40,6 +40,7 @@ SIGNATURES = {
     "pg_pack_chars": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i, _i, _vp]),
     "pg_sweep_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),
     "pg_eps_workspace_bytes": (_sz, [_i64, _i64, _i]),
+    "pg_eps_workspace_bytes_capture": (_sz, [_i64, _i64, _i, _i]),
     "pg_eps_count_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "pg_hamming_knn": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "pg_knn_sym_workspace_bytes": (_sz, [_i64, _i]),
@@ -54,6 +55,9 @@ SIGNATURES = {
     "pg_knn_sym_plan": (_i, [_i64, _i, _i, _i64, _i, _i, _i, _i, _vp, _i64, _pi64]),
     "pg_hamming_eps_count": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pg_hamming_eps_fill": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "pg_hamming_eps_count_capture": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "pg_hamming_eps_fill_capture": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _sz,
+                                         _vp]),
     "pg_hamming_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i64, _vp]),
     "pg_hamming_flags_tile": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _vp]),
     "pg_flags_or_rows": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),

@@ -55,7 +55,7 @@ static int tile_cols_for(int words) { return words > 16 ? 32 : 512 / words; }   
 // c_ins ~ 18 = a warp-cooperative insertion stalls its 32 rows for about 0.6 stream rows
 // (measured: profiles/r1_ncu_notes.md).  k1 = 0 (count / fill / tile) only balances the waves.
 static Geometry make_geometry(long long rows, long long stream_rows, int words, int rows_per_cta = kConsumers,
-                              int k1 = 17) {
+                              int k1 = 17, long long split_limit = 64) {
   Geometry g;
   g.tile_cols = tile_cols_for(words);
   g.n_rowblocks = static_cast<int>(ceil_div(rows, rows_per_cta));
@@ -63,6 +63,7 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
   const double resident = static_cast<double>(num_sms()) * 2;
   long long max_splits = g.n_tiles / 8;      // keep >= 8 ring tiles per item
   if (max_splits > 64) max_splits = 64;
+  if (max_splits > split_limit) max_splits = split_limit;
   if (max_splits < 1) max_splits = 1;
   long long best_s = 1;
   double best_cost = 1e300;
@@ -84,6 +85,7 @@ static Geometry make_geometry(long long rows, long long stream_rows, int words, 
     best_s = std::atoll(ev);
     if (best_s < 1) best_s = 1;
     if (best_s > g.n_tiles) best_s = g.n_tiles;
+    if (best_s > split_limit) best_s = split_limit;
   }
   g.tiles_per_split = static_cast<int>(ceil_div(g.n_tiles, best_s));
   g.n_splits = static_cast<int>(ceil_div(g.n_tiles, g.tiles_per_split));
@@ -226,14 +228,14 @@ __global__ void knn_finalize_kernel(const unsigned long long* __restrict__ part,
 }
 
 __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, int n_splits, long long rows,
-                                  long long* __restrict__ counts, uint8_t* __restrict__ over_flag) {
+                                  long long* __restrict__ counts, uint8_t* __restrict__ over_flag, int capture_cap) {
   const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (r >= rows) return;
   long long s = 0;
   bool over = false;
   for (int i = 0; i < n_splits; ++i) {
     const long long c = split_counts[static_cast<size_t>(i) * rows + r];
-    over |= c > kEpsCapture;
+    over |= c > capture_cap;
     s += c;
   }
   counts[r] = s;
@@ -241,36 +243,78 @@ __global__ void sum_splits_kernel(const long long* __restrict__ split_counts, in
 }
 
 // Fill from the captures of the count pass: row r's edges are the splits' captured hits in
-// split order, i.e. ascending stream index.  Rows with an overflowed capture are left to the
-// fill sweep over the overflow rows.
-__global__ void eps_from_capture_kernel(const unsigned long long* __restrict__ capture,
-                                        const long long* __restrict__ split_counts, int n_splits, long long rows,
-                                        const uint8_t* __restrict__ over_flag, const long long* __restrict__ indptr,
-                                        int weight, long long* __restrict__ out_idx, void* out_w) {
-  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (r >= rows || over_flag[r]) return;
-  long long at = indptr[r];
-  for (int s = 0; s < n_splits; ++s) {
-    const int c = static_cast<int>(split_counts[static_cast<size_t>(s) * rows + r]);
-    const unsigned long long* src = capture + (static_cast<size_t>(s) * rows + r) * kEpsCapture;
-    for (int j = 0; j < c; ++j) {
-      const unsigned long long e = src[j];
-      out_idx[at] = static_cast<long long>(e & 0xffffffffull);
-      write_weight(out_w, at, static_cast<int>(e >> 32), weight);
-      ++at;
+// split order, i.e. ascending stream index.  One warp per row, lanes along the row's hits (coalesced
+// on both sides: dense graphs keep thousands of hits per row).  Rows with an overflowed capture are
+// left to the fill sweep over the overflow rows.
+__global__ void __launch_bounds__(256) eps_from_capture_kernel(const unsigned long long* __restrict__ capture,
+                                                               const long long* __restrict__ split_counts,
+                                                               int n_splits, long long rows, int capture_cap,
+                                                               const uint8_t* __restrict__ over_flag,
+                                                               const long long* __restrict__ indptr, int weight,
+                                                               long long* __restrict__ out_idx, void* out_w) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long r = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    if (over_flag[r]) continue;
+    long long at = indptr[r];
+    for (int s = 0; s < n_splits; ++s) {
+      const int c = static_cast<int>(split_counts[static_cast<size_t>(s) * rows + r]);
+      const unsigned long long* src = capture + (static_cast<size_t>(s) * rows + r) * capture_cap;
+      for (int j = lane; j < c; j += 32) {
+        const unsigned long long e = __ldcs(src + j);
+        out_idx[at + j] = static_cast<long long>(e & 0xffffffffull);
+        write_weight(out_w, at + j, static_cast<int>(e >> 32), weight);
+      }
+      at += c;
     }
   }
 }
 
-// eps workspace: [split counts: n_splits*rows int64][header 256 B: number of overflow rows]
-//                [overflow flag per row, padded][overflow row list: rows int64][captures: n_splits*rows*kEpsCapture u64]
+// eps workspace: [split counts: n_splits*rows int64][header 256 B: number of overflow rows, capture slots in use]
+//                [overflow flag per row, padded][overflow row list: rows int64][captures: n_splits*rows*cap u64]
+// cap = kEpsCapture (128) by default: enough to finish sparse graphs without a second sweep.  A caller that
+// knows the graph is dense (degree sample) sizes the workspace with pg_eps_workspace_bytes_capture for the
+// largest degree it expects; the count pass keeps as many hits per (split,row) as the workspace holds.
 static size_t eps_counts_bytes(const Geometry& g, long long rows) { return static_cast<size_t>(g.n_splits) * rows * 8; }
-static size_t eps_capture_bytes(const Geometry& g, long long rows) {
-  return static_cast<size_t>(g.n_splits) * rows * kEpsCapture * 8;
+static size_t eps_capture_bytes(const Geometry& g, long long rows, int cap = kEpsCapture) {
+  return static_cast<size_t>(g.n_splits) * rows * static_cast<size_t>(cap) * 8;
 }
-constexpr size_t kEpsCaptureLimit = 8ull << 30;   // do not spend more than 8 GiB on captures
 static size_t eps_flag_bytes(long long rows) { return static_cast<size_t>(round_up(rows, 256)); }
 static size_t eps_list_bytes(long long rows) { return static_cast<size_t>(rows) * 8; }
+constexpr int kEpsCaptureMax = 1 << 20;
+constexpr size_t kEpsCaptureLimit = 8ull << 30;   // do not spend more than 8 GiB on captures
+
+// Geometry and capture slots of an epsilon count / fill pair.  capture = 0: the default geometry with
+// kEpsCapture slots per (split,row) when that fits the limit.  capture > 0 (the largest degree a
+// caller expects of a dense graph): as many slots, and no more column splits than keep the captures
+// within the limit -- every split of a row needs room for ALL of the row's hits, and the wave
+// balance that splits buy (C3: 35 splits) is worth less than the second sweep the captures save
+// (C3 eps=2, 358.7 M edges: count 15.5 + fill 16.2 ms -> count 16.2 + copy 2.1 ms).
+struct EpsPlan {
+  Geometry g;
+  int cap;          // capture slots per (split,row), 0 = no captures
+};
+static EpsPlan eps_plan(long long rows, long long stream_rows, int words, int capture) {
+  EpsPlan p;
+  p.cap = 0;
+  if (capture > 0 && rows < (1ll << 31)) {
+    const int cap = std::min(std::max(capture, kEpsCapture), kEpsCaptureMax);
+    const long long splits = static_cast<long long>(kEpsCaptureLimit / (static_cast<size_t>(rows) * cap * 8));
+    if (splits >= 1) {
+      p.g = make_geometry(rows, stream_rows, words, kConsumers, 0, splits);
+      p.cap = cap;
+      return p;
+    }
+  }
+  p.g = make_geometry(rows, stream_rows, words, kConsumers, 0);
+  if (eps_capture_bytes(p.g, rows) <= kEpsCaptureLimit && rows < (1ll << 31)) p.cap = kEpsCapture;
+  return p;
+}
+static size_t eps_plan_bytes(const EpsPlan& p, long long rows) {
+  size_t bytes = eps_counts_bytes(p.g, rows) + 256;
+  if (p.cap > 0) bytes += eps_flag_bytes(rows) + eps_list_bytes(rows) + eps_capture_bytes(p.g, rows, p.cap);
+  return bytes;
+}
 
 
 // ---- symmetric kNN sweep (pg_sweep_sym.cuh): host side ---------------------------------
@@ -657,11 +701,12 @@ size_t pg_sweep_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words
 
 size_t pg_eps_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) {
   if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
-  const Geometry g = make_geometry(own_rows, stream_rows, words, kConsumers, 0);
-  size_t bytes = eps_counts_bytes(g, own_rows) + 256;
-  if (eps_capture_bytes(g, own_rows) <= kEpsCaptureLimit && own_rows < (1ll << 31))
-    bytes += eps_flag_bytes(own_rows) + eps_list_bytes(own_rows) + eps_capture_bytes(g, own_rows);
-  return bytes;
+  return eps_plan_bytes(eps_plan(own_rows, stream_rows, words, 0), own_rows);
+}
+
+size_t pg_eps_workspace_bytes_capture(int64_t own_rows, int64_t stream_rows, int words, int capture) {
+  if (own_rows <= 0 || stream_rows <= 0 || words <= 0) return 0;
+  return eps_plan_bytes(eps_plan(own_rows, stream_rows, words, capture), own_rows);
 }
 
 size_t pg_eps_count_workspace_bytes(int64_t own_rows, int64_t stream_rows, int words) {
@@ -714,35 +759,43 @@ int pg_hamming_knn(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t 
 static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
                     const uint32_t* stream_tab, int64_t stream_rows, int planes, int words, const uint32_t* lut_host,
                     int lut_words, int64_t* counts, const int64_t* indptr, int weight, int64_t* out_idx, void* out_w,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+                    void* workspace, size_t workspace_bytes, void* stream, int capture = 0) {
   int rc = check_common(own, own_rows, row0, rows, stream_tab, stream_rows, planes, words);
   if (rc != PG_OK) return rc;
   PG_CHECK_ARG(lut_host && lut_words >= 1 && lut_words <= kMaxLutWords, "lut_words must be in [1,%d]", kMaxLutWords);
   PG_CHECK_ARG(lut_words * 32 > words * 32, "lut must cover distances 0..%d", words * 32);
   PG_CHECK_ARG(workspace, "null workspace");
-  const Geometry g = make_geometry(rows, stream_rows, words, kConsumers, 0);
+  PG_CHECK_ARG(capture >= 0, "capture must be >= 0");
+  const EpsPlan plan = eps_plan(rows, stream_rows, words, capture);
+  const Geometry g = plan.g;
   const size_t need = eps_counts_bytes(g, rows);
   PG_CHECK_ARG(workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   const size_t aux = 256 + eps_flag_bytes(rows) + eps_list_bytes(rows);
-  const bool capturing = workspace_bytes >= need + aux + eps_capture_bytes(g, rows);
+  // a counts-only workspace (pg_eps_count_workspace_bytes) keeps no captures
+  const bool fits = workspace_bytes >= eps_plan_bytes(plan, rows);
+  PG_CHECK_ARG(capture == 0 || fits, "workspace too small for capture=%d: size it with pg_eps_workspace_bytes_capture",
+               capture);
+  const bool capturing = plan.cap > 0 && fits;
+  const int capture_cap = capturing ? plan.cap : 0;
   char* wsb = static_cast<char*>(workspace);
   long long* n_over_dev = reinterpret_cast<long long*>(wsb + need);
   uint8_t* over_flag = reinterpret_cast<uint8_t*>(wsb + need + 256);
   long long* over_rows = reinterpret_cast<long long*>(wsb + need + 256 + eps_flag_bytes(rows));
-  unsigned long long* capture = reinterpret_cast<unsigned long long*>(wsb + need + aux);
+  unsigned long long* capture_buf = reinterpret_cast<unsigned long long*>(wsb + need + aux);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   SweepParams prm;
   fill_common(prm, g, own, row0, rows, stream_tab, stream_rows);
   prm.split_counts = static_cast<long long*>(workspace);
-  if (mode == MODE_COUNT && capturing) prm.capture = capture;
+  prm.capture_cap = capture_cap;
+  if (mode == MODE_COUNT && capturing) prm.capture = capture_buf;
   long long n_over = -1;     // fill: -1 = sweep every row, otherwise the number of overflow rows
   if (mode == MODE_FILL && capturing) {
     PG_CUDA(cudaMemcpyAsync(&n_over, n_over_dev, sizeof(long long), cudaMemcpyDeviceToHost, cs));
     PG_CUDA(cudaStreamSynchronize(cs));
-    const int threads = 128;
-    eps_from_capture_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, cs>>>(
-        capture, prm.split_counts, g.n_splits, rows, over_flag, reinterpret_cast<const long long*>(indptr), weight,
-        reinterpret_cast<long long*>(out_idx), out_w);
+    const long long blocks = std::min<long long>(ceil_div(rows, 8), static_cast<long long>(num_sms()) * 32);
+    eps_from_capture_kernel<<<static_cast<unsigned>(blocks), 256, 0, cs>>>(
+        capture_buf, prm.split_counts, g.n_splits, rows, capture_cap, over_flag, reinterpret_cast<const long long*>(indptr),
+        weight, reinterpret_cast<long long*>(out_idx), out_w);
     PG_LAUNCH_CHECK();
     if (n_over == 0) return PG_OK;
     // second sweep over the overflow rows only, with the count pass's split structure
@@ -766,7 +819,8 @@ static int eps_pass(int mode, const uint32_t* own, int64_t own_rows, int64_t row
   if (mode == MODE_COUNT) {
     const int threads = 256;
     sum_splits_kernel<<<static_cast<unsigned>(ceil_div(rows, threads)), threads, 0, l.stream>>>(
-        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts), capturing ? over_flag : nullptr);
+        prm.split_counts, g.n_splits, rows, reinterpret_cast<long long*>(counts), capturing ? over_flag : nullptr,
+        capture_cap);
     PG_LAUNCH_CHECK();
     if (capturing) {
       // list of the rows whose capture overflowed (they get a fill sweep of their own)
@@ -793,6 +847,25 @@ int pg_hamming_eps_count(const uint32_t* own, int64_t own_rows, int64_t row0, in
   PG_CHECK_ARG(counts, "null counts");
   return eps_pass(MODE_COUNT, own, own_rows, row0, rows, stream_tab, stream_rows, planes, words, lut_host, lut_words,
                   counts, nullptr, PG_W_I64, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int pg_hamming_eps_count_capture(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                                 const uint32_t* stream_tab, int64_t stream_rows, int planes, int words,
+                                 const uint32_t* lut_host, int lut_words, int capture, int64_t* counts, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  PG_CHECK_ARG(counts, "null counts");
+  return eps_pass(MODE_COUNT, own, own_rows, row0, rows, stream_tab, stream_rows, planes, words, lut_host, lut_words,
+                  counts, nullptr, PG_W_I64, nullptr, nullptr, workspace, workspace_bytes, stream, capture);
+}
+
+int pg_hamming_eps_fill_capture(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,
+                                const uint32_t* stream_tab, int64_t stream_rows, int planes, int words,
+                                const uint32_t* lut_host, int lut_words, int capture, const int64_t* indptr, int weight,
+                                int64_t* out_idx, void* out_w, void* workspace, size_t workspace_bytes, void* stream) {
+  PG_CHECK_ARG(indptr && out_idx && out_w, "null indptr/output");
+  PG_CHECK_ARG(weight == PG_W_I64 || weight == PG_W_SIM_F32, "fill writes int64 distances or float32 similarities");
+  return eps_pass(MODE_FILL, own, own_rows, row0, rows, stream_tab, stream_rows, planes, words, lut_host, lut_words,
+                  nullptr, indptr, weight, out_idx, out_w, workspace, workspace_bytes, stream, capture);
 }
 
 int pg_hamming_eps_fill(const uint32_t* own, int64_t own_rows, int64_t row0, int64_t rows,

@@ -30,7 +30,7 @@ constexpr int kConsumers = kConsumerWarps * 32;  // threads per CTA; each owns T
 constexpr int kSweepThreads = kConsumers;
 constexpr int kStages = 4;
 constexpr int kMaxLutWords = 64;                 // distances up to 2047
-constexpr int kEpsCapture = 128;                  // hits per (split, row) kept by the count pass
+constexpr int kEpsCapture = 128;                  // default hits per (split, row) kept by the count pass
 
 enum SweepMode { MODE_KNN = 0, MODE_COUNT = 1, MODE_FILL = 2, MODE_TILE = 3 };
 
@@ -57,7 +57,8 @@ struct SweepParams {
   int lo;                 // range test (unsigned)(d - lo) <= span when !LUT
   unsigned span;
   long long* split_counts;  // [n_splits][rows]
-  unsigned long long* capture;  // count pass: first kEpsCapture hits of every (split,row), d<<32|idx; or null
+  unsigned long long* capture;  // count pass: first capture_cap hits of every (split,row), d<<32|idx; or null
+  int capture_cap;              // slots per (split,row) of `capture` (kEpsCapture unless the caller sized the workspace for more)
   const long long* indptr;  // [rows+1]                          (fill)
   long long* out_idx;       // edges                              (fill)
   void* out_w;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
       }
       if constexpr (MODE == MODE_COUNT) {
         if (valid[i] && prm.capture != nullptr)
-          cap[i] = prm.capture + (static_cast<size_t>(split) * prm.rows_total + r[i]) * kEpsCapture;
+          cap[i] = prm.capture + (static_cast<size_t>(split) * prm.rows_total + r[i]) * prm.capture_cap;
       }
       if constexpr (MODE == MODE_FILL) {
         if (valid[i]) {
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kSweepThreads, MINB) sweep_kernel(const __grid
             else hit = static_cast<unsigned>(d[i] - lo) <= span;
             if (hit && valid[i]) {
               // sparse graphs: keep the first hits so that the fill sweep can be skipped
-              if (cap[i] != nullptr && cnt[i] < kEpsCapture)
+              if (cap[i] != nullptr && cnt[i] < prm.capture_cap)
                 cap[i][cnt[i]] = (static_cast<unsigned long long>(static_cast<unsigned>(d[i])) << 32) |
                                  static_cast<unsigned>(col0 + c);
               ++cnt[i];

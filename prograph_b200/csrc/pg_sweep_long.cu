@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_long_kernel(const __gr
     }
     if constexpr (MODE == MODE_COUNT) {
       if (valid && prm.capture != nullptr)
-        cap = prm.capture + (static_cast<size_t>(split) * prm.rows_total + r) * kEpsCapture;
+        cap = prm.capture + (static_cast<size_t>(split) * prm.rows_total + r) * prm.capture_cap;
     }
     if constexpr (MODE == MODE_FILL) {
       if (valid) {
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_long_kernel(const __gr
             else hit = static_cast<unsigned>(d - lo) <= span;
             if (hit && valid) {
               if constexpr (MODE == MODE_COUNT) {
-                if (cap != nullptr && cnt < kEpsCapture)
+                if (cap != nullptr && cnt < prm.capture_cap)
                   cap[cnt] = (static_cast<unsigned long long>(static_cast<unsigned>(d)) << 32) |
                              static_cast<unsigned>(col0 + j);
               } else {

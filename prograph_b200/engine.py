@@ -249,17 +249,20 @@ class CudaEngine:
                                             self._stream()))
         return out
 
-    def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
+    def hamming_eps(self, own, row0, rows, stream, lut, similarity=False, capture=None):
         """prograph.py:731-753 for own rows [row0,row0+rows): CSR (indptr, idx, w) of the
-        stream rows whose distance d has bit d set in `lut` (uint32 words, host)."""
+        stream rows whose distance d has bit d set in `lut` (uint32 words, host).  `capture`:
+        the largest degree the caller expects (a degree sample of a dense graph): the count pass
+        then keeps every hit and the fill pass is one copy instead of a second sweep."""
         self._check_pair(own, stream)
         lut, lut_p = _host_u32(lut)
         counts = self.empty((rows,), torch.int64)
-        nbytes = int(self.lib.pg_eps_workspace_bytes(int(rows), int(stream.rows), int(own.words)))
+        cap = int(min(capture, 1 << 20)) if capture else 0
+        nbytes = int(self.lib.pg_eps_workspace_bytes_capture(int(rows), int(stream.rows), int(own.words), cap))
         ws = self.empty((nbytes,), torch.uint8)
-        L.check(self.lib.pg_hamming_eps_count(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
-                                              stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(counts),
-                                              _ptr(ws), nbytes, self._stream()))
+        L.check(self.lib.pg_hamming_eps_count_capture(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
+                                                      stream.rows, own.planes, own.words, lut_p, len(lut), cap,
+                                                      _ptr(counts), _ptr(ws), nbytes, self._stream()))
         indptr = self.exclusive_scan(counts)
         nnz = int(indptr[-1].item())
         self.check_edge_budget(nnz)
@@ -267,9 +270,10 @@ class CudaEngine:
         idx = self.empty((nnz,), torch.int64)
         w = self.empty((nnz,), torch.float32 if similarity else torch.int64)
         if nnz:
-            L.check(self.lib.pg_hamming_eps_fill(_ptr(own.data), own.rows, int(row0), int(rows), _ptr(stream.data),
-                                                 stream.rows, own.planes, own.words, lut_p, len(lut), _ptr(indptr),
-                                                 weight, _ptr(idx), _ptr(w), _ptr(ws), nbytes, self._stream()))
+            L.check(self.lib.pg_hamming_eps_fill_capture(_ptr(own.data), own.rows, int(row0), int(rows),
+                                                         _ptr(stream.data), stream.rows, own.planes, own.words, lut_p,
+                                                         len(lut), cap, _ptr(indptr), weight, _ptr(idx), _ptr(w), _ptr(ws),
+                                                         nbytes, self._stream()))
         return indptr, idx, w
 
     def hamming_eps_degrees(self, own, row0, rows, stream, lut):
@@ -286,9 +290,11 @@ class CudaEngine:
         return counts
 
     def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
-        """Mean number of edges per row over a row sample: sizes the edge buffer of the symmetric
-        sweep and tells dense graphs apart."""
-        return float(self.hamming_eps_degrees(own, row0, rows, stream, lut).sum().item()) / rows
+        """(mean, largest) number of edges per row over a row sample: sizes the edge buffer of the
+        symmetric sweep, tells dense graphs apart and sizes their captures."""
+        deg = self.hamming_eps_degrees(own, row0, rows, stream, lut)
+        total, top = torch.stack([deg.sum(), deg.max()]).tolist()
+        return float(total) / rows, int(top)
 
     def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):
         """Symmetric epsilon sweep (pg_hamming_eps_sym): this rank's piece of the triangle of

@@ -380,8 +380,8 @@ def hamming_knn_tiles(eng, own, stream, k, similarity, row0, rows):
     return torch.cat(idxs), torch.cat(ws)
 
 
-def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows):
-    return eng.hamming_eps(own, row0, rows, stream, lut, similarity=similarity)
+def hamming_eps_device(eng, own, stream, lut, similarity, row0, rows, capture=None):
+    return eng.hamming_eps(own, row0, rows, stream, lut, similarity=similarity, capture=capture)
 
 
 SYM_EPS_MIN_ROWS = 32768    # smaller epsilon graphs: count + capture with the one-sided sweep
@@ -419,6 +419,7 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     n = packed.rows
     dev = eng.device
     sharded = world > 1 and n >= world
+    capture = None
     with phase("columns"):
         packed = informative_table(eng, packed)
     force = os.environ.get("PG_EPS_SYM")
@@ -431,14 +432,19 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
             s0, srows = _eps_sample(n)
             if sharded and srows >= 2 * world:
                 a, b = s0 + rank * srows // world, s0 + (rank + 1) * srows // world
-                total = eng.hamming_eps_degrees(packed, a, b - a, packed, lut).sum().reshape(1)
+                deg = eng.hamming_eps_degrees(packed, a, b - a, packed, lut)
+                total, top = deg.sum().reshape(1), deg.max().reshape(1)
                 torch.distributed.all_reduce(total, group=group)
-                degree = float(total.item()) / srows
+                torch.distributed.all_reduce(top, op=torch.distributed.ReduceOp.MAX, group=group)
+                degree, top_degree = float(total.item()) / srows, int(top.item())
             else:
-                degree = eng.hamming_eps_mean_degree(packed, s0, srows, packed, lut)
+                degree, top_degree = eng.hamming_eps_mean_degree(packed, s0, srows, packed, lut)
         capacity = int(1.5 * degree * n / parts) + (4 << 20)
         if (degree > SYM_EPS_MAX_DEGREE and force is None) or capacity * parts >= (1 << 31):
             use_sym = False        # dense graph, or more keys than one radix sort takes
+            # ... whose count pass keeps every hit (room for 1.25 x the largest sampled degree per row;
+            # rows beyond that get the fill sweep), so that the fill pass is one copy, not a second sweep
+            capture = int(1.25 * top_degree) + 64
     if use_sym:
         code, keys, edges, exc = _shard.OK, None, 0, None
         try:
@@ -467,7 +473,7 @@ def hamming_eps_graph(eng, packed, lut, similarity, rank, world, group):
     code, part, exc = _shard.OK, None, None
     try:
         with phase("sweep"):
-            part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows) if rows else None
+            part = hamming_eps_device(eng, packed, packed, lut, similarity, row0, rows, capture) if rows else None
     except MemoryError as e:
         code, exc = _shard.NO_MEMORY, e
     _raise_code(_shard.agree(code, world, group, dev) if sharded else code, exc)

@@ -143,7 +143,8 @@ class CheckerEngine:
         return indptr[1:] - indptr[:-1]
 
     def hamming_eps_mean_degree(self, own, row0, rows, stream, lut):
-        return float(self.hamming_eps_degrees(own, row0, rows, stream, lut).sum()) / rows
+        deg = self.hamming_eps_degrees(own, row0, rows, stream, lut)
+        return float(deg.sum()) / rows, int(deg.max())
 
     # symmetric epsilon sweep: edge keys row << 40 | column << 12 | distance (the checker's own packing)
     def hamming_eps_sym(self, table, lut, rank=0, world=1, mode=0, capacity=None):
@@ -185,8 +186,9 @@ class CheckerEngine:
                 w[r, j] = np.float32(1.0) / np.float32(1 + d) if similarity else d
         return torch.from_numpy(idx), torch.from_numpy(w)
 
-    def hamming_eps(self, own, row0, rows, stream, lut, similarity=False):
+    def hamming_eps(self, own, row0, rows, stream, lut, similarity=False, capture=None):
         self.rows_seen = (row0, rows)
+        self.captures = getattr(self, "captures", []) + [capture]
         D = O.hamming(stream.tokens, own.tokens[row0:row0 + rows])
         lut = np.asarray(lut, dtype=np.uint32)
         keep = ((lut[D >> 5] >> (D & 31).astype(np.uint32)) & 1).astype(bool)

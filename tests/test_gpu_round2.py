@@ -118,6 +118,54 @@ def test_build_graph_accepts_any_k(eng):
     assert np.array_equal(gm.idx, mi) and np.array_equal(gm.w, mw)
 
 
+# ------------------------------------------------------------------ dense epsilon graphs: captures sized from the degree sample
+@pytest.mark.parametrize("L,alphabet,eps", [(8, 3, 4), (40, 2, 18), (300, 2, 145), (600, 2, 290)])
+def test_eps_count_pass_keeps_every_hit_when_the_workspace_allows(eng, L, alphabet, eps):
+    """pg_eps_workspace_bytes_capture: with room for the largest degree the count pass keeps every hit
+    and the fill pass is a copy; with too little room the overflowing rows get the fill sweep.  Same
+    CSR as the default (128-slot) workspace and as the oracle (prograph.py:731-753)."""
+    from prograph_b200 import graph
+    rng = np.random.default_rng(L)
+    n = 3000
+    X = rng.integers(1, alphabet + 1, size=(n, L))
+    tab = eng.pack(X)
+    lut = graph.distance_lut(tab.words * 32, operator.le, eps, False)
+    ref = eng.hamming_eps(tab, 0, n, tab, lut)
+    D = O.hamming(X, X)
+    keep = (D <= eps) & (D > 0)
+    deg = keep.sum(1)
+    assert deg.max() > 400                                    # denser than the default captures
+    np.testing.assert_array_equal(np_(ref[0]), np.concatenate([[0], np.cumsum(deg)]))
+    np.testing.assert_array_equal(np_(ref[1]), np.nonzero(keep)[1])
+    for capture in (int(deg.max()), int(np.median(deg)), 130, 1 << 20):
+        got = eng.hamming_eps(tab, 0, n, tab, lut, capture=capture)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b), capture
+    sim = eng.hamming_eps(tab, 5, 1000, tab, lut, similarity=True, capture=int(deg.max()))
+    ref_sim = eng.hamming_eps(tab, 5, 1000, tab, lut, similarity=True)
+    for a, b in zip(sim, ref_sim):
+        assert torch.equal(a, b)
+
+
+def test_dense_epsilon_build_uses_the_sampled_degree(eng):
+    """build_neighbours on a table whose eps graph is dense (sampled mean degree > 384): the one-sided
+    count / fill path with captures sized from the sample, against the oracle on sampled rows."""
+    from oracle import c_oracle as CO
+    from prograph_b200 import build_neighbours
+    rng = np.random.default_rng(12)
+    n, L = 40000, 12
+    X = rng.integers(1, 4, size=(n, L)).astype(np.uint8)
+    g = build_neighbours(X, eps=4)
+    srows = np.unique(np.concatenate([[0, n - 1], rng.choice(n, size=30, replace=False)]))
+    D = CO.hamming_rows(CO.pack(X), L, srows)
+    assert np.diff(g.indptr).mean() > 384
+    for i, r in enumerate(srows):
+        cols = np.nonzero((D[i] <= 4) & (D[i] > 0))[0]
+        a, b = g.indptr[r], g.indptr[r + 1]
+        np.testing.assert_array_equal(g.idx[a:b], cols)
+        np.testing.assert_array_equal(g.w[a:b], D[i, cols])
+
+
 # ------------------------------------------------------------------ pack / masks
 @pytest.mark.parametrize("L", [1, 31, 32, 33, 56, 100, 255, 256, 257, 600])
 @pytest.mark.parametrize("alphabet", [20, 200])

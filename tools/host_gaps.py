@@ -17,7 +17,7 @@ for it in range(6):
     t0 = t(); tab = eng.pack(dev); t1 = t()
     if lut is None: lut = graph.distance_lut(tab.words*32, operator.le, 1, False)
     a = t(); free = torch.cuda.mem_get_info(); b = t()
-    deg = eng.hamming_eps_mean_degree(tab, *graph._eps_sample(160000), tab, lut); c = t()
+    deg, _ = eng.hamming_eps_mean_degree(tab, *graph._eps_sample(160000), tab, lut); c = t()
     keys, edges = eng.hamming_eps_sym(tab, lut, 0, 1, 0, capacity=int(1.5*deg*160000)+(4<<20)); d = t()
     eng.check_edge_budget(edges); e = t()
     csr = eng.edge_keys_to_csr(keys, 160000, tab.words, edges); f = t()
