@@ -766,8 +766,9 @@ def run_query_block(args, eng, rank, world, timed, cores):
 
     def run(name, fn, pairs, reps=2):
         fn()
-        ms = timed(fn, reps) / reps
-        cases.append({"name": name, "ms": ms, "gpairs_per_s": pairs / (ms * 1e-3) / 1e9})
+        each = [timed(fn, 1) for _ in range(reps)]          # every repetition on its own: shows the spread
+        ms = sum(each) / reps
+        cases.append({"name": name, "ms": ms, "gpairs_per_s": pairs / (ms * 1e-3) / 1e9, "ms_each": each})
 
     def hn():
         out["hn"] = query.nearest(lib, Q)
