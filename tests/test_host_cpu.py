@@ -358,6 +358,32 @@ def test_constant_columns_are_dropped_without_changing_the_graph(monkeypatch):
     assert graph.informative_table(eng, fresh) is fresh
 
 
+def test_dense_graph_capture_workspace_plan():
+    """pg_eps_workspace_bytes_capture (host-only arithmetic): no request or a small one = the default
+    128 slots per (split,row); a dense graph's request cuts the column range into fewer splits so that
+    the captures stay within 8 GiB; a request that one split cannot hold falls back to the default."""
+    from prograph_b200 import _lib
+    lib = _lib.load()
+    rows, words = 160_000, 1
+    default = lib.pg_eps_workspace_bytes(rows, rows, words)
+    counts_only = lib.pg_eps_count_workspace_bytes(rows, rows, words)
+    n_splits = (counts_only - 256) // (rows * 8)
+    assert n_splits >= 1 and (counts_only - 256) % (rows * 8) == 0
+    assert lib.pg_eps_workspace_bytes_capture(rows, rows, words, 0) == default
+    assert lib.pg_eps_workspace_bytes_capture(rows, rows, words, 100) == default
+    cap = 2866                                             # C3 eps=2: 1.25 x 2242 + 64
+    dense = lib.pg_eps_workspace_bytes_capture(rows, rows, words, cap)
+    capture_bytes = 8 << 30
+    splits = min(n_splits, capture_bytes // (rows * cap * 8))
+    assert 1 <= splits < n_splits
+    aux = 256 + -(-rows // 256) * 256 + rows * 8
+    sizes = {s * rows * 8 + aux + s * rows * cap * 8 for s in range(1, splits + 1)}
+    assert dense in sizes and dense - aux <= capture_bytes + splits * rows * 8
+    assert lib.pg_eps_workspace_bytes_capture(rows, rows, words, 1 << 20) == default      # 1.3 TB: not even one split
+    small = lib.pg_eps_workspace_bytes_capture(3000, 3000, 8, 1000)                       # small tables keep their splits
+    assert small > lib.pg_eps_workspace_bytes(3000, 3000, 8)
+
+
 def test_symmetric_planner_covers_the_triangle_once_in_l2_bands():
     """pg_knn_sym_plan (host-only): over all ranks the work items cover every (row block, stream tile)
     of the triangle exactly once; every CTA walks its items band by band (so that co-resident CTAs
