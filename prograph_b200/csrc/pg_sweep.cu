@@ -489,6 +489,9 @@ static SymPlan sym_plan(const SymLayout& s, long long rows, int part, int parts,
 }
 
 // item table in the workspace: [first: grid + 1 ints, padded to 16 B][items]
+// smallest kNN chunk (tiles) of the symmetric sweep: see pg_hamming_knn_sym
+static int sym_knn_chunk_floor(int words, int parts) { return (parts == 1 ? 256 : 32) * std::max(1, 8 / words); }
+
 static size_t sym_plan_bytes(const SymPlan& p) {
   return static_cast<size_t>(round_up(static_cast<int64_t>(p.first.size()) * 4, 16)) + p.items.size() * sizeof(SymItem);
 }
@@ -976,7 +979,7 @@ int pg_knn_sym_plan(int64_t rows, int planes, int words, int64_t boot_rows, int 
                    (mode == 0 || mode == 1) && boot_rows >= 0 && boot_rows % kStreamRowPad == 0,
                "bad plan arguments");
   const SymLayout lay = sym_layout(rows, words, planes);
-  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, grid, boot_rows, 32 * std::max(1, 8 / words));
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, grid, boot_rows, sym_knn_chunk_floor(words, parts));
   *n_items = static_cast<int64_t>(plan.items.size());
   PG_CHECK_ARG(sym_plan_bytes(plan) <= lay.item_bytes_max, "item table overflow (%zu items)", plan.items.size());
   if (items_host) {
@@ -1050,7 +1053,11 @@ int pg_hamming_knn_sym(const uint32_t* table, int64_t rows, int planes, int word
   // a kNN chunk starts with empty shared-memory lists and ends with a locked merge of 256 lists: on
   // small tables of narrow rows (C3: 160 000 x 20 bytes) that is as long as sweeping 32 tiles, so the
   // chunks are at least 32 * 8/W tiles there (C3 kNN 18.4 -> 16.5 ms, profiles/r4i_chunks.log)
-  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, boot_rows, 32 * std::max(1, 8 / words));
+  // On one GPU, tables below ~250 000 rows also build faster with chunks of at least 256 * 8/W tiles
+  // (70 000 rows: 12.4 -> 11.8 ms uniform, 13.7 -> 12.5 ms mutational; 131 072 rows: 36.0 -> 34.6 / 40.6 ->
+  // 37.3 ms); the bands of a multi-rank build do not (rank 7 of 8 at 1 M rows: 199.8 -> 216 ms with twice
+  // the default chunk: fewer merges mean staler row-side filters there) -- profiles/r4p_chunks.log.
+  const SymPlan plan = sym_plan(lay, rows, part, parts, mode, resident, boot_rows, sym_knn_chunk_floor(words, parts));
   sym_init_kernel<<<num_sms() * 4, 256, 0, cs>>>(prm.glist, static_cast<long long>(rows) * k1, prm.glast,
                                                  static_cast<long long>(lay.n_tiles) * lay.tile_cols, prm.glock, rows,
                                                  stats_dev, k1, boot_rows > 0 ? 1 : 0);
