@@ -764,11 +764,12 @@ def run_query_block(args, eng, rank, world, timed, cores):
     out = {}
     cases = []
 
-    def run(name, fn, pairs, reps=2):
+    def run(name, fn, pairs, reps=3):
         fn()
         each = [timed(fn, 1) for _ in range(reps)]          # every repetition on its own: shows the spread
-        ms = sum(each) / reps
-        cases.append({"name": name, "ms": ms, "gpairs_per_s": pairs / (ms * 1e-3) / 1e9, "ms_each": each})
+        ms = sorted(each)[len(each) // 2]                   # median: one slow first repetition does not decide
+        cases.append({"name": name, "ms": ms, "gpairs_per_s": pairs / (ms * 1e-3) / 1e9, "ms_each": each,
+                      "ms_is": "median of ms_each"})
 
     def hn():
         out["hn"] = query.nearest(lib, Q)
