@@ -31,6 +31,37 @@ def test_library_exports_every_declared_symbol():
     assert lib.pg_packed_bytes(1000, 256, 5) == 1024 * 5 * 8 * 4
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every declaration of include/prograph_b200.h against the ctypes table of prograph_b200/_lib.py:
+    same number of parameters, and the same class of type in every position (pointer / 32-bit int /
+    64-bit int / size_t / double) -- a drifted binding would corrupt arguments silently."""
+    import ctypes as C
+    from prograph_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "prograph_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = re.findall(r"\b(?:int|size_t|int64_t|const char\*)\s+(pg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(decls) == len(_lib.SIGNATURES)
+
+    def kind_of_c(param):
+        param = param.strip()
+        if "*" in param:
+            return "ptr"
+        base = param.rsplit(" ", 1)[0].replace("const", "").strip() if " " in param else param
+        return {"int": "i32", "int64_t": "i64", "size_t": "size", "double": "f64", "uint64_t": "i64"}[base]
+
+    def kind_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer):
+            return "ptr"
+        return {C.c_int: "i32", C.c_int64: "i64", C.c_size_t: "size", C.c_double: "f64"}[t]
+
+    for name, params in decls:
+        params = [q for q in params.split(",") if q.strip() and q.strip() != "void"]
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (q, t) in enumerate(zip(params, argtypes)):
+            assert kind_of_c(q) == kind_of_ctypes(t), (name, i, q.strip(), t)
+
+
 def test_argument_errors_map_to_reference_exceptions():
     """Bad arguments are rejected on the host side of the ABI, before any launch."""
     from prograph_b200 import _lib
